@@ -1,0 +1,16 @@
+"""gnuspeech_b200 -- B200-native Tube Resonance Model (TRM) synthesis: the hot path of grrrr/GnuSpeech's
+Tube.framework as hand-written sm_100a CUDA kernels behind the reference's TRM interface.
+
+    from gnuspeech_b200 import TRMDataList, TRMTubeModel, TRMInputParameters, TRMBatch
+
+The native libraries (gnuspeech_b200/lib/libtrm.so, libtrm_cuda.so) must be built first
+(`python -m gnuspeech_b200.build`); there is no CPU fallback.
+"""
+from ._native import (TRM_PRECISION_FP32, TRM_PRECISION_FP64, TRM_STAGE_PCM, TRM_STAGE_SRC, TRM_STAGE_TUBE,  # noqa: F401
+                      TRMError)
+from .api import (PinnedArray, TRMBatch, TRMDataList, TRMInputParameters, TRMParameters, TRMResident,  # noqa: F401
+                  TRMSynthesizer, TRMTubeModel, derive)
+
+__all__ = ["TRMBatch", "TRMDataList", "TRMInputParameters", "TRMParameters", "TRMResident", "TRMSynthesizer",
+           "TRMTubeModel", "TRMError", "PinnedArray", "derive", "TRM_PRECISION_FP64", "TRM_PRECISION_FP32",
+           "TRM_STAGE_TUBE", "TRM_STAGE_SRC", "TRM_STAGE_PCM"]

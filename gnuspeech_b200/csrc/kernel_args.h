@@ -1,0 +1,66 @@
+// kernel_args.h -- plain structs and tile constants shared by the kernels (device) and the shim (host).
+#pragma once
+
+#include <stdint.h>
+
+#include "trm_cuda.h"
+
+namespace trm {
+
+constexpr int TB = 16;           // samples per block == lanes per utterance
+constexpr int FIR_TAPS = 49;     // TRMFIRFilter.h:7-9 fixed design -> 49 taps (checked on the host)
+constexpr int FIR_HIST = 24;     // (FIR_TAPS-1)/2 previous even / odd oscillator values
+constexpr int FRAME_CHUNK = 4;   // control frames per bulk copy
+constexpr int WARPS_PER_CTA = 2;
+constexpr int UTT_PER_CTA = WARPS_PER_CTA * 2;
+
+constexpr int SRC_THREADS = 256;
+constexpr int SRC_TILE = 1024;       // outputs per tile
+constexpr int SRC_XW = 4096;         // staged input window (elements)
+constexpr int SRC_ZC = 13;           // zero crossings -> 13 taps per wing when up-sampling
+constexpr int PCM_THREADS = 256;
+constexpr int PCM_PER_THREAD = 8;
+
+struct TubeArgs {
+    const trm_cuda_utterance *desc;
+    const int *order;            // slot -> utterance (longest first), may be null
+    int n_utt;
+    const double *frames;        // [frame][16]
+    void *tube;                  // Real[...]
+    const double *wavetables;    // [voice][512]
+    uint64_t noise_k0;
+};
+
+template <typename R> struct HD { R h, dh; };
+
+struct SrcArgs {
+    const trm_cuda_utterance *desc;
+    int n_utt;
+    const void *tube;                // Real[]
+    void *out;                       // Real[]
+    unsigned long long *maxbits;     // [n_utt] bit pattern of the running max |y| as double
+    const void *table;               // HD<Real>[3328]
+    const long long *tile_base;      // [n_utt+1] prefix sum of tiles per utterance
+    long long total_tiles;
+};
+
+struct PcmArgs {
+    const trm_cuda_utterance *desc;
+    int n_utt;
+    const void *out;                 // Real[]
+    const unsigned long long *maxbits;
+    int16_t *pcm;
+};
+
+struct KernelInfo {
+    int tube_smem_bytes;
+    int tube_threads;
+    int tube_utt_per_cta;
+    int src_smem_bytes;
+    int src_threads;
+    int src_ctas_per_sm;
+    int tube_ctas_per_sm;
+    int tube_regs, src_regs, pcm_regs;
+};
+
+}  // namespace trm

@@ -1,0 +1,97 @@
+// launch.cuh -- per-precision launch wrappers.  Each kernels_*.cu translation unit instantiates these
+// for one Real type (the FP64 conformance TU is compiled with -fmad=false, the FP32 TU with FMA
+// contraction) and exports them with C linkage for trm_cuda.cu.
+#pragma once
+
+#include "src_kernel.cuh"
+#include "tube_kernel.cuh"
+
+namespace trm {
+
+template <typename R> static int configure_kernels(KernelInfo *info)
+{
+    const int tube_smem = UTT_PER_CTA * (int)sizeof(UttSmem<R>);
+    const int src_smem = TRM_SRC_FILTER_LEN * (int)sizeof(HD<R>) + SRC_XW * (int)sizeof(R);
+    cudaError_t e;
+    e = cudaFuncSetAttribute(tube_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, tube_smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(tube_kernel<R>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(src_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, src_smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(src_kernel<R>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return (int)e;
+    if (info) {
+        info->tube_smem_bytes = tube_smem;
+        info->tube_threads = WARPS_PER_CTA * 32;
+        info->tube_utt_per_cta = UTT_PER_CTA;
+        info->src_smem_bytes = src_smem;
+        info->src_threads = SRC_THREADS;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&info->src_ctas_per_sm, src_kernel<R>, SRC_THREADS, src_smem);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&info->tube_ctas_per_sm, tube_kernel<R>, WARPS_PER_CTA * 32, tube_smem);
+        if (e != cudaSuccess) return (int)e;
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, tube_kernel<R>) == cudaSuccess) info->tube_regs = fa.numRegs;
+        if (cudaFuncGetAttributes(&fa, src_kernel<R>) == cudaSuccess) info->src_regs = fa.numRegs;
+        if (cudaFuncGetAttributes(&fa, pcm_kernel<R>) == cudaSuccess) info->pcm_regs = fa.numRegs;
+    }
+    return 0;
+}
+
+static int upload_constants(const double *fir, int taps, const unsigned long long *noise_pow)
+{
+    if (taps != FIR_TAPS) return -1;
+    float firf[FIR_TAPS];
+    for (int i = 0; i < FIR_TAPS; ++i) firf[i] = (float)fir[i];
+    cudaError_t e = cudaMemcpyToSymbol(c_fir_d, fir, sizeof(double) * FIR_TAPS);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemcpyToSymbol(c_fir_f, firf, sizeof(float) * FIR_TAPS);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemcpyToSymbol(c_noise_pow, noise_pow, sizeof(unsigned long long) * (TRM_NOISE_JUMP + 1));
+    return (int)e;
+}
+
+template <typename R> static int launch_tube(const TubeArgs &a, cudaStream_t s)
+{
+    if (a.n_utt <= 0) return 0;
+    const int grid = (a.n_utt + UTT_PER_CTA - 1) / UTT_PER_CTA;
+    tube_kernel<R><<<grid, WARPS_PER_CTA * 32, UTT_PER_CTA * sizeof(UttSmem<R>), s>>>(a);
+    return (int)cudaGetLastError();
+}
+
+template <typename R> static int launch_src(const SrcArgs &a, int grid, cudaStream_t s)
+{
+    if (a.total_tiles <= 0) return 0;
+    if ((long long)grid > a.total_tiles) grid = (int)a.total_tiles;
+    const size_t smem = TRM_SRC_FILTER_LEN * sizeof(HD<R>) + SRC_XW * sizeof(R);
+    src_kernel<R><<<grid, SRC_THREADS, smem, s>>>(a);
+    return (int)cudaGetLastError();
+}
+
+template <typename R> static int launch_pcm(const PcmArgs &a, long long max_n_out, cudaStream_t s)
+{
+    if (a.n_utt <= 0 || max_n_out <= 0) return 0;
+    const long long per_cta = (long long)PCM_THREADS * PCM_PER_THREAD;
+    dim3 grid((unsigned)((max_n_out + per_cta - 1) / per_cta), (unsigned)a.n_utt);
+    pcm_kernel<R><<<grid, PCM_THREADS, 0, s>>>(a);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace trm
+
+#define TRM_DEFINE_LAUNCHERS(R, SUF)                                                                              \
+    extern "C" int trm_k_configure_##SUF(trm::KernelInfo *info) { return trm::configure_kernels<R>(info); }      \
+    extern "C" int trm_k_upload_##SUF(const double *fir, int taps, const unsigned long long *np)                 \
+    {                                                                                                             \
+        return trm::upload_constants(fir, taps, np);                                                              \
+    }                                                                                                             \
+    extern "C" int trm_k_tube_##SUF(const trm::TubeArgs *a, cudaStream_t s) { return trm::launch_tube<R>(*a, s); } \
+    extern "C" int trm_k_src_##SUF(const trm::SrcArgs *a, int grid, cudaStream_t s)                               \
+    {                                                                                                             \
+        return trm::launch_src<R>(*a, grid, s);                                                                   \
+    }                                                                                                             \
+    extern "C" int trm_k_pcm_##SUF(const trm::PcmArgs *a, long long max_n_out, cudaStream_t s)                    \
+    {                                                                                                             \
+        return trm::launch_pcm<R>(*a, max_n_out, s);                                                              \
+    }

@@ -1,0 +1,577 @@
+// trm_cuda.cu -- C-ABI shim (include/trm_cuda.h): device memory, streams, chunked copy/compute
+// pipeline and kernel launches.  No torch types, no C++ in the signatures.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "kernel_args.h"
+#include "trm_cuda.h"
+
+extern "C" {
+int trm_k_configure_f64(trm::KernelInfo *);
+int trm_k_configure_f32(trm::KernelInfo *);
+int trm_k_upload_f64(const double *, int, const unsigned long long *);
+int trm_k_upload_f32(const double *, int, const unsigned long long *);
+int trm_k_tube_f64(const trm::TubeArgs *, cudaStream_t);
+int trm_k_tube_f32(const trm::TubeArgs *, cudaStream_t);
+int trm_k_src_f64(const trm::SrcArgs *, int, cudaStream_t);
+int trm_k_src_f32(const trm::SrcArgs *, int, cudaStream_t);
+int trm_k_pcm_f64(const trm::PcmArgs *, long long, cudaStream_t);
+int trm_k_pcm_f32(const trm::PcmArgs *, long long, cudaStream_t);
+}
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char *what, cudaError_t e)
+{
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s (%d)", what, cudaGetErrorString(e), (int)e);
+    g_err = buf;
+    return -5;   // TRM_ERR_CUDA
+}
+int fail_msg(const char *what)
+{
+    g_err = what;
+    return -5;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) return fail(#call, _e);                                             \
+    } while (0)
+
+constexpr int N_SLOTS = 3;   // chunks in flight (copy-in / compute / copy-out)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Arena {
+    unsigned char *base = nullptr;
+    size_t cap = 0, used = 0;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (base) cudaFree(base);
+        base = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc((void **)&base, bytes);
+        if (e != cudaSuccess) return fail("cudaMalloc(arena)", e);
+        cap = bytes;
+        return 0;
+    }
+    void reset() { used = 0; }
+    void *take(size_t bytes)
+    {
+        size_t off = align_up(used, 256);
+        used = off + bytes;
+        return base + off;
+    }
+    void release()
+    {
+        if (base) cudaFree(base);
+        base = nullptr;
+        cap = used = 0;
+    }
+};
+
+struct HostStage {
+    unsigned char *base = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (base) cudaFreeHost(base);
+        base = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMallocHost((void **)&base, bytes);
+        if (e != cudaSuccess) return fail("cudaMallocHost(stage)", e);
+        cap = bytes;
+        return 0;
+    }
+    void release()
+    {
+        if (base) cudaFreeHost(base);
+        base = nullptr;
+        cap = 0;
+    }
+};
+
+// Everything one chunk needs on the device, carved from an arena.
+struct DeviceChunk {
+    int n = 0;
+    trm_cuda_utterance *desc = nullptr;
+    int *order = nullptr;
+    long long *tile_base = nullptr;
+    unsigned long long *maxbits = nullptr;
+    double *frames = nullptr;
+    void *tube = nullptr, *out = nullptr;
+    int16_t *pcm = nullptr;
+    long long total_tiles = 0, max_n_out = 0;
+    size_t tube_elems = 0, out_elems = 0, pcm_elems = 0, frame_rows = 0;
+};
+
+// Host-side plan of one chunk: rebased descriptors + where its spans live in the caller's arrays.
+struct ChunkPlan {
+    int u0 = 0, u1 = 0;
+    std::vector<trm_cuda_utterance> desc;   // rebased to chunk-local offsets
+    std::vector<int> order;
+    std::vector<long long> tile_base;
+    bool frames_dense = true;
+    long long frames_lo = 0;                // host frame index of the span start (dense case)
+    size_t frame_rows = 0;
+    long long tube_lo = 0, out_lo = 0, pcm_lo = 0;   // host element offsets of the spans
+    size_t tube_elems = 0, out_elems = 0, pcm_elems = 0;
+    long long total_tiles = 0, max_n_out = 0;
+    size_t arena_bytes(size_t esz, bool want_pcm) const
+    {
+        size_t n = desc.size(), b = 0;
+        auto add = [&](size_t x) { b = align_up(b, 256) + x; };
+        add(n * sizeof(trm_cuda_utterance));
+        add(n * sizeof(int));
+        add((n + 1) * sizeof(long long));
+        add(n * sizeof(unsigned long long));
+        add(frame_rows * 128);
+        add(tube_elems * esz);
+        add(out_elems * esz);
+        if (want_pcm) add(pcm_elems * sizeof(int16_t));
+        return b + 256;
+    }
+    size_t stage_bytes() const
+    {
+        size_t n = desc.size();
+        return align_up(n * sizeof(trm_cuda_utterance), 256) + align_up(n * sizeof(int), 256) +
+               align_up((n + 1) * sizeof(long long), 256) + align_up(n * sizeof(unsigned long long), 256);
+    }
+};
+
+}  // namespace
+
+struct trm_cuda_ctx {
+    int device = 0;
+    int sm_count = 0;
+    double *d_wavetables = nullptr;
+    int wt_capacity = 0;
+    void *d_tab_f64 = nullptr, *d_tab_f32 = nullptr;
+    uint64_t noise_k0 = 0;
+    trm::KernelInfo info64{}, info32{};
+    cudaStream_t streams[N_SLOTS]{};
+    Arena arenas[N_SLOTS];
+    HostStage stages[N_SLOTS];
+};
+
+struct trm_cuda_resident {
+    trm_cuda_ctx *ctx = nullptr;
+    int precision = 0;
+    ChunkPlan plan;
+    Arena arena;
+    DeviceChunk dc;
+};
+
+namespace {
+
+void plan_chunk(const trm_cuda_utterance *desc, int u0, int u1, ChunkPlan &p)
+{
+    const int n = u1 - u0;
+    p.u0 = u0;
+    p.u1 = u1;
+    p.desc.assign(desc + u0, desc + u1);
+    // spans in the caller's arrays
+    long long f_lo = INT64_MAX, f_hi = 0, f_sum = 0;
+    long long t_lo = INT64_MAX, t_hi = 0, o_lo = INT64_MAX, o_hi = 0, c_lo = INT64_MAX, c_hi = 0;
+    for (const auto &d : p.desc) {
+        f_lo = std::min<long long>(f_lo, d.frame_offset);
+        f_hi = std::max<long long>(f_hi, d.frame_offset + d.n_frames);
+        f_sum += d.n_frames;
+        t_lo = std::min<long long>(t_lo, d.tube_offset);
+        t_hi = std::max<long long>(t_hi, d.tube_offset + d.n_tube);
+        o_lo = std::min<long long>(o_lo, d.out_offset);
+        o_hi = std::max<long long>(o_hi, d.out_offset + d.n_out);
+        c_lo = std::min<long long>(c_lo, d.pcm_offset);
+        c_hi = std::max<long long>(c_hi, d.pcm_offset + d.n_out * d.channels);
+    }
+    if (n == 0) { f_lo = t_lo = o_lo = c_lo = 0; }
+    p.frames_dense = (f_hi - f_lo) <= f_sum + f_sum / 2 + 64;
+    p.frames_lo = f_lo;
+    p.tube_lo = t_lo; p.out_lo = o_lo; p.pcm_lo = c_lo;
+    p.tube_elems = (size_t)align_up((size_t)(t_hi - t_lo), TRM_ALIGN_ELEMS);
+    p.out_elems = (size_t)align_up((size_t)(o_hi - o_lo), TRM_ALIGN_ELEMS);
+    p.pcm_elems = (size_t)align_up((size_t)(c_hi - c_lo), TRM_ALIGN_ELEMS);
+    long long compact = 0;
+    p.max_n_out = 0;
+    p.tile_base.assign(n + 1, 0);
+    for (int i = 0; i < n; ++i) {
+        auto &d = p.desc[i];
+        if (p.frames_dense) d.frame_offset -= f_lo;
+        else { d.frame_offset = compact; compact += d.n_frames; }
+        d.tube_offset -= t_lo;
+        d.out_offset -= o_lo;
+        d.pcm_offset -= c_lo;
+        p.max_n_out = std::max<long long>(p.max_n_out, d.n_out);
+        p.tile_base[i + 1] = p.tile_base[i] + (d.n_out + trm::SRC_TILE - 1) / trm::SRC_TILE;
+    }
+    p.total_tiles = p.tile_base[n];
+    p.frame_rows = (size_t)(p.frames_dense ? (f_hi - f_lo) : compact);
+    // longest utterances first, so the two utterances of a warp (and the warps of a CTA) finish together
+    p.order.resize(n);
+    std::iota(p.order.begin(), p.order.end(), 0);
+    std::stable_sort(p.order.begin(), p.order.end(),
+                     [&](int a, int b) { return p.desc[a].n_tube > p.desc[b].n_tube; });
+}
+
+void carve(Arena &a, const ChunkPlan &p, size_t esz, bool want_pcm, DeviceChunk &dc)
+{
+    const size_t n = p.desc.size();
+    a.reset();
+    dc.n = (int)n;
+    dc.desc = (trm_cuda_utterance *)a.take(n * sizeof(trm_cuda_utterance));
+    dc.order = (int *)a.take(n * sizeof(int));
+    dc.tile_base = (long long *)a.take((n + 1) * sizeof(long long));
+    dc.maxbits = (unsigned long long *)a.take(n * sizeof(unsigned long long));
+    dc.frames = (double *)a.take(p.frame_rows * 128);
+    dc.tube = a.take(p.tube_elems * esz);
+    dc.out = a.take(p.out_elems * esz);
+    dc.pcm = want_pcm ? (int16_t *)a.take(p.pcm_elems * sizeof(int16_t)) : nullptr;
+    dc.total_tiles = p.total_tiles;
+    dc.max_n_out = p.max_n_out;
+    dc.tube_elems = p.tube_elems; dc.out_elems = p.out_elems; dc.pcm_elems = p.pcm_elems; dc.frame_rows = p.frame_rows;
+}
+
+// small tables (descriptors, order, tile prefix) -> device, through pinned staging when given
+int upload_plan(const ChunkPlan &p, const DeviceChunk &dc, unsigned char *stage, cudaStream_t s)
+{
+    const size_t n = p.desc.size();
+    if (n == 0) return 0;
+    const void *src_desc = p.desc.data(), *src_order = p.order.data(), *src_tb = p.tile_base.data();
+    if (stage) {
+        unsigned char *q = stage;
+        memcpy(q, p.desc.data(), n * sizeof(trm_cuda_utterance)); src_desc = q; q += align_up(n * sizeof(trm_cuda_utterance), 256);
+        memcpy(q, p.order.data(), n * sizeof(int)); src_order = q; q += align_up(n * sizeof(int), 256);
+        memcpy(q, p.tile_base.data(), (n + 1) * sizeof(long long)); src_tb = q;
+    }
+    CK(cudaMemcpyAsync(dc.desc, src_desc, n * sizeof(trm_cuda_utterance), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dc.order, src_order, n * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dc.tile_base, src_tb, (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, s));
+    return 0;
+}
+
+int upload_frames(const ChunkPlan &p, const DeviceChunk &dc, const trm_cuda_utterance *desc_global,
+                  const double *frames_host, cudaStream_t s)
+{
+    if (p.frame_rows == 0) return 0;
+    if (p.frames_dense) {
+        CK(cudaMemcpyAsync(dc.frames, frames_host + (size_t)p.frames_lo * 16, p.frame_rows * 128, cudaMemcpyHostToDevice, s));
+    } else {
+        for (size_t i = 0; i < p.desc.size(); ++i) {
+            const auto &g = desc_global[p.u0 + i];
+            CK(cudaMemcpyAsync(dc.frames + (size_t)p.desc[i].frame_offset * 16, frames_host + (size_t)g.frame_offset * 16,
+                               (size_t)g.n_frames * 128, cudaMemcpyHostToDevice, s));
+        }
+    }
+    return 0;
+}
+
+int launch_stage(trm_cuda_ctx *ctx, int precision, int stage, const DeviceChunk &dc, cudaStream_t s)
+{
+    const bool f64 = precision == 0;
+    int rc = 0;
+    if (stage == TRM_STAGE_TUBE) {
+        trm::TubeArgs a{};
+        a.desc = dc.desc; a.order = dc.order; a.n_utt = dc.n; a.frames = dc.frames; a.tube = dc.tube;
+        a.wavetables = ctx->d_wavetables; a.noise_k0 = ctx->noise_k0;
+        rc = f64 ? trm_k_tube_f64(&a, s) : trm_k_tube_f32(&a, s);
+    } else if (stage == TRM_STAGE_SRC) {
+        CK(cudaMemsetAsync(dc.maxbits, 0, (size_t)dc.n * sizeof(unsigned long long), s));
+        trm::SrcArgs a{};
+        a.desc = dc.desc; a.n_utt = dc.n; a.tube = dc.tube; a.out = dc.out; a.maxbits = dc.maxbits;
+        a.table = f64 ? ctx->d_tab_f64 : ctx->d_tab_f32; a.tile_base = dc.tile_base; a.total_tiles = dc.total_tiles;
+        const trm::KernelInfo &ki = f64 ? ctx->info64 : ctx->info32;
+        const int grid = ctx->sm_count * std::max(1, ki.src_ctas_per_sm);
+        rc = f64 ? trm_k_src_f64(&a, grid, s) : trm_k_src_f32(&a, grid, s);
+    } else if (stage == TRM_STAGE_PCM) {
+        if (!dc.pcm) return 0;
+        trm::PcmArgs a{};
+        a.desc = dc.desc; a.n_utt = dc.n; a.out = dc.out; a.maxbits = dc.maxbits; a.pcm = dc.pcm;
+        rc = f64 ? trm_k_pcm_f64(&a, dc.max_n_out, s) : trm_k_pcm_f32(&a, dc.max_n_out, s);
+    }
+    if (rc != 0) return fail("kernel launch", (cudaError_t)rc);
+    return 0;
+}
+
+int chunk_utterances(int n, const trm_cuda_utterance *desc, size_t esz)
+{
+    // Chunk size: enough utterances to fill the GPU (2 per warp), bounded by scratch memory.
+    const char *env = getenv("TRM_CHUNK_UTTERANCES");
+    if (env && atoi(env) > 0) return atoi(env);
+    size_t per_utt = 0;
+    const int probe = std::min(n, 64);
+    for (int i = 0; i < probe; ++i)
+        per_utt += (size_t)desc[i].n_frames * 128 + ((size_t)desc[i].n_tube + (size_t)desc[i].n_out) * esz +
+                   (size_t)desc[i].n_out * 2 * desc[i].channels;
+    per_utt = per_utt / std::max(probe, 1) + 1;
+    const size_t budget = (size_t)16 << 30;                     // per in-flight chunk
+    long long by_mem = (long long)(budget / per_utt);
+    long long want = 2048;                                      // ~7 warps per SM per chunk
+    if (n <= 1536) want = n;
+    long long c = std::max<long long>(1, std::min<long long>(std::min<long long>(want, by_mem), n));
+    const long long n_chunks = (n + c - 1) / c;                 // balance the chunks
+    return (int)((n + n_chunks - 1) / n_chunks);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *trm_cuda_last_error(void) { return g_err.c_str(); }
+
+int trm_cuda_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { fail("cudaGetDeviceCount", e); return 0; }
+    return n;
+}
+
+void *trm_cuda_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    cudaError_t e = cudaMallocHost(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) { fail("cudaMallocHost", e); return nullptr; }
+    return p;
+}
+
+void trm_cuda_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int trm_cuda_stage_launches(int stage) { return (stage >= 0 && stage < TRM_STAGE_COUNT) ? 1 : 0; }
+
+int trm_cuda_ctx_create(int device, const trm_cuda_tables *t, trm_cuda_ctx **out)
+{
+    *out = nullptr;
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail_msg("trm_cuda_ctx_create: no such CUDA device");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail_msg("trm_cuda_ctx_create: kernels are built for sm_100a only");
+    trm_cuda_ctx *c = new trm_cuda_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->noise_k0 = t->noise_k0;
+    int rc;
+    if ((rc = trm_k_upload_f64(t->fir_coef, t->fir_taps, (const unsigned long long *)t->noise_pow)) != 0 ||
+        (rc = trm_k_upload_f32(t->fir_coef, t->fir_taps, (const unsigned long long *)t->noise_pow)) != 0) {
+        delete c;
+        return rc < 0 ? fail_msg("FIR design is not the 49-tap filter the kernels are built for") : fail("constant upload", (cudaError_t)rc);
+    }
+    if ((rc = trm_k_configure_f64(&c->info64)) != 0 || (rc = trm_k_configure_f32(&c->info32)) != 0) {
+        delete c;
+        return fail("kernel configuration", (cudaError_t)rc);
+    }
+    // interleaved (h, deltaH) tables in both precisions
+    {
+        std::vector<trm::HD<double>> td(TRM_SRC_FILTER_LEN);
+        std::vector<trm::HD<float>> tf(TRM_SRC_FILTER_LEN);
+        for (int i = 0; i < TRM_SRC_FILTER_LEN; ++i) {
+            td[i].h = t->src_h[i]; td[i].dh = t->src_dh[i];
+            tf[i].h = (float)t->src_h[i]; tf[i].dh = (float)t->src_dh[i];
+        }
+        CK(cudaMalloc(&c->d_tab_f64, td.size() * sizeof(td[0])));
+        CK(cudaMalloc(&c->d_tab_f32, tf.size() * sizeof(tf[0])));
+        CK(cudaMemcpy(c->d_tab_f64, td.data(), td.size() * sizeof(td[0]), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_tab_f32, tf.data(), tf.size() * sizeof(tf[0]), cudaMemcpyHostToDevice));
+    }
+    for (auto &s : c->streams) CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *out = c;
+    return 0;
+}
+
+int trm_cuda_set_wavetables(trm_cuda_ctx *c, const double *tables, int n_voices)
+{
+    if (n_voices <= 0) return fail_msg("trm_cuda_set_wavetables: no voices");
+    CK(cudaSetDevice(c->device));
+    CK(cudaDeviceSynchronize());
+    if (n_voices > c->wt_capacity) {
+        if (c->d_wavetables) cudaFree(c->d_wavetables);
+        c->d_wavetables = nullptr;
+        c->wt_capacity = 0;
+        CK(cudaMalloc((void **)&c->d_wavetables, (size_t)n_voices * TRM_TABLE_LENGTH * sizeof(double)));
+        c->wt_capacity = n_voices;
+    }
+    CK(cudaMemcpy(c->d_wavetables, tables, (size_t)n_voices * TRM_TABLE_LENGTH * sizeof(double), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+void trm_cuda_ctx_destroy(trm_cuda_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto &s : c->streams) if (s) cudaStreamDestroy(s);
+    for (auto &a : c->arenas) a.release();
+    for (auto &h : c->stages) h.release();
+    if (c->d_wavetables) cudaFree(c->d_wavetables);
+    if (c->d_tab_f64) cudaFree(c->d_tab_f64);
+    if (c->d_tab_f32) cudaFree(c->d_tab_f32);
+    delete c;
+}
+
+int trm_cuda_synthesize_host(trm_cuda_ctx *ctx, int precision, int n, const trm_cuda_utterance *desc,
+                             const double *frames_host, int16_t *pcm_host, void *samples_host, double *max_host,
+                             void *tube_host, int64_t *launches)
+{
+    if (launches) *launches = 0;
+    if (n <= 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    const size_t esz = precision == 0 ? sizeof(double) : sizeof(float);
+    const bool want_pcm = pcm_host != nullptr;
+    const int per_chunk = chunk_utterances(n, desc, esz);
+    const int n_chunks = (n + per_chunk - 1) / per_chunk;
+    std::vector<ChunkPlan> plans(std::min(n_chunks, N_SLOTS));
+    std::vector<int> slot_chunk(N_SLOTS, -1);
+    int64_t n_launch = 0;
+
+    auto finish_slot = [&](int slot) -> int {
+        // wait for the slot's stream, then hand the per-utterance maxima to the caller
+        CK(cudaStreamSynchronize(ctx->streams[slot]));
+        const int ci = slot_chunk[slot];
+        if (ci >= 0 && max_host) {
+            const ChunkPlan &p = plans[slot];
+            const unsigned long long *mb =
+                (const unsigned long long *)(ctx->stages[slot].base + p.stage_bytes() - align_up(p.desc.size() * sizeof(unsigned long long), 256));
+            for (size_t i = 0; i < p.desc.size(); ++i) {
+                double v;
+                memcpy(&v, &mb[i], sizeof v);
+                max_host[p.u0 + i] = v;
+            }
+        }
+        slot_chunk[slot] = -1;
+        return 0;
+    };
+
+    for (int ci = 0; ci < n_chunks; ++ci) {
+        const int slot = ci % N_SLOTS;
+        int rc;
+        if (slot_chunk[slot] >= 0 && (rc = finish_slot(slot)) != 0) return rc;
+        ChunkPlan &p = plans[slot];
+        const int u0 = ci * per_chunk, u1 = std::min(n, u0 + per_chunk);
+        plan_chunk(desc, u0, u1, p);
+        if ((rc = ctx->arenas[slot].reserve(p.arena_bytes(esz, want_pcm))) != 0) return rc;
+        if ((rc = ctx->stages[slot].reserve(p.stage_bytes())) != 0) return rc;
+        DeviceChunk dc;
+        carve(ctx->arenas[slot], p, esz, want_pcm, dc);
+        cudaStream_t s = ctx->streams[slot];
+        if ((rc = upload_plan(p, dc, ctx->stages[slot].base, s)) != 0) return rc;
+        if ((rc = upload_frames(p, dc, desc, frames_host, s)) != 0) return rc;
+        for (int st = 0; st < TRM_STAGE_COUNT; ++st) {
+            if (st == TRM_STAGE_PCM && !want_pcm) continue;
+            if ((rc = launch_stage(ctx, precision, st, dc, s)) != 0) return rc;
+            ++n_launch;
+        }
+        if (want_pcm && p.pcm_elems) {
+            long long c_hi = 0;
+            for (const auto &d : p.desc) c_hi = std::max<long long>(c_hi, d.pcm_offset + d.n_out * d.channels);
+            CK(cudaMemcpyAsync(pcm_host + p.pcm_lo, dc.pcm, (size_t)c_hi * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
+        }
+        if (samples_host && p.out_elems) {
+            long long o_hi = 0;
+            for (const auto &d : p.desc) o_hi = std::max<long long>(o_hi, d.out_offset + d.n_out);
+            CK(cudaMemcpyAsync((unsigned char *)samples_host + (size_t)p.out_lo * esz, dc.out, (size_t)o_hi * esz, cudaMemcpyDeviceToHost, s));
+        }
+        if (tube_host && p.tube_elems) {
+            long long t_hi = 0;
+            for (const auto &d : p.desc) t_hi = std::max<long long>(t_hi, d.tube_offset + d.n_tube);
+            CK(cudaMemcpyAsync((unsigned char *)tube_host + (size_t)p.tube_lo * esz, dc.tube, (size_t)t_hi * esz, cudaMemcpyDeviceToHost, s));
+        }
+        if (max_host) {
+            unsigned char *mb = ctx->stages[slot].base + p.stage_bytes() - align_up(p.desc.size() * sizeof(unsigned long long), 256);
+            CK(cudaMemcpyAsync(mb, dc.maxbits, p.desc.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        }
+        slot_chunk[slot] = ci;
+    }
+    for (int slot = 0; slot < N_SLOTS; ++slot) {
+        int rc;
+        if (slot_chunk[slot] >= 0 && (rc = finish_slot(slot)) != 0) return rc;
+    }
+    if (launches) *launches = n_launch;
+    return 0;
+}
+
+int trm_cuda_resident_create(trm_cuda_ctx *ctx, int precision, int n, const trm_cuda_utterance *desc,
+                             const double *frames_host, trm_cuda_resident **out)
+{
+    *out = nullptr;
+    CK(cudaSetDevice(ctx->device));
+    const size_t esz = precision == 0 ? sizeof(double) : sizeof(float);
+    trm_cuda_resident *r = new trm_cuda_resident();
+    r->ctx = ctx;
+    r->precision = precision;
+    plan_chunk(desc, 0, n, r->plan);
+    int rc;
+    if ((rc = r->arena.reserve(r->plan.arena_bytes(esz, true))) != 0) { delete r; return rc; }
+    carve(r->arena, r->plan, esz, true, r->dc);
+    if ((rc = upload_plan(r->plan, r->dc, nullptr, 0)) != 0 || (rc = upload_frames(r->plan, r->dc, desc, frames_host, 0)) != 0) {
+        r->arena.release();
+        delete r;
+        return rc;
+    }
+    CK(cudaMemset(r->dc.maxbits, 0, (size_t)n * sizeof(unsigned long long)));
+    CK(cudaDeviceSynchronize());
+    *out = r;
+    return 0;
+}
+
+void trm_cuda_resident_destroy(trm_cuda_resident *r)
+{
+    if (!r) return;
+    cudaSetDevice(r->ctx->device);
+    cudaDeviceSynchronize();
+    r->arena.release();
+    delete r;
+}
+
+int trm_cuda_resident_stage(trm_cuda_resident *r, int stage, void *stream)
+{
+    CK(cudaSetDevice(r->ctx->device));
+    return launch_stage(r->ctx, r->precision, stage, r->dc, (cudaStream_t)stream);
+}
+
+int trm_cuda_resident_run(trm_cuda_resident *r, void *stream)
+{
+    for (int st = 0; st < TRM_STAGE_COUNT; ++st) {
+        int rc = trm_cuda_resident_stage(r, st, stream);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int trm_cuda_resident_fetch(trm_cuda_resident *r, int16_t *pcm_host, void *samples_host, double *max_host, void *tube_host)
+{
+    CK(cudaSetDevice(r->ctx->device));
+    CK(cudaDeviceSynchronize());
+    const size_t esz = r->precision == 0 ? sizeof(double) : sizeof(float);
+    const ChunkPlan &p = r->plan;
+    long long c_hi = 0, o_hi = 0, t_hi = 0;
+    for (const auto &d : p.desc) {
+        c_hi = std::max<long long>(c_hi, d.pcm_offset + d.n_out * d.channels);
+        o_hi = std::max<long long>(o_hi, d.out_offset + d.n_out);
+        t_hi = std::max<long long>(t_hi, d.tube_offset + d.n_tube);
+    }
+    if (pcm_host && c_hi) CK(cudaMemcpy(pcm_host + p.pcm_lo, r->dc.pcm, (size_t)c_hi * sizeof(int16_t), cudaMemcpyDeviceToHost));
+    if (samples_host && o_hi) CK(cudaMemcpy((unsigned char *)samples_host + (size_t)p.out_lo * esz, r->dc.out, (size_t)o_hi * esz, cudaMemcpyDeviceToHost));
+    if (tube_host && t_hi) CK(cudaMemcpy((unsigned char *)tube_host + (size_t)p.tube_lo * esz, r->dc.tube, (size_t)t_hi * esz, cudaMemcpyDeviceToHost));
+    if (max_host && !p.desc.empty()) {
+        std::vector<unsigned long long> mb(p.desc.size());
+        CK(cudaMemcpy(mb.data(), r->dc.maxbits, mb.size() * sizeof(mb[0]), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < mb.size(); ++i) memcpy(&max_host[i], &mb[i], sizeof(double));
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,1038 @@
+/*
+ * trm_host.c -- C host library behind include/trm.h (libtrm.so).
+ *
+ * Mirrors the host-side half of the reference's Tube.framework:
+ *   derived constants      -[TRMTubeModel initWithInputData:]        TRMTubeModel.m:186-260
+ *   wavetable set-up       -[TRMWavetable initWithWaveform:...]      TRMWavetable.m:56-106
+ *   FIR design             TRMFIRFilter.m:37-98, 161-310
+ *   SRC set-up / filter    TRMSampleRateConverter.m:69-131, TRMUtility.m:50-66
+ *   data list + parser     TRMDataList.m:22-247, TRMSynthesizer.m:98-106
+ *   output containers      TRMTubeModel.m:365-593, NSData-STExtensions.m:7-38
+ * Everything per-sample runs on the GPU through the libtrm_cuda shim; there is no CPU synthesis here.
+ */
+#include "trm.h"
+#include "trm_cuda.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------------------------------------
+ * errors
+ * ---------------------------------------------------------------------------------------------- */
+static __thread char g_errmsg[512];
+
+static int set_err(int code, const char *fmt, const char *detail)
+{
+    snprintf(g_errmsg, sizeof g_errmsg, fmt, detail ? detail : "");
+    return code;
+}
+const char *TRMLastErrorMessage(void) { return g_errmsg; }
+static int cuda_err(void) { return set_err(TRM_ERR_CUDA, "CUDA: %s", trm_cuda_last_error()); }
+
+/* ------------------------------------------------------------------------------------------------
+ * scalar conversions (TRMUtility.m:20-47)
+ * ---------------------------------------------------------------------------------------------- */
+static double sound_speed(double celsius) { return 331.4 + (0.6 * celsius); }
+
+static double db_to_amplitude(double db)
+{
+    db -= 60.0;                       /* 0..60 dB -> -60..0 dB */
+    if (db <= -60.0) return 0.0;
+    if (db >= 0.0) return 1.0;
+    return pow(10.0, db / 20.0);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * shared tables: FIR coefficients, SRC filter, noise jump multipliers
+ * ---------------------------------------------------------------------------------------------- */
+#define FIR_LIMIT 200
+
+/* best rational approximation p/q of x with q in [*order, 2*order] (TRMFIRFilter.m:265-310) */
+static void best_rational(double x, int *order, int *num, int *den)
+{
+    if (*order <= 0) { *num = *den = 0; *order = -1; return; }
+    const double frac = fabs(x - (int)x);
+    int q_max = 2 * (*order);
+    if (q_max > FIR_LIMIT) q_max = FIR_LIMIT;
+    int best_p = 0;
+    double best_err = 1.0;
+    for (int q = *order; q <= q_max; q++) {
+        const double scaled = q * frac;
+        const int p = (int)(scaled + 0.5);
+        const double err = fabs((scaled - (double)p) / (double)q);
+        if (err < best_err) { best_err = err; best_p = p; *den = q; }
+    }
+    *num = (int)fabs(x) * (*den) + best_p;
+    if (x < 0) *num = -*num;
+    *order = *den - 1;
+    if (*num == *den) { *den = q_max; *order = *num = *den - 1; }
+}
+
+/* maximally flat low-pass: one-sided coefficients w[1..*np] (TRMFIRFilter.m:161-233) */
+static int flat_lowpass(double beta, double gamma, int *np, double *w)
+{
+    double mag[FIR_LIMIT + 1], cs[FIR_LIMIT + 1];
+    *np = 0;
+    if (beta <= 0.0 || beta >= 0.5) return 1;
+    const double lim = ((2.0 * beta) < (1.0 - 2.0 * beta)) ? (2.0 * beta) : (1.0 - 2.0 * beta);
+    if (gamma <= 0.0 || gamma >= lim) return 2;
+    int nt = (int)(1.0 / (4.0 * gamma * gamma));
+    if (nt > 160) return 3;
+    const double ac = (1.0 + cos((2.0 * M_PI) * beta)) / 2.0;
+    int k;
+    best_rational(ac, &nt, &k, np);
+    const int n = (2 * (*np)) - 1;
+    if (k == 0) k = 1;
+    cs[1] = mag[1] = 1.0;
+    const int span = nt - k;
+    for (int i = 2; i <= *np; i++) {
+        double acc = 1.0;
+        cs[i] = cos((2.0 * M_PI) * ((double)(i - 1) / (double)n));
+        const double x = (1.0 - cs[i]) / 2.0;
+        double y = x;
+        if (k == nt) continue;
+        for (int j = 1; j <= span; j++) {
+            double z = y;
+            if (k != 1)
+                for (int jj = 1; jj <= (k - 1); jj++) z *= 1.0 + ((double)j / (double)jj);
+            y *= x;
+            acc += z;
+        }
+        mag[i] = acc * pow((1.0 - x), k);
+    }
+    for (int i = 1; i <= *np; i++) {       /* n-point inverse DFT of the sampled magnitude */
+        w[i] = mag[1] / 2.0;
+        for (int j = 2; j <= *np; j++) {
+            int m = ((i - 1) * (j - 1)) % n;
+            if (m > nt) m = n - m;
+            w[i] += cs[m + 1] * mag[j];
+        }
+        w[i] *= 2.0 / (double)n;
+    }
+    return 0;
+}
+
+/* tap layout of -[TRMFIRFilter initWithBeta:gamma:cutoff:] (TRMFIRFilter.m:37-98; trim :236-244) */
+static int design_fir(double *taps, int *n_taps)
+{
+    double w[FIR_LIMIT + 1];
+    int nc;
+    memset(w, 0, sizeof w);
+    if (flat_lowpass(.2, .1, &nc, w) != 0) return TRM_ERR_FIR;     /* TRMFIRFilter.h:7-9 */
+    for (int i = nc; i > 0; i--)
+        if (fabs(w[i]) >= fabs(.00000001)) { nc = i; break; }
+    *n_taps = (nc * 2) - 1;
+    if (*n_taps > TRM_FIR_MAX_TAPS) return TRM_ERR_FIR;
+    int step = -1, at = nc;
+    for (int i = 0; i < *n_taps; i++) {
+        taps[i] = w[at];
+        at += step;
+        if (at <= 0) { at = 2; step = 1; }
+    }
+    return TRM_OK;
+}
+
+/* modified Bessel I0 (TRMUtility.m:50-66) */
+static double bessel_i0(double x)
+{
+    double sum = 1, term = 1, n = 1;
+    const double half = x / 2.0;
+    do {
+        double t = half / n;
+        n += 1;
+        t *= t;
+        term *= t;
+        sum += term;
+    } while (term >= (1E-21 * sum));
+    return sum;
+}
+
+/* Kaiser-windowed sinc and its first difference (TRMSampleRateConverter.m:110-131) */
+static void design_src_filter(double *h, double *dh)
+{
+    const double cutoff = 11.0 / 13.0, kaiser_beta = 5.658;
+    h[0] = cutoff;
+    const double step = M_PI / 256.0;
+    for (int i = 1; i < TRM_SRC_FILTER_LEN; i++) {
+        const double y = (double)i * step;
+        h[i] = sin(y * cutoff) / y;
+    }
+    const double inv_i0 = 1.0 / bessel_i0(kaiser_beta);
+    for (int i = 0; i < TRM_SRC_FILTER_LEN; i++) {
+        const double t = (double)i / TRM_SRC_FILTER_LEN;
+        h[i] *= bessel_i0(kaiser_beta * sqrt(1.0 - (t * t))) * inv_i0;
+    }
+    for (int i = 0; i < TRM_SRC_FILTER_LEN - 1; i++) dh[i] = h[i + 1] - h[i];
+    dh[TRM_SRC_FILTER_LEN - 1] = 0.0 - h[TRM_SRC_FILTER_LEN - 1];
+}
+
+static trm_cuda_tables g_tables;
+static int g_tables_rc = TRM_OK;
+static pthread_once_t g_tables_once = PTHREAD_ONCE_INIT;
+
+static void build_tables(void)
+{
+    memset(&g_tables, 0, sizeof g_tables);
+    int taps = 0;
+    g_tables_rc = design_fir(g_tables.fir_coef, &taps);
+    g_tables.fir_taps = taps;
+    design_src_filter(g_tables.src_h, g_tables.src_dh);
+    /* The noise generator seed <- frac(seed*377), seed0 = 0.7892347 (TRMUtility.m:71-85) is, from the first
+     * draw on, the multiplicative congruential generator k <- 377 k mod 2^44 on k = seed * 2^44: the first
+     * product lies in [256,512) where doubles are spaced 2^-44, and 377 k < 2^53 keeps every later product exact. */
+    const uint64_t mask = (1ull << 44) - 1ull;
+    const double s0 = 0.7892347;
+    const double prod = s0 * 377.0;
+    const double s1 = prod - (int)prod;
+    const uint64_t k1 = (uint64_t)ldexp(s1, 44);
+    uint64_t inv = 377;                                  /* Newton iteration for 377^-1 mod 2^64 */
+    for (int i = 0; i < 6; i++) inv *= 2ull - 377ull * inv;
+    g_tables.noise_k0 = (k1 * inv) & mask;
+    uint64_t p = 1;
+    for (int i = 0; i <= TRM_NOISE_JUMP; i++) { g_tables.noise_pow[i] = p; p = (p * 377ull) & mask; }
+}
+
+static const trm_cuda_tables *tables(int *rc)
+{
+    pthread_once(&g_tables_once, build_tables);
+    if (rc) *rc = g_tables_rc;
+    return &g_tables;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * defaults and derived values
+ * ---------------------------------------------------------------------------------------------- */
+void TRMInputParametersSetDefaults(TRMInputParameters *ip, float outputRate)
+{
+    /* MMSynthesisParameters.m:163-187; control rate TRMSynthesizer.m:41; mono */
+    memset(ip, 0, sizeof *ip);
+    ip->outputFileFormat = TRMSoundFileFormat_AU;
+    ip->outputRate = outputRate;
+    ip->controlRate = 250;
+    ip->volume = 60;
+    ip->channels = 1;
+    ip->balance = 0;
+    ip->waveform = TRMWaveFormType_Pulse;
+    ip->tp = 40; ip->tnMin = 16; ip->tnMax = 32;
+    ip->breathiness = 1;
+    ip->length = 17.5; ip->temperature = 25; ip->lossFactor = 0.5;
+    ip->apScale = 3.05; ip->mouthCoef = 5000; ip->noseCoef = 5000;
+    ip->noseRadius[0] = 0; ip->noseRadius[1] = 1.35; ip->noseRadius[2] = 1.96;
+    ip->noseRadius[3] = 1.91; ip->noseRadius[4] = 1.3; ip->noseRadius[5] = 0.73;
+    ip->throatCutoff = 1500; ip->throatVol = 6;
+    ip->usesModulation = 1;
+    ip->mixOffset = 54;
+}
+
+typedef struct {
+    int32_t controlPeriod, sampleRate, padSize, upsample;
+    double actualTubeLength, ratio;
+    uint32_t tri, phaseIncrement;
+} rates_t;
+
+static int derive_rates(const TRMInputParameters *ip, rates_t *r)
+{
+    if (!(ip->length > 0.0)) return set_err(TRM_ERR_TUBE_LENGTH, "Illegal tube length%s", "");
+    if (!(ip->controlRate > 0.0f) || !(ip->outputRate > 0.0f))
+        return set_err(TRM_ERR_PARAM, "controlRate and outputRate must be positive%s", "");
+    /* TRMTubeModel.m:197-203 */
+    const double c = sound_speed(ip->temperature);
+    r->controlPeriod = rint((c * 10 * 100.0) / (ip->length * ip->controlRate));
+    r->sampleRate = ip->controlRate * r->controlPeriod;
+    if (r->controlPeriod < 1 || r->sampleRate < 1) return set_err(TRM_ERR_PARAM, "control period < 1 sample%s", "");
+    r->actualTubeLength = (c * 10 * 100.0) / r->sampleRate;
+    /* TRMSampleRateConverter.m:80-96 */
+    r->ratio = (double)ip->outputRate / (double)r->sampleRate;
+    r->tri = (int)rint(pow(2.0, 16) / r->ratio);
+    if (r->tri == 0) return set_err(TRM_ERR_PARAM, "sample-rate ratio too large%s", "");
+    const double rounded = pow(2.0, 16) / (double)r->tri;
+    r->upsample = r->ratio >= 1.0;
+    r->phaseIncrement = r->upsample ? 0u : (uint32_t)rint(r->ratio * 65536.0);
+    r->padSize = r->upsample ? 13 : (int32_t)((float)13 / rounded) + 1;
+    return TRM_OK;
+}
+
+static int64_t src_output_count(const rates_t *r, int64_t n_in)
+{
+    /* the converter emits one sample per time-register step until the read position reaches
+     * n_in + 2*pad (TRMSampleRateConverter.m:171,221-232; TRMRingBuffer.m:85-93) */
+    const int64_t total = n_in + 2 * (int64_t)r->padSize;
+    return (total * 65536 + (int64_t)r->tri - 1) / (int64_t)r->tri;
+}
+
+int TRMDeriveValues(const TRMInputParameters *ip, size_t n_frames, TRMDerivedValues *out)
+{
+    rates_t r;
+    int rc = derive_rates(ip, &r);
+    if (rc) return rc;
+    memset(out, 0, sizeof *out);
+    out->controlPeriod = r.controlPeriod;
+    out->sampleRate = r.sampleRate;
+    out->actualTubeLength = r.actualTubeLength;
+    out->padSize = r.padSize;
+    out->timeRegisterIncrement = r.tri;
+    out->tubeSamples = n_frames ? (int64_t)(n_frames - 1) * r.controlPeriod : 0;
+    out->numberSamples = n_frames ? (int32_t)src_output_count(&r, out->tubeSamples) : 0;   /* TRMTubeModel.m:274-277 */
+    return TRM_OK;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * voices: the init-time glottal table (TRMWavetable.m:56-106), deduplicated per batch
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t waveform, div1, div2;
+    double tp, tnMin, tnMax, tnDelta;
+} voice_key;
+
+typedef struct {
+    voice_key *keys;
+    double *tables;          /* n x 512 */
+    int n, cap;
+} voice_set;
+
+static void voice_set_free(voice_set *vs) { free(vs->keys); free(vs->tables); memset(vs, 0, sizeof *vs); }
+
+static int voice_lookup(voice_set *vs, const TRMInputParameters *ip, voice_key *out_key)
+{
+    voice_key k;
+    memset(&k, 0, sizeof k);
+    k.waveform = ip->waveform; k.tp = ip->tp; k.tnMin = ip->tnMin; k.tnMax = ip->tnMax;
+    for (int i = 0; i < vs->n; i++)
+        if (vs->keys[i].waveform == k.waveform && vs->keys[i].tp == k.tp && vs->keys[i].tnMin == k.tnMin &&
+            vs->keys[i].tnMax == k.tnMax) { *out_key = vs->keys[i]; return i; }
+    /* TRMWavetable.m:71-74 */
+    k.div1 = rint(TRM_TABLE_LENGTH * (ip->tp / 100.0));
+    k.div2 = rint(TRM_TABLE_LENGTH * ((ip->tp + ip->tnMax) / 100.0));
+    const double tnLength = k.div2 - k.div1;
+    k.tnDelta = rint(TRM_TABLE_LENGTH * ((ip->tnMax - ip->tnMin) / 100.0));
+    if (ip->waveform != TRMWaveFormType_Pulse && ip->waveform != TRMWaveFormType_Sine)
+        return set_err(TRM_ERR_PARAM, "unknown glottal waveform type%s", "");
+    if (ip->waveform == TRMWaveFormType_Pulse &&
+        !(k.div1 > 0 && k.div1 < k.div2 && k.div2 <= TRM_TABLE_LENGTH && k.tnDelta >= 0.0 && k.tnDelta < tnLength))
+        return set_err(TRM_ERR_PARAM, "glottal pulse shape (tp/tnMin/tnMax) outside 0 < tp, tnMin > 0, tp+tnMax <= 100%s", "");
+    if (vs->n == vs->cap) {
+        int cap = vs->cap ? vs->cap * 2 : 4;
+        voice_key *nk = realloc(vs->keys, (size_t)cap * sizeof *nk);
+        if (!nk) return set_err(TRM_ERR_NOMEM, "out of memory%s", "");
+        vs->keys = nk;
+        double *nt = realloc(vs->tables, (size_t)cap * TRM_TABLE_LENGTH * sizeof *nt);
+        if (!nt) return set_err(TRM_ERR_NOMEM, "out of memory%s", "");
+        vs->tables = nt;
+        vs->cap = cap;
+    }
+    double *t = vs->tables + (size_t)vs->n * TRM_TABLE_LENGTH;
+    if (ip->waveform == TRMWaveFormType_Pulse) {
+        /* TRMWavetable.m:78-96 */
+        for (int i = 0; i < k.div1; i++) {
+            const double x = (double)i / (double)k.div1;
+            const double x2 = x * x, x3 = x2 * x;
+            t[i] = (3.0 * x2) - (2.0 * x3);
+        }
+        for (int i = k.div1, j = 0; i < k.div2; i++, j++) {
+            const double x = (double)j / tnLength;
+            t[i] = 1.0 - (x * x);
+        }
+        for (int i = k.div2; i < TRM_TABLE_LENGTH; i++) t[i] = 0.0;
+    } else {
+        /* TRMWavetable.m:99-101 */
+        for (int i = 0; i < TRM_TABLE_LENGTH; i++) t[i] = sin(((double)i / (double)TRM_TABLE_LENGTH) * 2.0 * M_PI);
+    }
+    vs->keys[vs->n] = k;
+    *out_key = k;
+    return vs->n++;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * per-utterance descriptor: -initWithInputData: (TRMTubeModel.m:196-241)
+ * ---------------------------------------------------------------------------------------------- */
+#define SRC_TILE_OUT 1024
+#define SRC_WINDOW   4096
+
+static void radrefl_coefficients(double coeff, double *f)
+{
+    /* TRMFilters.m:34-45: a10 b11 a20 a21 b21 */
+    f[1] = -coeff;
+    f[0] = 1.0 - fabs(f[1]);
+    f[2] = coeff;
+    f[3] = f[4] = -(f[2]);
+}
+
+static int describe(const TRMInputParameters *ip, int32_t n_frames, voice_set *vs, trm_cuda_utterance *d, rates_t *rates_out)
+{
+    rates_t r;
+    int rc = derive_rates(ip, &r);
+    if (rc) return rc;
+    if (n_frames < 0) return set_err(TRM_ERR_PARAM, "negative frame count%s", "");
+    if (ip->channels != 1 && ip->channels != 2) return set_err(TRM_ERR_PARAM, "channels must be 1 or 2%s", "");
+    /* the resampler stages a bounded input window per output tile */
+    if ((double)SRC_TILE_OUT / r.ratio + 2.0 * (r.padSize + 2) + 8.0 > (double)SRC_WINDOW)
+        return set_err(TRM_ERR_PARAM, "outputRate / tube sample rate below the supported ratio%s", "");
+    voice_key vk;
+    const int voice = voice_lookup(vs, ip, &vk);
+    if (voice < 0) return voice;
+
+    memset(d, 0, sizeof *d);
+    d->n_frames = n_frames;
+    d->controlPeriod = r.controlPeriod;
+    d->n_tube = n_frames > 0 ? (int64_t)(n_frames - 1) * r.controlPeriod : 0;
+    d->n_out = n_frames > 0 ? src_output_count(&r, d->n_tube) : 0;
+    d->waveform = ip->waveform;
+    d->usesModulation = ip->usesModulation != 0;
+    d->voice = voice;
+    d->padSize = r.padSize;
+    d->upsample = r.upsample;
+    d->channels = ip->channels;
+    d->div1 = vk.div1;
+    d->div2 = vk.div2;
+    d->tri = r.tri;
+    d->phaseIncrement = r.phaseIncrement;
+    d->sampleRate = (double)r.sampleRate;
+    d->sampleRateRatio = r.ratio;
+    const double nyquist = (double)r.sampleRate / 2.0;
+    d->dampingFactor = (1.0 - (ip->lossFactor / 100.0));                       /* m:216 */
+    d->breathinessFactor = ip->breathiness / 100.0;                            /* m:210 */
+    d->crossmixFactor = 1.0 / db_to_amplitude(ip->mixOffset);                  /* m:213 */
+    d->basicIncrement = (double)TRM_TABLE_LENGTH / (double)r.sampleRate;       /* TRMWavetable.m:75 */
+    d->tnDelta = vk.tnDelta;
+    radrefl_coefficients((nyquist - ip->mouthCoef) / nyquist, d->mouth);       /* m:222 */
+    radrefl_coefficients((nyquist - ip->noseCoef) / nyquist, d->nose);         /* m:225 */
+    for (int i = 1; i < 5; i++) {                                              /* m:695-699: NC2..NC5 */
+        const double a2 = ip->noseRadius[i] * ip->noseRadius[i];
+        const double b2 = ip->noseRadius[i + 1] * ip->noseRadius[i + 1];
+        d->nasal_coeff[i - 1] = (a2 - b2) / (a2 + b2);
+    }
+    {
+        const double a2 = ip->noseRadius[5] * ip->noseRadius[5];               /* m:703-705: NC6 */
+        const double b2 = ip->apScale * ip->apScale;
+        d->nasal_coeff[4] = (a2 - b2) / (a2 + b2);
+        d->apScale2 = b2;
+    }
+    d->nr1sq = ip->noseRadius[1] * ip->noseRadius[1];                          /* m:741 */
+    d->ta0 = (ip->throatCutoff * 2.0) / r.sampleRate;                          /* TRMFilters.m:66-67 */
+    d->tb1 = 1.0 - d->ta0;
+    d->throatGain = db_to_amplitude(ip->throatVol);                            /* m:239 */
+    d->volumeAmp = db_to_amplitude(ip->volume);                                /* m:515 */
+    d->leftGain = -((ip->balance / 2.0) - 0.5);                                /* m:532 */
+    d->rightGain = ((ip->balance / 2.0) + 0.5);                                /* m:533 */
+    if (rates_out) *rates_out = r;
+    return TRM_OK;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * CUDA contexts: one per device, created on first use
+ * ---------------------------------------------------------------------------------------------- */
+#define MAX_DEVICES 64
+static trm_cuda_ctx *g_ctx[MAX_DEVICES];
+static pthread_mutex_t g_ctx_mu[MAX_DEVICES];
+static pthread_mutex_t g_ctx_table_mu = PTHREAD_MUTEX_INITIALIZER;
+static int g_ctx_mu_init;
+
+static int acquire_ctx(int device, trm_cuda_ctx **out)
+{
+    int rc;
+    const trm_cuda_tables *t = tables(&rc);
+    if (rc) return set_err(rc, "FIR design failed%s", "");
+    if (device < 0 || device >= MAX_DEVICES) return set_err(TRM_ERR_CUDA, "bad device ordinal%s", "");
+    pthread_mutex_lock(&g_ctx_table_mu);
+    if (!g_ctx_mu_init) {
+        for (int i = 0; i < MAX_DEVICES; i++) pthread_mutex_init(&g_ctx_mu[i], NULL);
+        g_ctx_mu_init = 1;
+    }
+    if (!g_ctx[device]) {
+        if (trm_cuda_ctx_create(device, t, &g_ctx[device]) != 0) {
+            pthread_mutex_unlock(&g_ctx_table_mu);
+            return cuda_err();
+        }
+    }
+    pthread_mutex_unlock(&g_ctx_table_mu);
+    pthread_mutex_lock(&g_ctx_mu[device]);       /* a context serves one call at a time */
+    *out = g_ctx[device];
+    return TRM_OK;
+}
+static void release_ctx(int device) { pthread_mutex_unlock(&g_ctx_mu[device]); }
+
+void *TRMHostAlloc(size_t bytes)
+{
+    void *p = trm_cuda_host_alloc(bytes);
+    if (!p) cuda_err();
+    return p;
+}
+void TRMHostFree(void *p) { trm_cuda_host_free(p); }
+void TRMFree(void *p) { free(p); }
+
+/* ------------------------------------------------------------------------------------------------
+ * TRMDataList
+ * ---------------------------------------------------------------------------------------------- */
+struct TRMDataList {
+    TRMInputParameters ip;
+    TRMParameters *values;
+    size_t count, cap;
+};
+
+TRMDataList *TRMDataListCreate(void) { return calloc(1, sizeof(TRMDataList)); }
+
+void TRMDataListFree(TRMDataList *l)
+{
+    if (!l) return;
+    free(l->values);
+    free(l);
+}
+
+TRMInputParameters *TRMDataListInputParameters(TRMDataList *l) { return &l->ip; }
+size_t TRMDataListCount(const TRMDataList *l) { return l->count; }
+const TRMParameters *TRMDataListValues(const TRMDataList *l) { return l->values; }
+void TRMDataListRemoveAllParameters(TRMDataList *l) { l->count = 0; }
+
+int TRMDataListAddParametersArray(TRMDataList *l, const TRMParameters *f, size_t n)
+{
+    if (l->count + n > l->cap) {
+        size_t cap = l->cap ? l->cap : 256;
+        while (cap < l->count + n) cap *= 2;
+        TRMParameters *nv = realloc(l->values, cap * sizeof *nv);
+        if (!nv) return set_err(TRM_ERR_NOMEM, "out of memory%s", "");
+        l->values = nv;
+        l->cap = cap;
+    }
+    memcpy(l->values + l->count, f, n * sizeof *f);
+    l->count += n;
+    return TRM_OK;
+}
+int TRMDataListAddParameters(TRMDataList *l, const TRMParameters *f) { return TRMDataListAddParametersArray(l, f, 1); }
+
+/* positional text format: 26 header lines (value first, comment ignored), then 16 numbers per line
+ * (TRMDataList.m:43-247).  Lines are read in 128-byte pieces like the reference's fgets(line, 128, fp). */
+TRMDataList *TRMDataListCreateWithContentsOfFile(const char *path, int *err)
+{
+    int dummy;
+    if (!err) err = &dummy;
+    FILE *fp = fopen(path, "r");
+    if (!fp) { *err = set_err(TRM_ERR_IO, "Can't open input file \"%s\".", path); return NULL; }
+    TRMDataList *l = TRMDataListCreate();
+    if (!l) { fclose(fp); *err = set_err(TRM_ERR_NOMEM, "out of memory%s", ""); return NULL; }
+    char line[128];
+    TRMInputParameters *ip = &l->ip;
+    double hv[26];
+    static const char *what[26] = {
+        "output file format", "output sample rate", "input control rate", "master volume",
+        "number of sound output channels", "stereo balance", "glottal source waveform type",
+        "glottal pulse rise time (tp)", "glottal pulse fall time minimum (tnMin)", "glottal pulse fall time maximum (tnMax)",
+        "glottal source breathiness", "nominal tube length", "tube temperature", "junction loss factor",
+        "aperture scaling radius", "mouth aperture coefficient", "nose aperture coefficient",
+        "nose radius 1", "nose radius 2", "nose radius 3", "nose radius 4", "nose radius 5",
+        "throat lowpass filter cutoff", "throat volume", "pulse modulation of noise flag", "noise crossmix offset"};
+    static const int is_int[26] = {1, 0, 0, 0, 1, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0};
+    for (int i = 0; i < 26; i++) {
+        if (!fgets(line, sizeof line, fp)) {
+            *err = set_err(TRM_ERR_IO, "Can't read %s.", what[i]);
+            fclose(fp);
+            TRMDataListFree(l);
+            return NULL;
+        }
+        hv[i] = is_int[i] ? (double)strtol(line, NULL, 10) : strtod(line, NULL);
+    }
+    ip->outputFileFormat = (int32_t)hv[0]; ip->outputRate = hv[1]; ip->controlRate = hv[2]; ip->volume = hv[3];
+    ip->channels = (int32_t)hv[4]; ip->balance = hv[5]; ip->waveform = (int32_t)hv[6]; ip->tp = hv[7];
+    ip->tnMin = hv[8]; ip->tnMax = hv[9]; ip->breathiness = hv[10]; ip->length = hv[11]; ip->temperature = hv[12];
+    ip->lossFactor = hv[13]; ip->apScale = hv[14]; ip->mouthCoef = hv[15]; ip->noseCoef = hv[16];
+    for (int i = 1; i < TRM_TOTAL_NASAL_SECTIONS; i++) ip->noseRadius[i] = hv[16 + i];
+    ip->throatCutoff = hv[22]; ip->throatVol = hv[23]; ip->usesModulation = (hv[24] != 0); ip->mixOffset = hv[25];
+
+    while (fgets(line, sizeof line, fp)) {
+        TRMParameters f;
+        char *at = line;
+        double *v = (double *)&f;
+        for (int q = 0; q < 16; q++) v[q] = strtod(at, &at);
+        if ((*err = TRMDataListAddParameters(l, &f)) != TRM_OK) { fclose(fp); TRMDataListFree(l); return NULL; }
+    }
+    if (l->count > 0) {               /* the parser doubles the last table (TRMDataList.m:239-241) */
+        TRMParameters last = l->values[l->count - 1];
+        if ((*err = TRMDataListAddParameters(l, &last)) != TRM_OK) { fclose(fp); TRMDataListFree(l); return NULL; }
+    }
+    fclose(fp);
+    *err = TRM_OK;
+    return l;
+}
+
+int TRMDataListWriteToFile(const TRMDataList *l, const char *path)
+{
+    FILE *fp = fopen(path, "w");
+    if (!fp) return set_err(TRM_ERR_IO, "Can't open output file \"%s\".", path);
+    const TRMInputParameters *ip = &l->ip;
+    fprintf(fp, "%d\t\t; output file format (0 = AU, 1 = AIFF, 2 = WAVE)\n", ip->outputFileFormat);
+    fprintf(fp, "%f\t; output sample rate (22050.0, 44100.0)\n", ip->outputRate);
+    fprintf(fp, "%d\t\t; input control rate (1 - 1000 Hz)\n", (int)ip->controlRate);
+    fprintf(fp, "%f\t; master volume (0 - 60 dB)\n", ip->volume);
+    fprintf(fp, "%d\t\t; number of sound output channels (1 or 2)\n", ip->channels);
+    fprintf(fp, "%f\t; stereo balance (-1 to +1)\n", ip->balance);
+    fprintf(fp, "%d\t\t; glottal source waveform type (0 = pulse, 1 = sine)\n", ip->waveform);
+    fprintf(fp, "%f\t; glottal pulse rise time (5 - 50 %% of GP period)\n", ip->tp);
+    fprintf(fp, "%f\t; glottal pulse fall time minimum (5 - 50 %% of GP period)\n", ip->tnMin);
+    fprintf(fp, "%f\t; glottal pulse fall time maximum (5 - 50 %% of GP period)\n", ip->tnMax);
+    fprintf(fp, "%f\t; glottal source breathiness (0 - 10 %% of GS amplitude)\n", ip->breathiness);
+    fprintf(fp, "%f\t; nominal tube length (10 - 20 cm)\n", ip->length);
+    fprintf(fp, "%f\t; tube temperature (25 - 40 degrees celsius)\n", ip->temperature);
+    fprintf(fp, "%f\t; junction loss factor (0 - 5 %% of unity gain)\n", ip->lossFactor);
+    fprintf(fp, "%f\t; aperture scaling radius (3.05 - 12 cm)\n", ip->apScale);
+    fprintf(fp, "%f\t; mouth aperture coefficient (0 - 0.99)\n", ip->mouthCoef);
+    fprintf(fp, "%f\t; nose aperture coefficient (0 - 0.99)\n", ip->noseCoef);
+    for (int i = 1; i < TRM_TOTAL_NASAL_SECTIONS; i++)
+        fprintf(fp, "%f\t; radius of nose section %d (0 - 3 cm)\n", ip->noseRadius[i], i);
+    fprintf(fp, "%f\t; throat lowpass frequency cutoff (50 - nyquist Hz)\n", ip->throatCutoff);
+    fprintf(fp, "%f\t; throat volume (0 - 48 dB)\n", ip->throatVol);
+    fprintf(fp, "%d\t\t; pulse modulation of noise (0 = off, 1 = on)\n", ip->usesModulation ? 1 : 0);
+    fprintf(fp, "%f\t; noise crossmix offset (30 - 60 db)\n", ip->mixOffset);
+    for (size_t i = 0; i < l->count; i++) {
+        const double *v = (const double *)&l->values[i];
+        for (int q = 0; q < 16; q++) fprintf(fp, q ? " %.3f" : "%.3f", v[q]);
+        fputc('\n', fp);
+    }
+    if (fclose(fp) != 0) return set_err(TRM_ERR_IO, "write error on \"%s\"", path);
+    return TRM_OK;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * TRMBatch
+ * ---------------------------------------------------------------------------------------------- */
+struct TRMBatch {
+    int n, precision;
+    trm_cuda_utterance *desc;      /* offsets relative to the caller's arrays */
+    voice_set voices;
+    int32_t *numberSamples;
+    int64_t *pcm_offsets, *out_offsets, *tube_offsets;
+    double *maxima;
+    TRMBatchLayout layout;
+    int64_t total_tube_elems;
+    int64_t launches;
+};
+
+static int64_t round_up_elems(int64_t v) { return (v + TRM_ALIGN_ELEMS - 1) / TRM_ALIGN_ELEMS * TRM_ALIGN_ELEMS; }
+
+void TRMBatchFree(TRMBatch *b)
+{
+    if (!b) return;
+    free(b->desc); free(b->numberSamples); free(b->pcm_offsets); free(b->out_offsets); free(b->tube_offsets); free(b->maxima);
+    voice_set_free(&b->voices);
+    free(b);
+}
+
+TRMBatch *TRMBatchCreate(int n, const TRMInputParameters *ip, int shared, const int64_t *frame_offset,
+                         const int32_t *n_frames, int precision, int *err)
+{
+    int dummy;
+    if (!err) err = &dummy;
+    if (n < 0 || (precision != TRM_PRECISION_FP64 && precision != TRM_PRECISION_FP32)) {
+        *err = set_err(TRM_ERR_PARAM, "bad batch size or precision%s", "");
+        return NULL;
+    }
+    int rc;
+    tables(&rc);
+    if (rc) { *err = set_err(rc, "FIR design failed%s", ""); return NULL; }
+    TRMBatch *b = calloc(1, sizeof *b);
+    if (!b) { *err = set_err(TRM_ERR_NOMEM, "out of memory%s", ""); return NULL; }
+    b->n = n;
+    b->precision = precision;
+    const size_t nn = (size_t)(n > 0 ? n : 1);
+    b->desc = calloc(nn, sizeof *b->desc);
+    b->numberSamples = calloc(nn, sizeof *b->numberSamples);
+    b->pcm_offsets = calloc(nn, sizeof *b->pcm_offsets);
+    b->out_offsets = calloc(nn, sizeof *b->out_offsets);
+    b->tube_offsets = calloc(nn, sizeof *b->tube_offsets);
+    b->maxima = calloc(nn, sizeof *b->maxima);
+    if (!b->desc || !b->numberSamples || !b->pcm_offsets || !b->out_offsets || !b->tube_offsets || !b->maxima) {
+        TRMBatchFree(b);
+        *err = set_err(TRM_ERR_NOMEM, "out of memory%s", "");
+        return NULL;
+    }
+    int64_t pcm_at = 0, out_at = 0, tube_at = 0, frames_hi = 0;
+    trm_cuda_utterance shared_desc;
+    rates_t shared_rates;
+    int32_t shared_nf = -1;
+    for (int u = 0; u < n; u++) {
+        const TRMInputParameters *p = shared ? ip : ip + u;
+        trm_cuda_utterance *d = &b->desc[u];
+        rates_t r;
+        if (shared && shared_nf >= 0) {
+            /* same voice: only the counts depend on the number of frames */
+            *d = shared_desc;
+            r = shared_rates;
+            if (n_frames[u] < 0) { rc = set_err(TRM_ERR_PARAM, "negative frame count%s", ""); goto bad; }
+            d->n_frames = n_frames[u];
+            d->n_tube = n_frames[u] > 0 ? (int64_t)(n_frames[u] - 1) * r.controlPeriod : 0;
+            d->n_out = n_frames[u] > 0 ? src_output_count(&r, d->n_tube) : 0;
+        } else {
+            rc = describe(p, n_frames[u], &b->voices, d, &r);
+            if (rc) goto bad;
+            if (shared) { shared_desc = *d; shared_rates = r; shared_nf = n_frames[u]; }
+        }
+        if (d->n_out > INT32_MAX) { rc = set_err(TRM_ERR_PARAM, "utterance too long (numberSamples is int32 in the reference)%s", ""); goto bad; }
+        d->frame_offset = frame_offset[u];
+        d->tube_offset = tube_at;
+        d->out_offset = out_at;
+        d->pcm_offset = pcm_at;
+        b->numberSamples[u] = (int32_t)d->n_out;
+        b->tube_offsets[u] = tube_at;
+        b->out_offsets[u] = out_at;
+        b->pcm_offsets[u] = pcm_at;
+        tube_at += round_up_elems(d->n_tube);
+        out_at += round_up_elems(d->n_out);
+        pcm_at += round_up_elems(d->n_out * d->channels);
+        if (frame_offset[u] + n_frames[u] > frames_hi) frames_hi = frame_offset[u] + n_frames[u];
+        b->layout.audio_seconds += n_frames[u] > 0 ? (double)(n_frames[u] - 1) / (double)p->controlRate : 0.0;
+        b->layout.tube_samples += d->n_tube;
+        b->layout.out_samples += d->n_out;
+    }
+    b->layout.total_frames = frames_hi;
+    b->layout.total_pcm_samples = pcm_at;
+    b->layout.total_out_samples = out_at;
+    b->total_tube_elems = tube_at;
+    *err = TRM_OK;
+    return b;
+bad:
+    TRMBatchFree(b);
+    *err = rc;
+    return NULL;
+}
+
+void TRMBatchGetLayout(const TRMBatch *b, TRMBatchLayout *l) { *l = b->layout; }
+const int32_t *TRMBatchNumberSamples(const TRMBatch *b) { return b->numberSamples; }
+const int64_t *TRMBatchPCMOffsets(const TRMBatch *b) { return b->pcm_offsets; }
+const int64_t *TRMBatchOutOffsets(const TRMBatch *b) { return b->out_offsets; }
+const double *TRMBatchMaximumSampleValues(const TRMBatch *b) { return b->maxima; }
+int64_t TRMBatchTubeElements(const TRMBatch *b) { return b->total_tube_elems; }
+const int64_t *TRMBatchTubeOffsets(const TRMBatch *b) { return b->tube_offsets; }
+int64_t TRMBatchKernelLaunches(const TRMBatch *b) { return b->launches; }
+
+typedef struct {
+    TRMBatch *b;
+    const TRMParameters *frames;
+    int16_t *pcm;
+    void *samples, *tube;
+    int device, u0, u1, rc;
+    int64_t launches;
+    char msg[512];
+} shard_job;
+
+static void *shard_main(void *arg)
+{
+    shard_job *j = arg;
+    trm_cuda_ctx *ctx;
+    j->rc = acquire_ctx(j->device, &ctx);
+    if (j->rc == TRM_OK) {
+        if (trm_cuda_set_wavetables(ctx, j->b->voices.tables, j->b->voices.n) != 0 ||
+            trm_cuda_synthesize_host(ctx, j->b->precision, j->u1 - j->u0, j->b->desc + j->u0, (const double *)j->frames,
+                                     j->pcm, j->samples, j->b->maxima + j->u0, j->tube, &j->launches) != 0)
+            j->rc = cuda_err();
+        release_ctx(j->device);
+    }
+    if (j->rc) snprintf(j->msg, sizeof j->msg, "%s", g_errmsg);
+    return NULL;
+}
+
+static int batch_run(TRMBatch *b, const TRMParameters *frames, int16_t *pcm, void *samples, void *tube,
+                     const int *devices, int n_devices)
+{
+    if (b->n == 0) return TRM_OK;
+    if (n_devices < 1) n_devices = 1;
+    if (n_devices > b->n) n_devices = b->n;
+    if (n_devices > MAX_DEVICES) n_devices = MAX_DEVICES;
+    shard_job jobs[MAX_DEVICES];
+    pthread_t th[MAX_DEVICES];
+    /* contiguous shards with equal shares of the tube-rate work; no data crosses devices */
+    const double per = (double)b->layout.tube_samples / n_devices;
+    int u = 0;
+    double acc = 0;
+    for (int k = 0; k < n_devices; k++) {
+        memset(&jobs[k], 0, sizeof jobs[k]);
+        jobs[k].b = b; jobs[k].frames = frames; jobs[k].pcm = pcm; jobs[k].samples = samples; jobs[k].tube = tube;
+        jobs[k].device = devices ? devices[k] : k;
+        jobs[k].u0 = u;
+        if (k == n_devices - 1) u = b->n;
+        else {
+            const int remaining_devices = n_devices - 1 - k;
+            while (u < b->n - remaining_devices && (u == jobs[k].u0 || acc + (double)b->desc[u].n_tube <= per * (k + 1))) {
+                acc += (double)b->desc[u].n_tube;
+                u++;
+            }
+        }
+        jobs[k].u1 = u;
+    }
+    if (n_devices == 1) shard_main(&jobs[0]);
+    else {
+        for (int k = 0; k < n_devices; k++)
+            if (pthread_create(&th[k], NULL, shard_main, &jobs[k]) != 0) { jobs[k].rc = TRM_ERR_NOMEM; th[k] = 0; shard_main(&jobs[k]); }
+        for (int k = 0; k < n_devices; k++)
+            if (th[k]) pthread_join(th[k], NULL);
+    }
+    b->launches = 0;
+    for (int k = 0; k < n_devices; k++) {
+        b->launches += jobs[k].launches;
+        if (jobs[k].rc) { snprintf(g_errmsg, sizeof g_errmsg, "%s", jobs[k].msg); return jobs[k].rc; }
+    }
+    return TRM_OK;
+}
+
+int TRMBatchSynthesize(TRMBatch *b, const TRMParameters *frames, int16_t *pcm_out, void *samples_out,
+                       const int *devices, int n_devices)
+{
+    return batch_run(b, frames, pcm_out, samples_out, NULL, devices, n_devices);
+}
+
+/* like TRMBatchSynthesize, additionally returning the tube-rate signal (TRMBatchTubeElements() elements) */
+int TRMBatchSynthesizeDebug(TRMBatch *b, const TRMParameters *frames, int16_t *pcm_out, void *samples_out,
+                            void *tube_out, int device)
+{
+    return batch_run(b, frames, pcm_out, samples_out, tube_out, &device, 1);
+}
+
+/* ---- device-resident batches (bench `value`, per-stage timing) ---- */
+typedef struct TRMResident {
+    trm_cuda_resident *res;
+    int device;
+} TRMResident;
+
+TRMResident *TRMBatchMakeResident(TRMBatch *b, const TRMParameters *frames, int device, int *err)
+{
+    int dummy;
+    if (!err) err = &dummy;
+    trm_cuda_ctx *ctx;
+    if ((*err = acquire_ctx(device, &ctx)) != TRM_OK) return NULL;
+    TRMResident *r = calloc(1, sizeof *r);
+    if (!r) { release_ctx(device); *err = set_err(TRM_ERR_NOMEM, "out of memory%s", ""); return NULL; }
+    r->device = device;
+    if (trm_cuda_set_wavetables(ctx, b->voices.tables, b->voices.n) != 0 ||
+        trm_cuda_resident_create(ctx, b->precision, b->n, b->desc, (const double *)frames, &r->res) != 0) {
+        *err = cuda_err();
+        free(r);
+        r = NULL;
+    } else
+        *err = TRM_OK;
+    release_ctx(device);
+    return r;
+}
+int TRMResidentRunStage(TRMResident *r, int stage, void *cuda_stream)
+{
+    return trm_cuda_resident_stage(r->res, stage, cuda_stream) ? cuda_err() : TRM_OK;
+}
+int TRMResidentRun(TRMResident *r, void *cuda_stream) { return trm_cuda_resident_run(r->res, cuda_stream) ? cuda_err() : TRM_OK; }
+int TRMResidentFetch(TRMResident *r, int16_t *pcm, void *samples, double *maxima, void *tube)
+{
+    return trm_cuda_resident_fetch(r->res, pcm, samples, maxima, tube) ? cuda_err() : TRM_OK;
+}
+void TRMResidentFree(TRMResident *r)
+{
+    if (!r) return;
+    trm_cuda_resident_destroy(r->res);
+    free(r);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * TRMTubeModel
+ * ---------------------------------------------------------------------------------------------- */
+struct TRMTubeModel {
+    TRMInputParameters ip;
+    TRMParameters *frames;
+    size_t n_frames;
+    int precision, device, done;
+    TRMDerivedValues derived;
+    double *resampled, *tube;
+    int16_t *pcm;             /* device-scaled PCM (WAV variant) */
+    int32_t numberSamples;
+    double maximum;
+};
+
+TRMTubeModel *TRMTubeModelCreate(const TRMDataList *in, int *err)
+{
+    int dummy;
+    if (!err) err = &dummy;
+    TRMDerivedValues dv;
+    if ((*err = TRMDeriveValues(&in->ip, in->count, &dv)) != TRM_OK) {
+        if (*err == TRM_ERR_TUBE_LENGTH) fprintf(stderr, "Illegal tube length: %g\n", in->ip.length);   /* m:205 */
+        return NULL;
+    }
+    /* validate everything else now, as -initWithInputData: builds the wavetable / filters up front */
+    voice_set vs;
+    memset(&vs, 0, sizeof vs);
+    trm_cuda_utterance d;
+    *err = describe(&in->ip, (int32_t)in->count, &vs, &d, NULL);
+    voice_set_free(&vs);
+    if (*err) return NULL;
+    TRMTubeModel *m = calloc(1, sizeof *m);
+    if (!m) { *err = set_err(TRM_ERR_NOMEM, "out of memory%s", ""); return NULL; }
+    m->ip = in->ip;
+    m->n_frames = in->count;
+    m->derived = dv;
+    if (in->count) {
+        m->frames = malloc(in->count * sizeof *m->frames);
+        if (!m->frames) { free(m); *err = set_err(TRM_ERR_NOMEM, "out of memory%s", ""); return NULL; }
+        memcpy(m->frames, in->values, in->count * sizeof *m->frames);
+    }
+    *err = TRM_OK;
+    return m;
+}
+
+void TRMTubeModelFree(TRMTubeModel *m)
+{
+    if (!m) return;
+    free(m->frames); free(m->resampled); free(m->tube); free(m->pcm);
+    free(m);
+}
+
+int TRMTubeModelSetPrecision(TRMTubeModel *m, int precision)
+{
+    if (precision != TRM_PRECISION_FP64 && precision != TRM_PRECISION_FP32) return set_err(TRM_ERR_PARAM, "bad precision%s", "");
+    m->precision = precision;
+    return TRM_OK;
+}
+int TRMTubeModelSetDevice(TRMTubeModel *m, int device) { m->device = device; return TRM_OK; }
+void TRMTubeModelGetDerivedValues(const TRMTubeModel *m, TRMDerivedValues *out) { *out = m->derived; }
+
+int TRMTubeModelSynthesize(TRMTubeModel *m)
+{
+    if (m->done) return set_err(TRM_ERR_STATE, "a TRMTubeModel is single-use%s", "");
+    m->done = 1;
+    if (m->n_frames == 0) return TRM_OK;                 /* no data: returns without flushing (m:274-277) */
+    int err;
+    const int64_t off = 0;
+    const int32_t nf = (int32_t)m->n_frames;
+    TRMBatch *b = TRMBatchCreate(1, &m->ip, 1, &off, &nf, m->precision, &err);
+    if (!b) return err;
+    const size_t n_out = (size_t)b->layout.total_out_samples, n_pcm = (size_t)b->layout.total_pcm_samples;
+    const size_t n_tube = (size_t)b->total_tube_elems;
+    const size_t esz = m->precision == TRM_PRECISION_FP64 ? sizeof(double) : sizeof(float);
+    void *samples = malloc((n_out ? n_out : 1) * esz), *tube = malloc((n_tube ? n_tube : 1) * esz);
+    m->pcm = malloc((n_pcm ? n_pcm : 1) * sizeof(int16_t));
+    m->resampled = malloc((n_out ? n_out : 1) * sizeof(double));
+    m->tube = malloc((n_tube ? n_tube : 1) * sizeof(double));
+    if (!samples || !tube || !m->pcm || !m->resampled || !m->tube) {
+        free(samples); free(tube); TRMBatchFree(b);
+        return set_err(TRM_ERR_NOMEM, "out of memory%s", "");
+    }
+    err = TRMBatchSynthesizeDebug(b, m->frames, m->pcm, samples, tube, m->device);
+    if (err == TRM_OK) {
+        m->numberSamples = b->numberSamples[0];
+        m->maximum = b->maxima[0];
+        if (m->precision == TRM_PRECISION_FP64) {
+            memcpy(m->resampled, samples, (size_t)m->numberSamples * sizeof(double));
+            memcpy(m->tube, tube, (size_t)b->desc[0].n_tube * sizeof(double));
+        } else {
+            for (int32_t i = 0; i < m->numberSamples; i++) m->resampled[i] = ((float *)samples)[i];
+            for (int64_t i = 0; i < b->desc[0].n_tube; i++) m->tube[i] = ((float *)tube)[i];
+        }
+    }
+    free(samples); free(tube);
+    TRMBatchFree(b);
+    return err;
+}
+
+int32_t TRMTubeModelNumberSamples(const TRMTubeModel *m) { return m->numberSamples; }
+double TRMTubeModelMaximumSampleValue(const TRMTubeModel *m) { return m->maximum; }
+const double *TRMTubeModelResampledData(const TRMTubeModel *m) { return m->resampled; }
+const double *TRMTubeModelTubeSignal(const TRMTubeModel *m, int64_t *count)
+{
+    if (count) *count = m->done ? m->derived.tubeSamples : 0;
+    return m->tube;
+}
+
+int64_t TRMTubeModelPullPCM16(const TRMTubeModel *m, int16_t *dst, size_t max_frames, int file_variant)
+{
+    if (!m->done) return set_err(TRM_ERR_STATE, "pull before synthesize%s", "");
+    size_t n = (size_t)m->numberSamples;
+    if (n > max_frames) n = max_frames;
+    const int ch = m->ip.channels == 2 ? 2 : 1;
+    if (!(file_variant && ch == 2)) {
+        if (n) memcpy(dst, m->pcm, n * ch * sizeof(int16_t));          /* scaled on the GPU (m:515-557) */
+        return (int64_t)n;
+    }
+    /* -saveOutputToFile: stereo scaling carries an extra factor 2 (m:382-383) */
+    const double scale = (32767.0 / m->maximum) * db_to_amplitude(m->ip.volume);
+    const double ls = -((m->ip.balance / 2.0) - 0.5) * scale * 2.0, rs = ((m->ip.balance / 2.0) + 0.5) * scale * 2.0;
+    for (size_t i = 0; i < n; i++) {
+        dst[2 * i] = (int16_t)rint(m->resampled[i] * ls);
+        dst[2 * i + 1] = (int16_t)rint(m->resampled[i] * rs);
+    }
+    return (int64_t)n;
+}
+
+static void wr_le16(uint8_t **p, uint16_t v) { (*p)[0] = (uint8_t)v; (*p)[1] = (uint8_t)(v >> 8); *p += 2; }
+static void wr_le32(uint8_t **p, uint32_t v) { wr_le16(p, (uint16_t)v); wr_le16(p, (uint16_t)(v >> 16)); }
+static void wr_be16(uint8_t **p, uint16_t v) { (*p)[0] = (uint8_t)(v >> 8); (*p)[1] = (uint8_t)v; *p += 2; }
+static void wr_be32(uint8_t **p, uint32_t v) { wr_be16(p, (uint16_t)(v >> 16)); wr_be16(p, (uint16_t)v); }
+
+uint8_t *TRMTubeModelGenerateWAVData(const TRMTubeModel *m, size_t *length, int *err)
+{
+    int dummy;
+    if (!err) err = &dummy;
+    if (!m->done) { *err = set_err(TRM_ERR_STATE, "generateWAVData before synthesize%s", ""); return NULL; }
+    if (m->maximum == 0) { *err = set_err(TRM_ERR_SILENT, "maximumSampleValue is 0%s", ""); return NULL; }   /* m:511 */
+    const int ch = m->ip.channels == 2 ? 2 : 1;
+    const size_t data_bytes = (size_t)m->numberSamples * ch * 2;
+    uint8_t *buf = malloc(46 + data_bytes), *p = buf;
+    if (!buf) { *err = set_err(TRM_ERR_NOMEM, "out of memory%s", ""); return NULL; }
+    /* m:562-590: RIFF / WAVE / "fmt " with an 18-byte chunk (extra cbSize = 0) / data */
+    const int frameSize = (int)ceil(m->ip.channels * ((double)16 / 8));
+    const int bytesPerSecond = (int)ceil(m->ip.outputRate * frameSize);
+    wr_be32(&p, 0x52494646u); wr_le32(&p, (uint32_t)(4 + (8 + 18) + (8 + data_bytes))); wr_be32(&p, 0x57415645u);
+    wr_be32(&p, 0x666d7420u); wr_le32(&p, 18); wr_le16(&p, 1); wr_le16(&p, (uint16_t)m->ip.channels);
+    wr_le32(&p, (uint32_t)m->ip.outputRate); wr_le32(&p, (uint32_t)bytesPerSecond);
+    wr_le16(&p, (uint16_t)frameSize); wr_le16(&p, 16); wr_le16(&p, 0);
+    wr_be32(&p, 0x64617461u); wr_le32(&p, (uint32_t)data_bytes);
+    for (size_t i = 0; i < data_bytes / 2; i++) wr_le16(&p, (uint16_t)m->pcm[i]);
+    *length = 46 + data_bytes;
+    *err = TRM_OK;
+    return buf;
+}
+
+/* 80-bit IEEE extended for the AIFF COMM chunk */
+static void wr_ext80(uint8_t **p, double v)
+{
+    int e;
+    double f = frexp(v, &e);                 /* v = f * 2^e, f in [0.5,1) */
+    uint64_t mant = (uint64_t)ldexp(f, 64);
+    wr_be16(p, (uint16_t)(e - 1 + 16383));
+    wr_be32(p, (uint32_t)(mant >> 32));
+    wr_be32(p, (uint32_t)mant);
+}
+
+int TRMTubeModelSaveOutputToFile(const TRMTubeModel *m, const char *path)
+{
+    if (!m->done) return set_err(TRM_ERR_STATE, "saveOutputToFile before synthesize%s", "");
+    const int ch = m->ip.channels == 2 ? 2 : 1;
+    const size_t n = (size_t)m->numberSamples, data_bytes = n * ch * 2;
+    int16_t *pcm = malloc(data_bytes ? data_bytes : 2);
+    if (!pcm) return set_err(TRM_ERR_NOMEM, "out of memory%s", "");
+    TRMTubeModelPullPCM16(m, pcm, n, 1);
+    uint8_t hdr[64], *p = hdr;
+    const int fmt = m->ip.outputFileFormat;
+    const uint32_t rate = (uint32_t)m->ip.outputRate;
+    if (fmt == TRMSoundFileFormat_WAVE) {
+        wr_be32(&p, 0x52494646u); wr_le32(&p, (uint32_t)(36 + data_bytes)); wr_be32(&p, 0x57415645u);
+        wr_be32(&p, 0x666d7420u); wr_le32(&p, 16); wr_le16(&p, 1); wr_le16(&p, (uint16_t)ch);
+        wr_le32(&p, rate); wr_le32(&p, rate * 2u * ch); wr_le16(&p, (uint16_t)(2 * ch)); wr_le16(&p, 16);
+        wr_be32(&p, 0x64617461u); wr_le32(&p, (uint32_t)data_bytes);
+    } else if (fmt == TRMSoundFileFormat_AIFF) {
+        wr_be32(&p, 0x464f524du); wr_be32(&p, (uint32_t)(4 + 26 + 16 + data_bytes)); wr_be32(&p, 0x41494646u);
+        wr_be32(&p, 0x434f4d4du); wr_be32(&p, 18); wr_be16(&p, (uint16_t)ch); wr_be32(&p, (uint32_t)n); wr_be16(&p, 16);
+        wr_ext80(&p, (double)m->ip.outputRate);
+        wr_be32(&p, 0x53534e44u); wr_be32(&p, (uint32_t)(8 + data_bytes)); wr_be32(&p, 0); wr_be32(&p, 0);
+    } else if (fmt == TRMSoundFileFormat_AU) {
+        wr_be32(&p, 0x2e736e64u); wr_be32(&p, 24); wr_be32(&p, (uint32_t)data_bytes); wr_be32(&p, 3);
+        wr_be32(&p, rate); wr_be32(&p, (uint32_t)ch);
+    } else {
+        free(pcm);
+        return set_err(TRM_ERR_PARAM, "unknown output file format%s", "");
+    }
+    FILE *fp = fopen(path, "wb");
+    if (!fp) { free(pcm); return set_err(TRM_ERR_IO, "Can't open output file \"%s\".", path); }
+    int ok = fwrite(hdr, 1, (size_t)(p - hdr), fp) == (size_t)(p - hdr);
+    if (fmt != TRMSoundFileFormat_WAVE) {             /* AU / AIFF are big-endian (m:410-412) */
+        uint8_t *b = (uint8_t *)pcm;
+        for (size_t i = 0; i < data_bytes; i += 2) { uint8_t t = b[i]; b[i] = b[i + 1]; b[i + 1] = t; }
+    }
+    ok = ok && fwrite(pcm, 1, data_bytes, fp) == data_bytes;
+    ok = (fclose(fp) == 0) && ok;
+    free(pcm);
+    return ok ? TRM_OK : set_err(TRM_ERR_IO, "write error on \"%s\"", path);
+}

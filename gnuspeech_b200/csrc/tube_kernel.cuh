@@ -1,0 +1,506 @@
+// tube_kernel.cuh -- the TRM waveguide kernel for sm_100a.
+//
+// Replaces the sample-rate loop of -[TRMTubeModel synthesize]
+// (/root/reference/Frameworks/Tube/TRMTubeModel.m:292-354) and everything it calls:
+// parameter interpolation (m:611-688), frequency()/amplitude() (TRMUtility.m:26-47), tube and
+// frication coefficients (m:712-773), band-pass coefficients/filter (TRMFilters.m:9-29), noise +
+// one-zero low-pass (TRMUtility.m:71-85, TRMFilters.m:81-86), glottal wavetable + 2x oversampling
+// oscillator + 49-tap FIR (TRMWavetable.m:117-195, TRMFIRFilter.m:116-146), source mixing (m:305-337),
+// Kelly-Lochbaum ladder with the velum 3-way junction and nasal branch (m:778-853), mouth/nose
+// reflection + radiation filters (TRMFilters.m:34-60) and the throat low-pass (TRMFilters.m:64-77).
+//
+// Mapping (BASELINE.json north_star): one utterance per HALF-WARP, two per warp.  The path has two
+// kinds of work and each gets the lane mapping that suits it, alternating every 16 samples:
+//
+//   time-parallel phases  (lane = sample t of the block): everything that does not depend on the tube
+//       state -- transcendentals, junction coefficients, taps, band-pass coefficients, jump-ahead
+//       noise, table look-ups, FIR, source mixing.  Results go to shared memory.
+//   section-parallel phase (lane = scattering junction): the strictly sequential ladder.  Lane j owns
+//       the two waves incident on junction j (registers); after each sample the outgoing waves move to
+//       the neighbouring junctions with __shfl_sync (3 shuffles: right-going, left-going, velum port).
+//
+//   lane: 0 S1|S2 (+glottis end)  1 S2|S3  2 S3|S4  3 S4|S5|N1 (3-way)  4 S5|S6  5 S6|S7 (k=0)
+//         6 S7|S8  7 S8|S9  8 S9|S10  9 mouth  10 N1|N2  11 N2|N3  12 N3|N4  13 N4|N5  14 N5|N6  15 nose
+//
+// Control frames (128 B each) are staged into shared memory by TMA bulk copies
+// (cp.async.bulk + mbarrier), double-buffered FRAME_CHUNK frames ahead of the sample loop.
+// Tube-rate output is gathered in shared memory and stored with 128-bit vector stores.
+//
+// Real = double : FP64 conformance mode, compile this TU with -fmad=false (reference build has no FMA).
+// Real = float  : FP32 fast mode: state/signal/coefficients FP32; parameter interpolation, pitch -> f0 ->
+//                 table position, the glottal-closure decision rint(ax*tnDelta) and the noise MCG stay
+//                 FP64 / integer.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "kernel_args.h"
+#include "trm_cuda.h"
+
+namespace trm {
+
+constexpr double TWO_M44 = 5.684341886080801486968994140625e-14;   // 2^-44 exactly
+
+// Per-TU constant tables (uploaded by the TU's upload function).
+static __constant__ double c_fir_d[FIR_TAPS];
+static __constant__ float c_fir_f[FIR_TAPS];
+static __constant__ unsigned long long c_noise_pow[TRM_NOISE_JUMP + 1];
+
+template <typename R> struct FirCoef;
+template <> struct FirCoef<double> { static __device__ __forceinline__ double at(int i) { return c_fir_d[i]; } };
+template <> struct FirCoef<float> { static __device__ __forceinline__ float at(int i) { return c_fir_f[i]; } };
+
+template <typename R>
+struct alignas(16) UttSmem {
+    // control-frame staging (TMA destination), double-buffered
+    double FR[2][FRAME_CHUNK][16];
+    unsigned long long mbar[2];
+    // P (interpolated parameters, written by the parameter lanes, read by phase A1) is dead once A1 has
+    // loaded it, so the per-sample vectors produced later in the block share its storage.
+    union {
+        double P[TB][17];
+        struct {
+            double INC[TB];                  // oscillator increment (f0/2)*basicIncrement
+            R U[TB], G[TB], BT[TB];          // band-pass: alpha*(x[n]-x[n-2]), gamma, beta
+            R THX[TB];                       // ta0 * (pulse * VT_SCALE)
+            R OUTM[TB], OUTN[TB];            // mouth / nose radiation outputs
+            R YB[TB];                        // finished tube-rate samples, for the vector store
+        } v;
+    } a;
+    R KQ[TB][13];                            // junction coefficient per lane (cols 0..10), alphaU (11)
+    R TAPV[TB][9];                           // col 0: glottal input; cols 1..8: frication taps FC1..FC8
+    R HE[FIR_HIST + TB], HO[FIR_HIST + TB];  // oscillator history, even / odd 2x-rate samples
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA bulk copy (global -> shared)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(void *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(void *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(void *bar, uint32_t parity)
+{
+    // try_wait suspends in hardware; the bound turns a lost copy into a trap instead of a hang
+    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
+        if (spin > (1u << 24)) __trap();
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, void *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// math helpers
+// ---------------------------------------------------------------------------------------------
+// amplitude(): TRMUtility.m:26-41.  Always evaluated in double (it is off the serial chain and the
+// glottal-closure decision rint(ax*tnDelta) must not move).
+__device__ __forceinline__ double amplitude_db(double dB)
+{
+    double x = dB - 60.0;
+    if (x <= -60.0) return 0.0;
+    if (x >= 0.0) return 1.0;
+    return exp10(x / 20.0);
+}
+template <typename R> __device__ __forceinline__ R amplitude_r(double dB);
+template <> __device__ __forceinline__ double amplitude_r<double>(double dB) { return amplitude_db(dB); }
+template <> __device__ __forceinline__ float amplitude_r<float>(double dB)
+{
+    float x = (float)(dB - 60.0);
+    if (x <= -60.0f) return 0.0f;
+    if (x >= 0.0f) return 1.0f;
+    return exp10f(x / 20.0f);
+}
+
+template <typename R> __device__ __forceinline__ R r_tan(R x);
+template <> __device__ __forceinline__ double r_tan<double>(double x) { return tan(x); }
+template <> __device__ __forceinline__ float r_tan<float>(float x) { return tanf(x); }
+template <typename R> __device__ __forceinline__ R r_cos(R x);
+template <> __device__ __forceinline__ double r_cos<double>(double x) { return cos(x); }
+template <> __device__ __forceinline__ float r_cos<float>(float x) { return cosf(x); }
+
+template <typename R> __device__ __forceinline__ R shfl16(unsigned mask, R v, int src)
+{
+    return __shfl_sync(mask, v, src, 16);
+}
+
+// Glottal table value at integer index i for the current closure point (TRMWavetable.m:78-102 init,
+// :117-162 update, vDSP order 1 - (j*j)*(1/(L*L))).  The reference rewrites the table every sample; the
+// table is a pure function of the current amplitude, so it is evaluated on look-up instead.
+template <typename R>
+__device__ __forceinline__ R table_value(const double *__restrict__ base, int i, int div1, int div2, double newDiv2,
+                                         R scale, bool pulse)
+{
+    if (!pulse || i < div1 || i >= div2) return (R)__ldg(base + i);
+    if ((double)i >= newDiv2) return (R)0;
+    R j = (R)(i - div1);
+    return (R)1 - ((j * j) * scale);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+template <typename R>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8) tube_kernel(TubeArgs args)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int half = lane >> 4, hl = lane & 15;
+    const unsigned hmask = 0xFFFFu << (half * 16);
+    const int slot = (blockIdx.x * WARPS_PER_CTA + warp) * 2 + half;
+    if (slot >= args.n_utt) return;                       // the whole half-warp leaves together
+    UttSmem<R> &S = reinterpret_cast<UttSmem<R> *>(smem_raw)[warp * 2 + half];
+
+    const int u = args.order ? args.order[slot] : slot;
+    const trm_cuda_utterance *__restrict__ D = args.desc + u;
+    const int64_t n_tube = D->n_tube;
+    if (n_tube <= 0) return;
+    const int n_frames = D->n_frames;
+    const int cp = D->controlPeriod;
+    const double *__restrict__ F = args.frames + D->frame_offset * 16;
+    R *__restrict__ out = reinterpret_cast<R *>(args.tube) + D->tube_offset;
+    const double *__restrict__ wt_base = args.wavetables + (size_t)D->voice * TRM_TABLE_LENGTH;
+
+    // ---- per-utterance constants -------------------------------------------------------------
+    const bool pulse_wave = D->waveform == 0;
+    const bool modulation = D->usesModulation != 0;
+    const int div1 = D->div1, div2 = D->div2;
+    const double tnDelta = D->tnDelta;
+    const double basicIncrement = D->basicIncrement;
+    const R sr = (R)D->sampleRate;
+    const R apScale2 = (R)D->apScale2, nr1sq = (R)D->nr1sq;
+    const R bf = (R)D->breathinessFactor, one_minus_bf = (R)(1.0 - D->breathinessFactor);
+    const R cmf = (R)D->crossmixFactor;
+    const R ta0 = (R)D->ta0, tb1 = (R)D->tb1, throatGain = (R)D->throatGain;
+    const R d = (R)D->dampingFactor;
+
+    // ---- lane roles for the section-parallel phase ----------------------------------------------
+    const int role = (hl == 3) ? 1 : ((hl == 9 || hl == 15) ? 2 : 0);
+    const bool kvar = (hl <= 10) && (hl != 5);
+    const R kconst = (hl >= 11) ? (R)D->nasal_coeff[hl - 11] : (R)0;
+    const bool has_tap = (hl >= 1 && hl <= 8);
+    const int tap_col = (hl <= 8) ? hl : 0;
+    const int srcA = hl - 1, srcB = hl + 1, srcC = (hl == 3) ? 10 : 3;
+    const double *fc = (hl == 9) ? D->mouth : D->nose;
+    const R f_a10 = (R)fc[0], f_b11 = (R)fc[1], f_a20 = (R)fc[2], f_a21 = (R)fc[3], f_b21 = (R)fc[4];
+
+    // ---- shared-memory init + first two frame chunks ---------------------------------------------
+    {
+        // zero everything the block phases may read before they first write it (not the TMA
+        // destination / mbarriers: those are only ever written through the async proxy / mbarrier ops)
+        uint32_t *w = reinterpret_cast<uint32_t *>(&S.a);
+        constexpr int NW = (int)((sizeof(UttSmem<R>) - offsetof(UttSmem<R>, a)) / 4);
+        for (int i = hl; i < NW; i += 16) w[i] = 0u;
+    }
+    __syncwarp(hmask);
+    const int n_chunks = (n_frames + FRAME_CHUNK - 1) / FRAME_CHUNK;
+    if (hl == 0) {
+        mbar_init(&S.mbar[0], 1);
+        mbar_init(&S.mbar[1], 1);
+        mbar_fence_init();
+    }
+    __syncwarp(hmask);
+    if (hl == 0) {
+        for (int c = 0; c < 2 && c < n_chunks; ++c) {
+            int cnt = min(FRAME_CHUNK, n_frames - c * FRAME_CHUNK);
+            mbar_expect_tx(&S.mbar[c], (uint32_t)cnt * 128u);
+            tma_bulk_g2s(&S.FR[c][0][0], F + (size_t)c * FRAME_CHUNK * 16, (uint32_t)cnt * 128u, &S.mbar[c]);
+        }
+    }
+    mbar_wait(&S.mbar[0], 0);
+
+    // ---- running state ---------------------------------------------------------------------------
+    // parameter lane p = hl (TRMTubeModel.m:611-688)
+    double p_cur = 0.0, p_delta = 0.0, p_next = S.FR[0][0][hl];
+    int f_idx = 0, jc = 0;                 // current interval, sample inside it
+    // oscillator position (all lanes carry the same value)
+    double pos = 0.0;
+    // noise MCG: state after the previous block's last draw; per-lane jump multipliers
+    unsigned long long kb = args.noise_k0;
+    const unsigned long long MASK44 = (1ull << 44) - 1ull;
+    const unsigned long long pw0 = c_noise_pow[hl], pw1 = c_noise_pow[hl + 1], pwB = c_noise_pow[TB];
+    // band-pass / throat memories (replicated in all lanes), x[n-1], x[n-2] of the band-pass input
+    R y1 = 0, y2 = 0, thy = 0, xm1 = 0, xm2 = 0;
+    // junction state: waves incident on this lane's junction
+    R a = 0, b = 0, c3 = 0, s1bot = 0, ry = 0, rx = 0, rY = 0;
+
+    for (int64_t n0 = 0; n0 < n_tube; n0 += TB) {
+        const int nb = (int)min((int64_t)TB, n_tube - n0);
+        const bool active = hl < nb;
+
+        // =========================================================================================
+        // S0  parameter interpolation, lane = parameter (m:611-688): cur = prev; delta = (next-prev)/cp;
+        //     one add per sample AFTER the sample is used.
+        // =========================================================================================
+        for (int s = 0; s < nb; ++s) {
+            if (jc == 0) {
+                const int fn = f_idx + 1;                    // frame that ends this interval
+                const int ch = fn / FRAME_CHUNK;
+                if ((fn % FRAME_CHUNK) == 0) {
+                    // entering chunk ch: all lanes are done with chunk ch-1, whose buffer is refilled
+                    __syncwarp(hmask);
+                    if (hl == 0 && ch + 1 < n_chunks) {
+                        const int cn = ch + 1;
+                        int cnt = min(FRAME_CHUNK, n_frames - cn * FRAME_CHUNK);
+                        mbar_expect_tx(&S.mbar[cn & 1], (uint32_t)cnt * 128u);
+                        tma_bulk_g2s(&S.FR[cn & 1][0][0], F + (size_t)cn * FRAME_CHUNK * 16, (uint32_t)cnt * 128u,
+                                     &S.mbar[cn & 1]);
+                    }
+                    mbar_wait(&S.mbar[ch & 1], (uint32_t)((ch >> 1) & 1));
+                }
+                const double nxt = S.FR[ch & 1][fn % FRAME_CHUNK][hl];
+                p_cur = p_next;
+                p_delta = (nxt - p_cur) / (double)cp;
+                p_next = nxt;
+            }
+            S.a.P[s][hl] = p_cur;
+            p_cur += p_delta;
+            if (++jc == cp) { jc = 0; ++f_idx; }
+        }
+        __syncwarp(hmask);
+
+        // =========================================================================================
+        // A1  lane = sample t: conversions and coefficients (m:294-300, 712-773; TRMFilters.m:9-17)
+        // =========================================================================================
+        double prm[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) prm[q] = S.a.P[hl][q];
+        __syncwarp(hmask);                                  // P is dead from here: its storage is reused
+
+        // pitch -> f0 -> increment: always double
+        const double f0 = 220.0 * exp2((prm[0] + 3.0) / 12.0);
+        const double inc = (f0 / 2.0) * basicIncrement;
+        const double ax_d = amplitude_db(prm[1]);
+        const R ax = (R)ax_d;
+        const R ah1 = amplitude_r<R>(prm[2]);
+        const R fa = amplitude_r<R>(prm[3]);
+        S.a.v.INC[hl] = inc;
+
+        {
+            R r2[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { R r = (R)prm[7 + q]; r2[q] = r * r; }
+            R kk[8];
+#pragma unroll
+            for (int q = 0; q < 7; ++q) kk[q] = (r2[q] - r2[q + 1]) / (r2[q] + r2[q + 1]);
+            kk[7] = (r2[7] - apScale2) / (r2[7] + apScale2);
+            const R vel = (R)prm[15];
+            const R v2 = vel * vel;
+            const R sum = (R)2 / ((r2[3] + r2[3]) + v2);
+            const R aL = sum * r2[3], aU = sum * v2;
+            const R nc1 = (v2 - nr1sq) / (v2 + nr1sq);
+            R *kq = S.KQ[hl];
+            kq[0] = kk[0]; kq[1] = kk[1]; kq[2] = kk[2]; kq[3] = aL; kq[4] = kk[3];
+            kq[6] = kk[4]; kq[7] = kk[5]; kq[8] = kk[6]; kq[9] = kk[7]; kq[10] = nc1; kq[11] = aU;
+        }
+        {
+            // frication taps (m:748-765)
+            const int ipos = (int)prm[4];
+            const R comp = (R)(prm[4] - (double)ipos);
+            const R rem = (R)1 - comp;
+            R *tv = S.TAPV[hl];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                R v = (R)0;
+                if (q == ipos) v = rem * fa;
+                else if (ipos >= 0 && q == ipos + 1) v = comp * fa;
+                tv[q + 1] = v;
+            }
+        }
+        R bp_alpha;
+        {
+            // band-pass coefficients (TRMFilters.m:9-17)
+            const R pi = (R)3.14159265358979323846;
+            const R tanv = r_tan<R>((pi * (R)prm[6]) / sr);
+            const R cosv = r_cos<R>((((R)2 * pi) * (R)prm[5]) / sr);
+            const R beta = ((R)1 - tanv) / ((R)2 * ((R)1 + tanv));
+            S.a.v.BT[hl] = beta;
+            S.a.v.G[hl] = ((R)0.5 + beta) * cosv;
+            bp_alpha = ((R)0.5 - beta) / (R)2;
+        }
+        // noise (TRMUtility.m:71-85 as the equivalent MCG mod 2^44) + one-zero low-pass (TRMFilters.m:81-86)
+        R lp_noise;
+        {
+            const unsigned long long kt = (kb * pw1) & MASK44, kp = (kb * pw0) & MASK44;
+            const double nz = (double)(long long)kt * TWO_M44 - 0.5;
+            const double nzp = (n0 + hl == 0) ? 0.0 : ((double)(long long)kp * TWO_M44 - 0.5);
+            lp_noise = (R)(nz + nzp);
+            kb = (kb * pwB) & MASK44;
+        }
+        __syncwarp(hmask);
+
+        // =========================================================================================
+        // S1  oscillator position (TRMWavetable.m:165-168, 28-34), sequential, replicated in all lanes
+        // =========================================================================================
+        double p0 = 0.0, p1 = 0.0;
+        for (int s = 0; s < nb; ++s) {
+            const double di = S.a.v.INC[s];
+            pos = pos + di;
+            if (pos > 511.0) pos -= 512.0;
+            if (s == hl) p0 = pos;
+            pos = pos + di;
+            if (pos > 511.0) pos -= 512.0;
+            if (s == hl) p1 = pos;
+        }
+
+        // =========================================================================================
+        // A2  lane = sample t: table look-ups, FIR, source mixing (TRMWavetable.m:174-195, m:305-337)
+        // =========================================================================================
+        {
+            const double newDiv2 = (double)div2 - rint(ax_d * tnDelta);
+            const double Ld = newDiv2 - (double)div1;
+            const R scale = (R)1 / ((R)Ld * (R)Ld);
+            int lo = ((int)p0) & (TRM_TABLE_LENGTH - 1);
+            int hi = lo + 1; if (hi > 511) hi -= 512;
+            R w0 = table_value<R>(wt_base, lo, div1, div2, newDiv2, scale, pulse_wave);
+            R w1 = table_value<R>(wt_base, hi, div1, div2, newDiv2, scale, pulse_wave);
+            S.HE[FIR_HIST + hl] = w0 + ((R)(p0 - (double)lo) * (w1 - w0));
+            lo = ((int)p1) & (TRM_TABLE_LENGTH - 1);
+            hi = lo + 1; if (hi > 511) hi -= 512;
+            w0 = table_value<R>(wt_base, lo, div1, div2, newDiv2, scale, pulse_wave);
+            w1 = table_value<R>(wt_base, hi, div1, div2, newDiv2, scale, pulse_wave);
+            S.HO[FIR_HIST + hl] = w0 + ((R)(p1 - (double)lo) * (w1 - w0));
+        }
+        __syncwarp(hmask);
+        R sig;
+        {
+            // 49-tap FIR at the odd sample, newest -> oldest from 0.0 (TRMFIRFilter.m:116-131)
+            R acc = (R)0;
+            const R *ho = &S.HO[FIR_HIST + hl], *he = &S.HE[FIR_HIST + hl];
+#pragma unroll
+            for (int q = 0; q < FIR_HIST; ++q) {
+                acc += ho[-q] * FirCoef<R>::at(2 * q);
+                acc += he[-q] * FirCoef<R>::at(2 * q + 1);
+            }
+            acc += ho[-FIR_HIST] * FirCoef<R>::at(2 * FIR_HIST);
+            const R pulse0 = acc;
+            const R pulsed_noise = lp_noise * pulse0;
+            const R pulse = ax * ((pulse0 * one_minus_bf) + (pulsed_noise * bf));
+            if (modulation) {
+                R crossmix = ax * cmf;
+                crossmix = (crossmix < (R)1) ? crossmix : (R)1;
+                sig = (pulsed_noise * crossmix) + (lp_noise * ((R)1 - crossmix));
+            } else
+                sig = lp_noise;
+            S.TAPV[hl][0] = (pulse + (ah1 * sig)) * (R)0.125;
+            S.a.v.THX[hl] = ta0 * (pulse * (R)0.125);
+        }
+        {
+            // band-pass feed-forward part alpha*(x[n]-x[n-2]); x[n-2] comes from two lanes down or the carry
+            R x2 = shfl16<R>(hmask, sig, hl - 2);
+            if (hl == 0) x2 = xm2;
+            if (hl == 1) x2 = xm1;
+            S.a.v.U[hl] = bp_alpha * (sig - x2);
+            const int last = nb - 1;
+            const R l1 = shfl16<R>(hmask, sig, last);
+            const R l2 = shfl16<R>(hmask, sig, last > 0 ? last - 1 : 0);
+            xm2 = (last > 0) ? l2 : xm1;
+            xm1 = l1;
+        }
+        __syncwarp(hmask);
+        {
+            // slide the oscillator history down by one block (rows TB.. -> 0..)
+            const R e0 = S.HE[TB + hl], o0 = S.HO[TB + hl];
+            const R e1 = (hl < FIR_HIST - TB + 0) ? S.HE[2 * TB + hl] : (R)0;
+            const R o1 = (hl < FIR_HIST - TB + 0) ? S.HO[2 * TB + hl] : (R)0;
+            __syncwarp(hmask);
+            S.HE[hl] = e0; S.HO[hl] = o0;
+            if (hl < FIR_HIST - TB) { S.HE[TB + hl] = e1; S.HO[TB + hl] = o1; }
+        }
+
+        // =========================================================================================
+        // B   lane = junction: band-pass / throat recursions + the Kelly-Lochbaum ladder (m:778-853)
+        // =========================================================================================
+        R th_mine = (R)0;
+        for (int s = 0; s < nb; ++s) {
+            // frication band-pass recursion (TRMFilters.m:19-29)
+            const R fr = (R)2 * ((S.a.v.U[s] + (S.a.v.G[s] * y1)) - (S.a.v.BT[s] * y2));
+            y2 = y1; y1 = fr;
+            // throat low-pass (TRMFilters.m:72-77)
+            const R th = S.a.v.THX[s] + (tb1 * thy);
+            thy = th;
+            if (s == hl) th_mine = th;
+
+            const R k = kvar ? S.KQ[s][hl] : kconst;
+            const R inj = S.TAPV[s][tap_col];
+            R Rr, Lo, X3;
+            if (role == 0) {
+                const R delta = k * (a - b);
+                Rr = (a + delta) * d;
+                if (has_tap) Rr = Rr + (inj * fr);
+                Lo = (b + delta) * d;
+                X3 = Lo;
+            } else if (role == 1) {
+                const R aU = S.KQ[s][11];
+                const R p = ((k * a) + (k * b)) + (aU * c3);
+                Lo = (p - a) * d;
+                Rr = ((p - b) * d) + (inj * fr);
+                X3 = (p - c3) * d;
+            } else {
+                const R x = k * a;
+                const R refl = (f_a10 * x) - (f_b11 * ry);
+                ry = refl;
+                Lo = d * refl;
+                const R xr = ((R)1 + k) * a;
+                const R rad = ((f_a20 * xr) + (f_a21 * rx)) - (f_b21 * rY);
+                rx = xr; rY = rad;
+                if (hl == 9) S.a.v.OUTM[s] = rad; else S.a.v.OUTN[s] = rad;
+                Rr = (R)0; X3 = (R)0;
+            }
+            const R nA = shfl16<R>(hmask, Rr, srcA);
+            const R nB = shfl16<R>(hmask, Lo, srcB);
+            const R nC = shfl16<R>(hmask, X3, srcC);
+            if (hl == 0) { a = (s1bot * d) + inj; s1bot = Lo; }
+            else if (hl == 10) a = nC;
+            else a = nA;
+            b = nB;
+            if (hl == 3) c3 = nC;
+        }
+        __syncwarp(hmask);
+
+        // =========================================================================================
+        // A4  lane = sample t: sum mouth + nose + throat (m:835,849,341); 128-bit coalesced store
+        // =========================================================================================
+        if (active) S.a.v.YB[hl] = (S.a.v.OUTM[hl] + S.a.v.OUTN[hl]) + (th_mine * throatGain);
+        __syncwarp(hmask);
+        {
+            constexpr int VEC = 16 / (int)sizeof(R);          // elements per 128-bit store
+            R *dst = out + n0;                                // n0 and tube_offset are multiples of 16
+            if (nb == TB) {
+                if (hl < TB / VEC) reinterpret_cast<float4 *>(dst)[hl] = reinterpret_cast<const float4 *>(S.a.v.YB)[hl];
+            } else if (active) {
+                dst[hl] = S.a.v.YB[hl];
+            }
+        }
+        __syncwarp(hmask);                                    // v.* is reused as P by the next block
+    }
+}
+
+}  // namespace trm

@@ -1,0 +1,229 @@
+/*
+ * trm.h -- C API of the B200-native Tube Resonance Model (TRM) synthesizer.
+ *
+ * Drop-in boundary for the reference's Tube.framework public classes
+ * (/root/reference/Frameworks/Tube/Tube.h:7-10):
+ *
+ *   TRMInputParameters   <- TRMInputParameters.h:24-56   (utterance-rate "voice" parameters)
+ *   TRMParameters        <- TRMParameters.h:7-19         (one 250 Hz control frame)
+ *   TRMDataList          <- TRMDataList.h:8-18           (parameters + growing frame list, file parser)
+ *   TRMTubeModel         <- TRMTubeModel.h:29-40         (-initWithInputData:, -synthesize,
+ *                                                         -generateWAVData, -saveOutputToFile:error:)
+ *
+ * plus a batched entry point (TRMBatch*) that the reference does not have: many independent
+ * utterances in one call, sharded over the GPUs of one box.
+ *
+ * All synthesis runs on the GPU through libtrm_cuda (include/trm_cuda.h).  There is NO CPU
+ * fallback: if CUDA is unavailable every synthesize call returns TRM_ERR_CUDA.
+ *
+ * Host code is C99.  Nothing in these signatures is a torch or C++ type.
+ */
+#ifndef TRM_H
+#define TRM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Oropharynx regions / nasal sections (TRMTubeModel.h:7-25) */
+#define TRM_TOTAL_REGIONS          8
+#define TRM_TOTAL_NASAL_SECTIONS   6
+
+/* TRMInputParameters.h:7-21 */
+enum { TRMSoundFileFormat_AU = 0, TRMSoundFileFormat_AIFF = 1, TRMSoundFileFormat_WAVE = 2 };
+enum { TRMWaveFormType_Pulse = 0, TRMWaveFormType_Sine = 1 };
+
+/* Error codes.  The reference returns nil / NO and prints to stderr (TRMTubeModel.m:204-207,
+ * TRMFIRFilter.m:49-51, TRMDataList.m:45-57) or asserts (TRMTubeModel.m:417,511). */
+enum {
+    TRM_OK               = 0,
+    TRM_ERR_TUBE_LENGTH  = -1,   /* length <= 0                     (TRMTubeModel.m:204-207)            */
+    TRM_ERR_FIR          = -2,   /* FIR design failure              (TRMFIRFilter.m:49-51)              */
+    TRM_ERR_NOMEM        = -3,   /* allocation failure              (TRMWavetable.m:65-68)              */
+    TRM_ERR_PARAM        = -4,   /* parameters outside what the path defines (see DESIGN.md "deviations")*/
+    TRM_ERR_CUDA         = -5,   /* no usable CUDA device / CUDA runtime error; trm_cuda_last_error()   */
+    TRM_ERR_IO           = -6,   /* file open / read / write failure (TRMDataList.m:45-49)              */
+    TRM_ERR_STATE        = -7,   /* call order: pull before synthesize, synthesize twice (single-use)   */
+    TRM_ERR_SILENT       = -8    /* maximumSampleValue == 0: reference asserts (TRMTubeModel.m:511)     */
+};
+
+/* Arithmetic mode of the GPU path (BASELINE.json north_star). */
+enum {
+    TRM_PRECISION_FP64 = 0,   /* conformance: every value double, no FMA contraction                   */
+    TRM_PRECISION_FP32 = 1    /* fast: FP32 state/signal, FP64 pitch->f0->phase, integer noise         */
+};
+
+/* TRMInputParameters.h:26-54.  Field order follows the reference declaration. */
+typedef struct TRMInputParameters {
+    int32_t outputFileFormat;          /* TRMSoundFileFormat_*                                          */
+    float   outputRate;                /* output sample rate (22050, 44100 Hz)                          */
+    float   controlRate;               /* 1.0-1000.0 input tables/second (Hz)                           */
+    double  volume;                    /* master volume (0 - 60 dB)                                     */
+    int32_t channels;                  /* # of sound output channels (1, 2)                             */
+    double  balance;                   /* stereo balance (-1 to +1)                                     */
+    int32_t waveform;                  /* TRMWaveFormType_*                                             */
+    double  tp;                        /* % glottal pulse rise time                                     */
+    double  tnMin;                     /* % glottal pulse fall time minimum                             */
+    double  tnMax;                     /* % glottal pulse fall time maximum                             */
+    double  breathiness;               /* % glottal source breathiness                                  */
+    double  length;                    /* nominal tube length (10 - 20 cm)                              */
+    double  temperature;               /* tube temperature (25 - 40 C)                                  */
+    double  lossFactor;                /* junction loss factor in (0 - 5 %)                             */
+    double  apScale;                   /* aperture scl. radius (3.05 - 12 cm)                           */
+    double  mouthCoef;                 /* mouth aperture coefficient                                    */
+    double  noseCoef;                  /* nose aperture coefficient                                     */
+    double  noseRadius[TRM_TOTAL_NASAL_SECTIONS]; /* fixed nose radii (0 - 3 cm); [0] is never read     */
+    double  throatCutoff;              /* throat lp cutoff (50 - nyquist Hz)                            */
+    double  throatVol;                 /* throat volume (0 - 48 dB)                                     */
+    int32_t usesModulation;            /* pulse mod. of noise                                           */
+    double  mixOffset;                 /* noise crossmix offset (30 - 60 dB)                            */
+} TRMInputParameters;
+
+/* TRMParameters.h:9-17 -- 16 doubles, 128 bytes, the unit the GPU stages with bulk copies. */
+typedef struct TRMParameters {
+    double glottalPitch;
+    double glottalVolume;
+    double aspirationVolume;
+    double fricationVolume;
+    double fricationPosition;
+    double fricationCenterFrequency;
+    double fricationBandwidth;
+    double radius[TRM_TOTAL_REGIONS];
+    double velum;
+} TRMParameters;
+
+/* Male-voice defaults of Monet (MMSynthesisParameters.m:160-191), mono, `outputRate` as given. */
+void TRMInputParametersSetDefaults(TRMInputParameters *ip, float outputRate);
+
+/* Values derived in -initWithInputData: (TRMTubeModel.m:196-203) and the SRC set-up
+ * (TRMSampleRateConverter.m:69-106), available without running anything. */
+typedef struct TRMDerivedValues {
+    int32_t  controlPeriod;
+    int32_t  sampleRate;
+    double   actualTubeLength;
+    int32_t  padSize;
+    uint32_t timeRegisterIncrement;
+    int64_t  tubeSamples;        /* (n_frames-1)*controlPeriod                                          */
+    int32_t  numberSamples;      /* output-rate frames the converter will emit for n_frames frames      */
+} TRMDerivedValues;
+int TRMDeriveValues(const TRMInputParameters *ip, size_t n_frames, TRMDerivedValues *out);
+
+/* ---------------------------------------------------------------------------------------------
+ * TRMDataList  (TRMDataList.h:8-18; TRMSynthesizer.m:98-106 for add/removeAll)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct TRMDataList TRMDataList;
+
+TRMDataList *TRMDataListCreate(void);                                  /* -init                          */
+TRMDataList *TRMDataListCreateWithContentsOfFile(const char *path, int *err); /* -initWithContentsOfFile: */
+void         TRMDataListFree(TRMDataList *list);
+TRMInputParameters *TRMDataListInputParameters(TRMDataList *list);     /* .inputParameters               */
+int          TRMDataListAddParameters(TRMDataList *list, const TRMParameters *frame); /* [values addObject:] */
+int          TRMDataListAddParametersArray(TRMDataList *list, const TRMParameters *frames, size_t n);
+void         TRMDataListRemoveAllParameters(TRMDataList *list);        /* [values removeAllObjects]      */
+size_t       TRMDataListCount(const TRMDataList *list);
+const TRMParameters *TRMDataListValues(const TRMDataList *list);
+/* Writes the list in the reference's text input format (MMSynthesisParameters.m:278-310,
+ * TRMParameters.m:26-45) -- what Monet dumps to /tmp/Monet.parameters. */
+int          TRMDataListWriteToFile(const TRMDataList *list, const char *path);
+
+/* ---------------------------------------------------------------------------------------------
+ * TRMTubeModel  (TRMTubeModel.h:29-40).  Single-use like the reference (TRMSynthesizer.m:120).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct TRMTubeModel TRMTubeModel;
+
+/* -initWithInputData: (TRMTubeModel.m:186-260).  Copies parameters and frames.  NULL on error, *err set. */
+TRMTubeModel *TRMTubeModelCreate(const TRMDataList *inputData, int *err);
+void          TRMTubeModelFree(TRMTubeModel *model);
+int           TRMTubeModelSetPrecision(TRMTubeModel *model, int precision);   /* default TRM_PRECISION_FP64 */
+int           TRMTubeModelSetDevice(TRMTubeModel *model, int device);         /* default 0                  */
+
+/* -synthesize (TRMTubeModel.m:272-361): whole utterance, blocking. */
+int           TRMTubeModelSynthesize(TRMTubeModel *model);
+
+/* sampleRateConverter.numberSamples / .maximumSampleValue / .resampledData (TRMSampleRateConverter.h:13-17) */
+int32_t       TRMTubeModelNumberSamples(const TRMTubeModel *model);
+double        TRMTubeModelMaximumSampleValue(const TRMTubeModel *model);
+const double *TRMTubeModelResampledData(const TRMTubeModel *model);
+/* tube-rate signal before the converter (what -synthesize hands to dataFill:, TRMTubeModel.m:346) */
+const double *TRMTubeModelTubeSignal(const TRMTubeModel *model, int64_t *count);
+void          TRMTubeModelGetDerivedValues(const TRMTubeModel *model, TRMDerivedValues *out);
+
+/* Scaled 16-bit PCM, host endian; channels interleaved (TRMTubeModel.m:515-557 scaling = the WAV variant;
+ * file_variant != 0 selects the x2 stereo scaling of -saveOutputToFile:, TRMTubeModel.m:382-383).
+ * Returns the number of sample frames written or a negative error. */
+int64_t       TRMTubeModelPullPCM16(const TRMTubeModel *model, int16_t *dst, size_t max_frames, int file_variant);
+
+/* -generateWAVData (TRMTubeModel.m:509-593): malloc'ed RIFF/WAVE bytes (18-byte fmt chunk as the reference
+ * writes it); free with TRMFree. */
+uint8_t      *TRMTubeModelGenerateWAVData(const TRMTubeModel *model, size_t *length, int *err);
+/* -saveOutputToFile:error: (TRMTubeModel.m:365-490): AU / AIFF (big-endian) or WAVE by outputFileFormat. */
+int           TRMTubeModelSaveOutputToFile(const TRMTubeModel *model, const char *path);
+void          TRMFree(void *p);
+
+/* ---------------------------------------------------------------------------------------------
+ * Batched entry point (new).  n independent utterances; utterance u uses ip[u] (or ip[0] when
+ * shared_parameters != 0) and frames[frame_offset[u] .. frame_offset[u]+n_frames[u]).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct TRMBatch TRMBatch;
+
+typedef struct TRMBatchLayout {
+    int64_t total_frames;        /* frames consumed from the input array                                */
+    int64_t total_pcm_samples;   /* int16 elements needed in the PCM output buffer                      */
+    int64_t total_out_samples;   /* elements needed in the optional float/double output buffer          */
+    double  audio_seconds;       /* sum over utterances of (n_frames-1)/controlRate                     */
+    int64_t tube_samples;        /* sum of tube-rate samples                                            */
+    int64_t out_samples;         /* sum of numberSamples                                                */
+} TRMBatchLayout;
+
+/* Plans the batch: validates parameters, derives per-utterance constants, sizes and offsets. */
+TRMBatch *TRMBatchCreate(int n_utterances, const TRMInputParameters *ip, int shared_parameters,
+                         const int64_t *frame_offset, const int32_t *n_frames, int precision, int *err);
+void      TRMBatchFree(TRMBatch *batch);
+void      TRMBatchGetLayout(const TRMBatch *batch, TRMBatchLayout *layout);
+/* per-utterance results / placement; valid after TRMBatchCreate (offsets, counts) and after synthesis (max) */
+const int32_t *TRMBatchNumberSamples(const TRMBatch *batch);       /* [n] output frames                   */
+const int64_t *TRMBatchPCMOffsets(const TRMBatch *batch);          /* [n] element offset into pcm_out     */
+const int64_t *TRMBatchOutOffsets(const TRMBatch *batch);          /* [n] element offset into samples_out */
+const double  *TRMBatchMaximumSampleValues(const TRMBatch *batch); /* [n]                                 */
+
+/* Synthesizes the whole batch on `n_devices` GPUs (devices[] lists CUDA ordinals; NULL = 0..n-1), host
+ * buffers in and out.  frames: TRMParameters array in host memory (pinned memory from TRMHostAlloc makes
+ * the copies asynchronous).  pcm_out: int16, TRMBatchLayout.total_pcm_samples elements, may be NULL.
+ * samples_out: unscaled output-rate samples, double (FP64 mode) or float (FP32 mode),
+ * total_out_samples elements, may be NULL.  Blocking. */
+int TRMBatchSynthesize(TRMBatch *batch, const TRMParameters *frames, int16_t *pcm_out, void *samples_out,
+                       const int *devices, int n_devices);
+
+/* Debug / conformance variant on one device: additionally returns the tube-rate signal (what -synthesize
+ * hands to dataFill:, TRMTubeModel.m:346) in the batch's arithmetic type; TRMBatchTubeElements() elements,
+ * utterance u at TRMBatchTubeOffsets()[u]. */
+int TRMBatchSynthesizeDebug(TRMBatch *batch, const TRMParameters *frames, int16_t *pcm_out, void *samples_out,
+                            void *tube_out, int device);
+int64_t        TRMBatchTubeElements(const TRMBatch *batch);
+const int64_t *TRMBatchTubeOffsets(const TRMBatch *batch);
+int64_t        TRMBatchKernelLaunches(const TRMBatch *batch);      /* kernels launched by the last synthesize */
+
+/* Device-resident batch: frames uploaded once, each stage (TRM_STAGE_* of trm_cuda.h: 0 waveguide,
+ * 1 resampler, 2 PCM) launched on the caller's CUDA stream (cudaStream_t as void*, NULL = default stream)
+ * with no host<->device traffic, so the caller can bracket stages with CUDA events on that stream. */
+typedef struct TRMResident TRMResident;
+TRMResident *TRMBatchMakeResident(TRMBatch *batch, const TRMParameters *frames, int device, int *err);
+int  TRMResidentRunStage(TRMResident *r, int stage, void *cuda_stream);
+int  TRMResidentRun(TRMResident *r, void *cuda_stream);
+int  TRMResidentFetch(TRMResident *r, int16_t *pcm_out, void *samples_out, double *maxima, void *tube_out);
+void TRMResidentFree(TRMResident *r);
+
+/* Pinned host memory for the batch buffers. */
+void *TRMHostAlloc(size_t bytes);
+void  TRMHostFree(void *p);
+
+/* Text of the last error of the calling thread's most recent failing call. */
+const char *TRMLastErrorMessage(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRM_H */

@@ -1,0 +1,126 @@
+/*
+ * trm_cuda.h -- thin C-ABI shim between the C host library (libtrm) and the sm_100a kernels
+ * (libtrm_cuda).  Plain pointers and sizes only.
+ *
+ * What each entry point replaces in the reference (all under /root/reference/Frameworks/Tube/):
+ *   trm_cuda_stage TRM_STAGE_TUBE  -> the sample-rate loop of -[TRMTubeModel synthesize]
+ *                                     TRMTubeModel.m:292-354 (+611-688, 712-853), TRMWavetable.m:117-195,
+ *                                     TRMFIRFilter.m:116-146, TRMFilters.m:9-86, TRMUtility.m:26-47,71-85
+ *   trm_cuda_stage TRM_STAGE_SRC   -> -[TRMSampleRateConverter processDataFromRingBuffer:]
+ *                                     TRMSampleRateConverter.m:155-298 + TRMRingBuffer.m:47-93 (stateless form)
+ *   trm_cuda_stage TRM_STAGE_PCM   -> the scaling loops of -saveOutputToFile: / -generateWAVData
+ *                                     TRMTubeModel.m:370-383,420-484 / 515-559
+ * The derived constants in trm_cuda_utterance are computed by the host library exactly as
+ * -initWithInputData: does (TRMTubeModel.m:196-241).
+ */
+#ifndef TRM_CUDA_H
+#define TRM_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRM_FIR_MAX_TAPS     64
+#define TRM_SRC_FILTER_LEN   3328      /* 13 zero crossings x 256 phases (TRMSampleRateConverter.m:11-21) */
+#define TRM_TABLE_LENGTH     512       /* TRMWavetable.m:22 */
+#define TRM_NOISE_JUMP       16        /* noise powers 377^0..377^16 mod 2^44 */
+#define TRM_ALIGN_ELEMS      32        /* every per-utterance buffer offset is a multiple of this */
+
+enum { TRM_STAGE_TUBE = 0, TRM_STAGE_SRC = 1, TRM_STAGE_PCM = 2, TRM_STAGE_COUNT = 3 };
+
+/* One utterance as the kernels see it.  Offsets are element offsets into the job's buffers. */
+typedef struct trm_cuda_utterance {
+    int64_t  frame_offset;      /* first control frame (unit: frames of 16 doubles)                     */
+    int64_t  tube_offset;       /* first tube-rate sample                                              */
+    int64_t  out_offset;        /* first output-rate sample (also PCM frame offset)                     */
+    int64_t  pcm_offset;        /* first int16 element of this utterance in the PCM buffer             */
+    int64_t  n_tube;            /* (n_frames-1)*controlPeriod                                          */
+    int64_t  n_out;             /* numberSamples                                                       */
+    int32_t  n_frames;
+    int32_t  controlPeriod;
+    int32_t  waveform;          /* 0 pulse, 1 sine                                                     */
+    int32_t  usesModulation;
+    int32_t  voice;             /* row of the wavetable array                                          */
+    int32_t  padSize;
+    int32_t  upsample;          /* sampleRateRatio >= 1                                                */
+    int32_t  channels;
+    int32_t  div1, div2;        /* tableDiv1 / tableDiv2 (TRMWavetable.m:71-72)                        */
+    uint32_t tri;               /* timeRegisterIncrement                                               */
+    uint32_t phaseIncrement;
+    double   sampleRate;        /* (double)_sampleRate                                                 */
+    double   sampleRateRatio;
+    double   dampingFactor;
+    double   breathinessFactor;
+    double   crossmixFactor;
+    double   basicIncrement;
+    double   tnDelta;
+    double   mouth[5];          /* a10 b11 a20 a21 b21 (TRMFilters.m:34-45)                            */
+    double   nose[5];
+    double   nasal_coeff[5];    /* NC2..NC6 (TRMTubeModel.m:692-707)                                   */
+    double   nr1sq;             /* noseRadius[1]^2 (TRMTubeModel.m:741)                                */
+    double   apScale2;          /* apScale^2 (TRMTubeModel.m:724)                                      */
+    double   ta0, tb1;          /* throat low-pass (TRMFilters.m:64-68)                                */
+    double   throatGain;
+    double   volumeAmp;         /* amplitude(volume)                                                   */
+    double   leftGain, rightGain; /* stereo factors applied on top of scale (TRMTubeModel.m:532-533)   */
+} trm_cuda_utterance;
+
+/* Constant tables shared by all utterances; computed on the host by libtrm. */
+typedef struct trm_cuda_tables {
+    int32_t  fir_taps;
+    double   fir_coef[TRM_FIR_MAX_TAPS];
+    double   src_h[TRM_SRC_FILTER_LEN];
+    double   src_dh[TRM_SRC_FILTER_LEN];
+    uint64_t noise_pow[TRM_NOISE_JUMP + 1];   /* 377^i mod 2^44                                        */
+    uint64_t noise_k0;                         /* state before the first draw: k1 * 377^-1 mod 2^44     */
+} trm_cuda_tables;
+
+typedef struct trm_cuda_ctx trm_cuda_ctx;
+typedef struct trm_cuda_resident trm_cuda_resident;
+
+int         trm_cuda_device_count(void);
+const char *trm_cuda_last_error(void);
+void       *trm_cuda_host_alloc(size_t bytes);      /* pinned */
+void        trm_cuda_host_free(void *p);
+
+/* One context per (process, device): uploads the tables, owns streams and scratch. */
+int  trm_cuda_ctx_create(int device, const trm_cuda_tables *tables, trm_cuda_ctx **ctx);
+void trm_cuda_ctx_destroy(trm_cuda_ctx *ctx);
+/* Glottal wavetables as built at init time (TRMWavetable.m:78-102), n_voices x 512 doubles; utterances pick a
+ * row with trm_cuda_utterance.voice.  Replaces the previous set (blocking). */
+int  trm_cuda_set_wavetables(trm_cuda_ctx *ctx, const double *tables, int n_voices);
+
+/*
+ * Host-buffer path (what TRMTubeModelSynthesize / TRMBatchSynthesize call): copies the frames of the
+ * n utterances described by desc[] (offsets relative to the host arrays) to the device in chunks,
+ * runs the three stages, copies PCM / samples / max back.  Chunks are double-buffered over CUDA
+ * streams so copies overlap kernels.  Blocking.
+ *   pcm_host     int16 [..]  or NULL      samples_host  double/float [..] or NULL
+ *   max_host     double[n]   or NULL      tube_host     double/float tube-rate signal or NULL
+ *   launches     receives the number of kernel launches issued (may be NULL)
+ */
+int trm_cuda_synthesize_host(trm_cuda_ctx *ctx, int precision, int n, const trm_cuda_utterance *desc,
+                             const double *frames_host, int16_t *pcm_host, void *samples_host,
+                             double *max_host, void *tube_host, int64_t *launches);
+
+/*
+ * Device-resident path (bench `value`, roofline timing): inputs uploaded once, stages launched on the
+ * caller's stream (a cudaStream_t passed as void*, NULL = the legacy default stream) without any
+ * host<->device copy, so they can be bracketed by CUDA events on that stream.
+ */
+int  trm_cuda_resident_create(trm_cuda_ctx *ctx, int precision, int n, const trm_cuda_utterance *desc,
+                              const double *frames_host, trm_cuda_resident **res);
+void trm_cuda_resident_destroy(trm_cuda_resident *res);
+int  trm_cuda_resident_stage(trm_cuda_resident *res, int stage, void *stream);   /* one kernel stage      */
+int  trm_cuda_resident_run(trm_cuda_resident *res, void *stream);                /* all stages, in order  */
+int  trm_cuda_resident_fetch(trm_cuda_resident *res, int16_t *pcm_host, void *samples_host,
+                             double *max_host, void *tube_host);                 /* blocking D2H          */
+int  trm_cuda_stage_launches(int stage);     /* kernel launches one stage issues */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRM_CUDA_H */
