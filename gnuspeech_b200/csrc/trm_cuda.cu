@@ -26,6 +26,20 @@ int trm_k_pcm_f64(const trm::PcmArgs *, long long, cudaStream_t);
 int trm_k_pcm_f32(const trm::PcmArgs *, long long, cudaStream_t);
 }
 
+// FMA-chain kernels used to MEASURE the FP32 / FP64 CUDA-core peak of the device the bench runs on
+// (MEASURED_PEAKS.json only carries HBM and bf16 tensor numbers; the waveguide kernel is bound by neither).
+template <typename T> __global__ void fp_peak_kernel(T *out, int iters)
+{
+    T a0 = (T)threadIdx.x * (T)1e-3, a1 = a0 + (T)1, a2 = a0 + (T)2, a3 = a0 + (T)3;
+    T a4 = a0 + (T)4, a5 = a0 + (T)5, a6 = a0 + (T)6, a7 = a0 + (T)7;
+    const T m = (T)0.999999, c = (T)1e-7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = a0 * m + c; a1 = a1 * m + c; a2 = a2 * m + c; a3 = a3 * m + c;
+        a4 = a4 * m + c; a5 = a5 * m + c; a6 = a6 * m + c; a7 = a7 * m + c;
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
 namespace {
 
 thread_local std::string g_err;
@@ -347,6 +361,37 @@ void *trm_cuda_host_alloc(size_t bytes)
 }
 
 void trm_cuda_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+/* Measured FMA peak in TFLOP/s (2 flops per FMA) for precision 0 = FP64, 1 = FP32; best of `reps` runs. */
+int trm_cuda_fp_peak(int device, int precision, int reps, double *tflops)
+{
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = precision == 0 ? 1 << 14 : 1 << 16;
+    void *buf = nullptr;
+    CK(cudaMalloc(&buf, (size_t)threads * blocks * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    double best = 0;
+    for (int r = 0; r < reps + 1; ++r) {
+        CK(cudaEventRecord(e0, 0));
+        if (precision == 0) fp_peak_kernel<double><<<blocks, threads>>>((double *)buf, iters);
+        else fp_peak_kernel<float><<<blocks, threads>>>((float *)buf, iters);
+        CK(cudaEventRecord(e1, 0));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double tf = 2.0 * 8.0 * (double)iters * threads * blocks / (ms * 1e-3) / 1e12;
+        if (r > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    *tflops = best;
+    return 0;
+}
 
 int trm_cuda_stage_launches(int stage) { return (stage >= 0 && stage < TRM_STAGE_COUNT) ? 1 : 0; }
 

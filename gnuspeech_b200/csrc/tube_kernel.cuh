@@ -58,20 +58,27 @@ struct alignas(16) UttSmem {
     // control-frame staging (TMA destination), double-buffered
     double FR[2][FRAME_CHUNK][16];
     unsigned long long mbar[2];
-    // P (interpolated parameters, written by the parameter lanes, read by phase A1) is dead once A1 has
-    // loaded it, so the per-sample vectors produced later in the block share its storage.
+    // P (interpolated parameters: written by the parameter lanes, read by phase A1) is dead once A1 is
+    // done; vectors produced after A1 share its storage.
     union {
         double P[TB][17];
         struct {
-            double INC[TB];                  // oscillator increment (f0/2)*basicIncrement
-            R U[TB], G[TB], BT[TB];          // band-pass: alpha*(x[n]-x[n-2]), gamma, beta
-            R THX[TB];                       // ta0 * (pulse * VT_SCALE)
+            double POS[2 * TB];              // oscillator positions of the two 2x-rate steps of each sample
             R OUTM[TB], OUTN[TB];            // mouth / nose radiation outputs
             R YB[TB];                        // finished tube-rate samples, for the vector store
         } v;
     } a;
-    R KQ[TB][13];                            // junction coefficient per lane (cols 0..10), alphaU (11)
-    R TAPV[TB][9];                           // col 0: glottal input; cols 1..8: frication taps FC1..FC8
+    double INC[TB];                          // oscillator increment (f0/2)*basicIncrement
+    R BC[TB][4];                             // per-sample scalars every junction lane needs (broadcast reads):
+                                             //   [0] 2*alpha*(x[n]-x[n-2])  [1] 2*gamma  [2] 2*beta  (band-pass)
+                                             //   [3] ta0*(pulse*VT_SCALE)                           (throat)
+    // conformance mode (R = double): reference-order arithmetic needs one coefficient per junction
+    R KQ[sizeof(R) == 8 ? TB : 1][13];       // junction coefficient per lane (cols 0..10), alphaU (11)
+    R TAPV[sizeof(R) == 8 ? TB : 1][9];      // col 0: glottal input; cols 1..8: frication taps FC1..FC8
+    // fast mode (R = float): cancellation-free forms with the damping folded in, one 128-bit load per lane
+    //   two-port lanes : {d(1+k), d k, d(1-k), injection}      mouth lane 9 : {a10 k, 1+k, -, -}
+    //   3-way lane 3   : {d aL, d(aL-1), d aU, d(aU-1)}, its tap in column 5 (.w)
+    float4 KF[sizeof(R) == 4 ? TB : 1][13];
     R HE[FIR_HIST + TB], HO[FIR_HIST + TB];  // oscillator history, even / odd 2x-rate samples
 };
 
@@ -129,28 +136,6 @@ __device__ __forceinline__ double amplitude_db(double dB)
     if (x >= 0.0) return 1.0;
     return exp10(x / 20.0);
 }
-template <typename R> __device__ __forceinline__ R amplitude_r(double dB);
-template <> __device__ __forceinline__ double amplitude_r<double>(double dB) { return amplitude_db(dB); }
-template <> __device__ __forceinline__ float amplitude_r<float>(double dB)
-{
-    float x = (float)(dB - 60.0);
-    if (x <= -60.0f) return 0.0f;
-    if (x >= 0.0f) return 1.0f;
-    return exp10f(x / 20.0f);
-}
-
-template <typename R> __device__ __forceinline__ R r_tan(R x);
-template <> __device__ __forceinline__ double r_tan<double>(double x) { return tan(x); }
-template <> __device__ __forceinline__ float r_tan<float>(float x) { return tanf(x); }
-template <typename R> __device__ __forceinline__ R r_cos(R x);
-template <> __device__ __forceinline__ double r_cos<double>(double x) { return cos(x); }
-template <> __device__ __forceinline__ float r_cos<float>(float x) { return cosf(x); }
-
-template <typename R> __device__ __forceinline__ R shfl16(unsigned mask, R v, int src)
-{
-    return __shfl_sync(mask, v, src, 16);
-}
-
 // Glottal table value at integer index i for the current closure point (TRMWavetable.m:78-102 init,
 // :117-162 update, vDSP order 1 - (j*j)*(1/(L*L))).  The reference rewrites the table every sample; the
 // table is a pure function of the current amplitude, so it is evaluated on look-up instead.
@@ -167,21 +152,30 @@ __device__ __forceinline__ R table_value(const double *__restrict__ base, int i,
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
 template <typename R>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8) tube_kernel(TubeArgs args)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) tube_kernel(TubeArgs args)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int half = lane >> 4, hl = lane & 15;
-    const unsigned hmask = 0xFFFFu << (half * 16);
     const int slot = (blockIdx.x * WARPS_PER_CTA + warp) * 2 + half;
-    if (slot >= args.n_utt) return;                       // the whole half-warp leaves together
     UttSmem<R> &S = reinterpret_cast<UttSmem<R> *>(smem_raw)[warp * 2 + half];
 
-    const int u = args.order ? args.order[slot] : slot;
+    // A warp always runs both halves in lock step (full-mask shuffles and syncs).  A half without an
+    // utterance (odd batch) or whose utterance is shorter than its partner's keeps executing with
+    // n_tube = 0 / past its end: it computes on stale shared memory and never touches global memory.
+    const bool has_utt = slot < args.n_utt;
+    const int u = args.order ? args.order[has_utt ? slot : args.n_utt - 1] : (has_utt ? slot : args.n_utt - 1);
     const trm_cuda_utterance *__restrict__ D = args.desc + u;
-    const int64_t n_tube = D->n_tube;
-    if (n_tube <= 0) return;
+    const int64_t n_tube = has_utt ? D->n_tube : 0;
+    int64_t n_warp = n_tube;
+    {
+        const int64_t other = __shfl_xor_sync(FULL, n_tube, 16);
+        n_warp = other > n_tube ? other : n_tube;
+    }
+    if (n_warp <= 0) return;
     const int n_frames = D->n_frames;
     const int cp = D->controlPeriod;
     const double *__restrict__ F = args.frames + D->frame_offset * 16;
@@ -192,13 +186,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8) tube_kernel(TubeArgs ar
     const bool pulse_wave = D->waveform == 0;
     const bool modulation = D->usesModulation != 0;
     const int div1 = D->div1, div2 = D->div2;
-    const double tnDelta = D->tnDelta;
-    const double basicIncrement = D->basicIncrement;
-    const R sr = (R)D->sampleRate;
-    const R apScale2 = (R)D->apScale2, nr1sq = (R)D->nr1sq;
-    const R bf = (R)D->breathinessFactor, one_minus_bf = (R)(1.0 - D->breathinessFactor);
-    const R cmf = (R)D->crossmixFactor;
-    const R ta0 = (R)D->ta0, tb1 = (R)D->tb1, throatGain = (R)D->throatGain;
+    const R tb1 = (R)D->tb1;
     const R d = (R)D->dampingFactor;
 
     // ---- lane roles for the section-parallel phase ----------------------------------------------
@@ -207,7 +195,20 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8) tube_kernel(TubeArgs ar
     const R kconst = (hl >= 11) ? (R)D->nasal_coeff[hl - 11] : (R)0;
     const bool has_tap = (hl >= 1 && hl <= 8);
     const int tap_col = (hl <= 8) ? hl : 0;
-    const int srcA = hl - 1, srcB = hl + 1, srcC = (hl == 3) ? 10 : 3;
+    const int kq_col = kvar ? hl : 12;
+    constexpr bool FAST = sizeof(R) == 4;
+    // fast mode: constant-coefficient lanes (pure delay 5, nasal 11..14, nose 15) keep their forms in registers;
+    // lane 5 still reads its frication tap (FC5) from column 11
+    const int kf_col = kvar ? hl : 11;
+    float fc0 = 0.0f, fc1 = 0.0f, fc2 = 0.0f;
+    if (FAST && !kvar) {
+        const double dd = D->dampingFactor;
+        const double k = (hl >= 11) ? D->nasal_coeff[hl - 11] : 0.0;
+        if (hl == 15) { fc0 = (float)(D->nose[0] * k); fc1 = (float)(1.0 + k); }
+        else { fc0 = (float)(dd * (1.0 + k)); fc1 = (float)(dd * k); fc2 = (float)(dd * (1.0 - k)); }
+    }
+    const int srcA = (lane & 16) | ((hl - 1) & 15), srcB = (lane & 16) | ((hl + 1) & 15);
+    const int srcC = (lane & 16) | ((hl == 3) ? 10 : 3);
     const double *fc = (hl == 9) ? D->mouth : D->nose;
     const R f_a10 = (R)fc[0], f_b11 = (R)fc[1], f_a20 = (R)fc[2], f_a21 = (R)fc[3], f_b21 = (R)fc[4];
 
@@ -219,26 +220,27 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8) tube_kernel(TubeArgs ar
         constexpr int NW = (int)((sizeof(UttSmem<R>) - offsetof(UttSmem<R>, a)) / 4);
         for (int i = hl; i < NW; i += 16) w[i] = 0u;
     }
-    __syncwarp(hmask);
+    __syncwarp(FULL);
+    const bool feeds = n_tube > 0;                        // this half stages frames
     const int n_chunks = (n_frames + FRAME_CHUNK - 1) / FRAME_CHUNK;
-    if (hl == 0) {
+    if (hl == 0 && feeds) {
         mbar_init(&S.mbar[0], 1);
         mbar_init(&S.mbar[1], 1);
         mbar_fence_init();
     }
-    __syncwarp(hmask);
-    if (hl == 0) {
+    __syncwarp(FULL);
+    if (hl == 0 && feeds) {
         for (int c = 0; c < 2 && c < n_chunks; ++c) {
             int cnt = min(FRAME_CHUNK, n_frames - c * FRAME_CHUNK);
             mbar_expect_tx(&S.mbar[c], (uint32_t)cnt * 128u);
             tma_bulk_g2s(&S.FR[c][0][0], F + (size_t)c * FRAME_CHUNK * 16, (uint32_t)cnt * 128u, &S.mbar[c]);
         }
     }
-    mbar_wait(&S.mbar[0], 0);
+    if (feeds) mbar_wait(&S.mbar[0], 0);
 
     // ---- running state ---------------------------------------------------------------------------
     // parameter lane p = hl (TRMTubeModel.m:611-688)
-    double p_cur = 0.0, p_delta = 0.0, p_next = S.FR[0][0][hl];
+    double p_cur = 0.0, p_delta = 0.0, p_next = feeds ? S.FR[0][0][hl] : 0.0;
     int f_idx = 0, jc = 0;                 // current interval, sample inside it
     // oscillator position (all lanes carry the same value)
     double pos = 0.0;
@@ -251,28 +253,23 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8) tube_kernel(TubeArgs ar
     // junction state: waves incident on this lane's junction
     R a = 0, b = 0, c3 = 0, s1bot = 0, ry = 0, rx = 0, rY = 0;
 
-    for (int64_t n0 = 0; n0 < n_tube; n0 += TB) {
-        const int nb = (int)min((int64_t)TB, n_tube - n0);
+    for (int64_t n0 = 0; n0 < n_warp; n0 += TB) {
+        const int64_t left = n_tube - n0;
+        const int nb = left >= TB ? TB : (left > 0 ? (int)left : 0);    // valid samples of this half's block
         const bool active = hl < nb;
 
         // =========================================================================================
         // S0  parameter interpolation, lane = parameter (m:611-688): cur = prev; delta = (next-prev)/cp;
-        //     one add per sample AFTER the sample is used.
+        //     one add per sample AFTER the sample is used.  Frame boundaries are handled between runs of
+        //     plain adds; the TMA refill a boundary asks for is issued after the warp-wide sync below.
         // =========================================================================================
-        for (int s = 0; s < nb; ++s) {
-            if (jc == 0) {
+        int refill = -1;
+        for (int s = 0; s < TB;) {
+            if (jc == 0 && f_idx + 1 < n_frames && feeds) {
                 const int fn = f_idx + 1;                    // frame that ends this interval
                 const int ch = fn / FRAME_CHUNK;
-                if ((fn % FRAME_CHUNK) == 0) {
-                    // entering chunk ch: all lanes are done with chunk ch-1, whose buffer is refilled
-                    __syncwarp(hmask);
-                    if (hl == 0 && ch + 1 < n_chunks) {
-                        const int cn = ch + 1;
-                        int cnt = min(FRAME_CHUNK, n_frames - cn * FRAME_CHUNK);
-                        mbar_expect_tx(&S.mbar[cn & 1], (uint32_t)cnt * 128u);
-                        tma_bulk_g2s(&S.FR[cn & 1][0][0], F + (size_t)cn * FRAME_CHUNK * 16, (uint32_t)cnt * 128u,
-                                     &S.mbar[cn & 1]);
-                    }
+                if ((fn % FRAME_CHUNK) == 0) {               // entering chunk ch
+                    refill = ch + 1;
                     mbar_wait(&S.mbar[ch & 1], (uint32_t)((ch >> 1) & 1));
                 }
                 const double nxt = S.FR[ch & 1][fn % FRAME_CHUNK][hl];
@@ -280,70 +277,105 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8) tube_kernel(TubeArgs ar
                 p_delta = (nxt - p_cur) / (double)cp;
                 p_next = nxt;
             }
-            S.a.P[s][hl] = p_cur;
-            p_cur += p_delta;
-            if (++jc == cp) { jc = 0; ++f_idx; }
+            const int run = min(TB - s, cp - jc);
+            for (int i = 0; i < run; ++i) {
+                S.a.P[s + i][hl] = p_cur;
+                p_cur += p_delta;
+            }
+            s += run;
+            jc += run;
+            if (jc == cp) { jc = 0; ++f_idx; }
         }
-        __syncwarp(hmask);
+        __syncwarp(FULL);
+        if (hl == 0 && refill >= 0 && refill < n_chunks) {
+            // every lane is past its last read of chunk refill-2, whose buffer is refilled now
+            const int cnt = min(FRAME_CHUNK, n_frames - refill * FRAME_CHUNK);
+            mbar_expect_tx(&S.mbar[refill & 1], (uint32_t)cnt * 128u);
+            tma_bulk_g2s(&S.FR[refill & 1][0][0], F + (size_t)refill * FRAME_CHUNK * 16, (uint32_t)cnt * 128u,
+                         &S.mbar[refill & 1]);
+        }
 
         // =========================================================================================
-        // A1  lane = sample t: conversions and coefficients (m:294-300, 712-773; TRMFilters.m:9-17)
+        // A1  lane = sample t: conversions and coefficients (m:294-300, 712-773; TRMFilters.m:9-17).
+        //     Coefficient math is double in both precision modes (it is feed-forward,
+        //     so it costs issue slots but no serial latency, and FP32 here is the dominant error source).
         // =========================================================================================
-        double prm[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) prm[q] = S.a.P[hl][q];
-        __syncwarp(hmask);                                  // P is dead from here: its storage is reused
-
-        // pitch -> f0 -> increment: always double
-        const double f0 = 220.0 * exp2((prm[0] + 3.0) / 12.0);
-        const double inc = (f0 / 2.0) * basicIncrement;
+        const double *prm = S.a.P[hl];
         const double ax_d = amplitude_db(prm[1]);
         const R ax = (R)ax_d;
-        const R ah1 = amplitude_r<R>(prm[2]);
-        const R fa = amplitude_r<R>(prm[3]);
-        S.a.v.INC[hl] = inc;
-
+        const R ah1 = (R)amplitude_db(prm[2]);
         {
-            R r2[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) { R r = (R)prm[7 + q]; r2[q] = r * r; }
-            R kk[8];
-#pragma unroll
-            for (int q = 0; q < 7; ++q) kk[q] = (r2[q] - r2[q + 1]) / (r2[q] + r2[q + 1]);
-            kk[7] = (r2[7] - apScale2) / (r2[7] + apScale2);
-            const R vel = (R)prm[15];
-            const R v2 = vel * vel;
-            const R sum = (R)2 / ((r2[3] + r2[3]) + v2);
-            const R aL = sum * r2[3], aU = sum * v2;
-            const R nc1 = (v2 - nr1sq) / (v2 + nr1sq);
-            R *kq = S.KQ[hl];
-            kq[0] = kk[0]; kq[1] = kk[1]; kq[2] = kk[2]; kq[3] = aL; kq[4] = kk[3];
-            kq[6] = kk[4]; kq[7] = kk[5]; kq[8] = kk[6]; kq[9] = kk[7]; kq[10] = nc1; kq[11] = aU;
+            // pitch -> f0 -> increment
+            const double f0 = 220.0 * exp2((prm[0] + 3.0) / 12.0);
+            S.INC[hl] = (f0 / 2.0) * D->basicIncrement;
         }
         {
-            // frication taps (m:748-765)
-            const int ipos = (int)prm[4];
-            const R comp = (R)(prm[4] - (double)ipos);
-            const R rem = (R)1 - comp;
-            R *tv = S.TAPV[hl];
+            double r2[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                R v = (R)0;
-                if (q == ipos) v = rem * fa;
-                else if (ipos >= 0 && q == ipos + 1) v = comp * fa;
-                tv[q + 1] = v;
+            for (int q = 0; q < 8; ++q) { const double r = prm[7 + q]; r2[q] = r * r; }
+            double kk[10];                   // k of lanes 0,1,2,(3 unused),4,(5 unused),6,7,8,9
+            kk[0] = (r2[0] - r2[1]) / (r2[0] + r2[1]);
+            kk[1] = (r2[1] - r2[2]) / (r2[1] + r2[2]);
+            kk[2] = (r2[2] - r2[3]) / (r2[2] + r2[3]);
+            kk[4] = (r2[3] - r2[4]) / (r2[3] + r2[4]);
+            kk[6] = (r2[4] - r2[5]) / (r2[4] + r2[5]);
+            kk[7] = (r2[5] - r2[6]) / (r2[5] + r2[6]);
+            kk[8] = (r2[6] - r2[7]) / (r2[6] + r2[7]);
+            const double ap2 = D->apScale2;
+            kk[9] = (r2[7] - ap2) / (r2[7] + ap2);
+            const double vel = prm[15];
+            const double v2 = vel * vel;
+            const double sum = 2.0 / ((r2[3] + r2[3]) + v2);
+            const double aL = sum * r2[3], aU = sum * v2;
+            const double n2 = D->nr1sq;
+            const double nc1 = (v2 - n2) / (v2 + n2);
+            // frication taps (m:748-765)
+            const double fa = amplitude_db(prm[3]);
+            const double fpos = prm[4];
+            const int ipos = (int)fpos;
+            const double comp = fpos - (double)ipos;
+            const double rem = 1.0 - comp;
+            const R t0 = (R)(rem * fa), t1 = (R)(comp * fa);
+            if constexpr (FAST) {
+                const double dd = D->dampingFactor;
+                float4 *kf = S.KF[hl];
+                float tap[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) tap[q] = (q == ipos) ? t0 : ((ipos >= 0 && q == ipos + 1) ? t1 : 0.0f);
+#pragma unroll
+                for (int j = 0; j <= 8; ++j) {
+                    if (j == 3 || j == 5) continue;
+                    const double k = kk[j];
+                    // .w of lane 0 (glottal input) is written by phase A2
+                    if (j == 0) { kf[0].x = (float)(dd * (1.0 + k)); kf[0].y = (float)(dd * k); kf[0].z = (float)(dd * (1.0 - k)); }
+                    else kf[j] = make_float4((float)(dd * (1.0 + k)), (float)(dd * k), (float)(dd * (1.0 - k)), tap[j - 1]);
+                }
+                kf[3] = make_float4((float)(dd * aL), (float)(dd * (aL - 1.0)), (float)(dd * aU), (float)(dd * (aU - 1.0)));
+                kf[5] = make_float4(0.0f, 0.0f, 0.0f, tap[2]);            // FC3 for the 3-way lane
+                kf[9] = make_float4((float)(D->mouth[0] * kk[9]), (float)(1.0 + kk[9]), 0.0f, 0.0f);
+                kf[10] = make_float4((float)(dd * (1.0 + nc1)), (float)(dd * nc1), (float)(dd * (1.0 - nc1)), 0.0f);
+                kf[11] = make_float4(0.0f, 0.0f, 0.0f, tap[4]);           // FC5 for the pure-delay lane 5
+            } else {
+                R *kq = S.KQ[hl];
+                kq[0] = kk[0]; kq[1] = kk[1]; kq[2] = kk[2]; kq[3] = aL; kq[4] = kk[4];
+                kq[6] = kk[6]; kq[7] = kk[7]; kq[8] = kk[8]; kq[9] = kk[9]; kq[10] = nc1; kq[11] = aU;
+                R *tv = S.TAPV[hl];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) tv[q + 1] = (q == ipos) ? t0 : ((ipos >= 0 && q == ipos + 1) ? t1 : (R)0);
             }
         }
-        R bp_alpha;
+        R bp_alpha2;
         {
-            // band-pass coefficients (TRMFilters.m:9-17)
-            const R pi = (R)3.14159265358979323846;
-            const R tanv = r_tan<R>((pi * (R)prm[6]) / sr);
-            const R cosv = r_cos<R>((((R)2 * pi) * (R)prm[5]) / sr);
-            const R beta = ((R)1 - tanv) / ((R)2 * ((R)1 + tanv));
-            S.a.v.BT[hl] = beta;
-            S.a.v.G[hl] = ((R)0.5 + beta) * cosv;
-            bp_alpha = ((R)0.5 - beta) / (R)2;
+            // band-pass coefficients (TRMFilters.m:9-17).  The filter output is 2*(...): the factor is folded
+            // into the coefficients, which is exact (scaling by 2 commutes with rounding).
+            const double sr = D->sampleRate;
+            const double pi = 3.14159265358979323846;
+            const double tanv = tan((pi * prm[6]) / sr);
+            const double cosv = cos(((2.0 * pi) * prm[5]) / sr);
+            const double beta = (1.0 - tanv) / (2.0 * (1.0 + tanv));
+            S.BC[hl][2] = (R)(2.0 * beta);
+            S.BC[hl][1] = (R)(2.0 * ((0.5 + beta) * cosv));
+            bp_alpha2 = (R)(2.0 * ((0.5 - beta) / 2.0));
         }
         // noise (TRMUtility.m:71-85 as the equivalent MCG mod 2^44) + one-zero low-pass (TRMFilters.m:81-86)
         R lp_noise;
@@ -354,29 +386,32 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8) tube_kernel(TubeArgs ar
             lp_noise = (R)(nz + nzp);
             kb = (kb * pwB) & MASK44;
         }
-        __syncwarp(hmask);
+        __syncwarp(FULL);                                   // P is dead from here: its storage is reused
 
         // =========================================================================================
         // S1  oscillator position (TRMWavetable.m:165-168, 28-34), sequential, replicated in all lanes
         // =========================================================================================
-        double p0 = 0.0, p1 = 0.0;
-        for (int s = 0; s < nb; ++s) {
-            const double di = S.a.v.INC[s];
+#pragma unroll
+        for (int s = 0; s < TB; ++s) {
+            const double di = S.INC[s];
             pos = pos + di;
             if (pos > 511.0) pos -= 512.0;
-            if (s == hl) p0 = pos;
+            const double pa = pos;
             pos = pos + di;
             if (pos > 511.0) pos -= 512.0;
-            if (s == hl) p1 = pos;
+            if (hl == 0) *reinterpret_cast<double2 *>(&S.a.v.POS[2 * s]) = make_double2(pa, pos);
         }
+        __syncwarp(FULL);
 
         // =========================================================================================
         // A2  lane = sample t: table look-ups, FIR, source mixing (TRMWavetable.m:174-195, m:305-337)
         // =========================================================================================
         {
-            const double newDiv2 = (double)div2 - rint(ax_d * tnDelta);
+            const double2 pp = *reinterpret_cast<const double2 *>(&S.a.v.POS[2 * hl]);
+            const double p0 = active ? pp.x : 0.0, p1 = active ? pp.y : 0.0;
+            const double newDiv2 = (double)div2 - rint(ax_d * D->tnDelta);
             const double Ld = newDiv2 - (double)div1;
-            const R scale = (R)1 / ((R)Ld * (R)Ld);
+            const R scale = (R)(1.0 / (Ld * Ld));
             int lo = ((int)p0) & (TRM_TABLE_LENGTH - 1);
             int hi = lo + 1; if (hi > 511) hi -= 512;
             R w0 = table_value<R>(wt_base, lo, div1, div2, newDiv2, scale, pulse_wave);
@@ -388,7 +423,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8) tube_kernel(TubeArgs ar
             w1 = table_value<R>(wt_base, hi, div1, div2, newDiv2, scale, pulse_wave);
             S.HO[FIR_HIST + hl] = w0 + ((R)(p1 - (double)lo) * (w1 - w0));
         }
-        __syncwarp(hmask);
+        __syncwarp(FULL);
         R sig;
         {
             // 49-tap FIR at the odd sample, newest -> oldest from 0.0 (TRMFIRFilter.m:116-131)
@@ -401,95 +436,145 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8) tube_kernel(TubeArgs ar
             }
             acc += ho[-FIR_HIST] * FirCoef<R>::at(2 * FIR_HIST);
             const R pulse0 = acc;
+            const R bf = (R)D->breathinessFactor, one_minus_bf = (R)(1.0 - D->breathinessFactor);
             const R pulsed_noise = lp_noise * pulse0;
             const R pulse = ax * ((pulse0 * one_minus_bf) + (pulsed_noise * bf));
             if (modulation) {
-                R crossmix = ax * cmf;
+                R crossmix = ax * (R)D->crossmixFactor;
                 crossmix = (crossmix < (R)1) ? crossmix : (R)1;
                 sig = (pulsed_noise * crossmix) + (lp_noise * ((R)1 - crossmix));
             } else
                 sig = lp_noise;
-            S.TAPV[hl][0] = (pulse + (ah1 * sig)) * (R)0.125;
-            S.a.v.THX[hl] = ta0 * (pulse * (R)0.125);
+            const R tube_in = (pulse + (ah1 * sig)) * (R)0.125;
+            if constexpr (FAST) S.KF[hl][0].w = tube_in; else S.TAPV[hl][0] = tube_in;
+            S.BC[hl][3] = (R)D->ta0 * (pulse * (R)0.125);
         }
         {
             // band-pass feed-forward part alpha*(x[n]-x[n-2]); x[n-2] comes from two lanes down or the carry
-            R x2 = shfl16<R>(hmask, sig, hl - 2);
+            R x2 = __shfl_sync(FULL, sig, (lane & 16) | ((hl - 2) & 15));
             if (hl == 0) x2 = xm2;
             if (hl == 1) x2 = xm1;
-            S.a.v.U[hl] = bp_alpha * (sig - x2);
-            const int last = nb - 1;
-            const R l1 = shfl16<R>(hmask, sig, last);
-            const R l2 = shfl16<R>(hmask, sig, last > 0 ? last - 1 : 0);
+            S.BC[hl][0] = bp_alpha2 * (sig - x2);
+            const int last = nb > 0 ? nb - 1 : 0;
+            const R l1 = __shfl_sync(FULL, sig, (lane & 16) | last);
+            const R l2 = __shfl_sync(FULL, sig, (lane & 16) | (last > 0 ? last - 1 : 0));
             xm2 = (last > 0) ? l2 : xm1;
             xm1 = l1;
         }
-        __syncwarp(hmask);
+        __syncwarp(FULL);
         {
             // slide the oscillator history down by one block (rows TB.. -> 0..)
             const R e0 = S.HE[TB + hl], o0 = S.HO[TB + hl];
-            const R e1 = (hl < FIR_HIST - TB + 0) ? S.HE[2 * TB + hl] : (R)0;
-            const R o1 = (hl < FIR_HIST - TB + 0) ? S.HO[2 * TB + hl] : (R)0;
-            __syncwarp(hmask);
+            const R e1 = (hl < FIR_HIST - TB) ? S.HE[2 * TB + hl] : (R)0;
+            const R o1 = (hl < FIR_HIST - TB) ? S.HO[2 * TB + hl] : (R)0;
+            __syncwarp(FULL);
             S.HE[hl] = e0; S.HO[hl] = o0;
             if (hl < FIR_HIST - TB) { S.HE[TB + hl] = e1; S.HO[TB + hl] = o1; }
         }
 
         // =========================================================================================
-        // B   lane = junction: band-pass / throat recursions + the Kelly-Lochbaum ladder (m:778-853)
+        // B   lane = junction: band-pass / throat recursions + the Kelly-Lochbaum ladder (m:778-853).
+        //     Always TB iterations (fully unrolled, constant shared-memory offsets); samples past the end
+        //     of an utterance compute on stale data and are never stored.
         // =========================================================================================
         R th_mine = (R)0;
-        for (int s = 0; s < nb; ++s) {
-            // frication band-pass recursion (TRMFilters.m:19-29)
-            const R fr = (R)2 * ((S.a.v.U[s] + (S.a.v.G[s] * y1)) - (S.a.v.BT[s] * y2));
-            y2 = y1; y1 = fr;
-            // throat low-pass (TRMFilters.m:72-77)
-            const R th = S.a.v.THX[s] + (tb1 * thy);
-            thy = th;
-            if (s == hl) th_mine = th;
+        if constexpr (FAST) {
+#pragma unroll
+            for (int s = 0; s < TB; ++s) {
+                const float4 bc = *reinterpret_cast<const float4 *>(S.BC[s]);
+                const float fr = (bc.x + (bc.y * y1)) - (bc.z * y2);
+                y2 = y1; y1 = fr;
+                const float th = bc.w + (tb1 * thy);
+                thy = th;
+                if (s == hl) th_mine = th;
 
-            const R k = kvar ? S.KQ[s][hl] : kconst;
-            const R inj = S.TAPV[s][tap_col];
-            R Rr, Lo, X3;
-            if (role == 0) {
-                const R delta = k * (a - b);
-                Rr = (a + delta) * d;
-                if (has_tap) Rr = Rr + (inj * fr);
-                Lo = (b + delta) * d;
-                X3 = Lo;
-            } else if (role == 1) {
-                const R aU = S.KQ[s][11];
-                const R p = ((k * a) + (k * b)) + (aU * c3);
-                Lo = (p - a) * d;
-                Rr = ((p - b) * d) + (inj * fr);
-                X3 = (p - c3) * d;
-            } else {
-                const R x = k * a;
-                const R refl = (f_a10 * x) - (f_b11 * ry);
-                ry = refl;
-                Lo = d * refl;
-                const R xr = ((R)1 + k) * a;
-                const R rad = ((f_a20 * xr) + (f_a21 * rx)) - (f_b21 * rY);
-                rx = xr; rY = rad;
-                if (hl == 9) S.a.v.OUTM[s] = rad; else S.a.v.OUTN[s] = rad;
-                Rr = (R)0; X3 = (R)0;
+                float4 c = S.KF[s][kf_col];
+                if (!kvar) c = make_float4(fc0, fc1, fc2, (hl == 5) ? c.w : 0.0f);
+                float Rr, Lo, X3;
+                if (role == 0) {
+                    Rr = (c.x * a) - (c.y * b);                  // d(1+k) a - d k b
+                    Rr = Rr + (c.w * ((hl == 0) ? 0.0f : fr));
+                    Lo = (c.y * a) + (c.z * b);                  // d k a + d(1-k) b
+                    X3 = Lo;
+                } else if (role == 1) {
+                    const float tap3 = S.KF[s][5].w;
+                    Lo = ((c.y * a) + (c.x * b)) + (c.z * c3);   // d(aL-1) a + d aL b + d aU c
+                    Rr = (((c.x * a) + (c.y * b)) + (c.z * c3)) + (tap3 * fr);
+                    X3 = ((c.x * a) + (c.x * b)) + (c.w * c3);   // d aL (a+b) + d(aU-1) c
+                } else {
+                    const float refl = (c.x * a) - (f_b11 * ry); // a10 k a - b11 y
+                    ry = refl;
+                    Lo = d * refl;
+                    const float xr = c.y * a;                    // (1+k) a
+                    const float rad = ((f_a20 * xr) + (f_a21 * rx)) - (f_b21 * rY);
+                    rx = xr; rY = rad;
+                    if (hl == 9) S.a.v.OUTM[s] = rad; else S.a.v.OUTN[s] = rad;
+                    Rr = 0.0f; X3 = 0.0f;
+                }
+                const float nA = __shfl_sync(FULL, Rr, srcA);
+                const float nB = __shfl_sync(FULL, Lo, srcB);
+                const float nC = __shfl_sync(FULL, X3, srcC);
+                if (hl == 0) { a = (s1bot * d) + c.w; s1bot = Lo; }
+                else if (hl == 10) a = nC;
+                else a = nA;
+                b = nB;
+                if (hl == 3) c3 = nC;
             }
-            const R nA = shfl16<R>(hmask, Rr, srcA);
-            const R nB = shfl16<R>(hmask, Lo, srcB);
-            const R nC = shfl16<R>(hmask, X3, srcC);
-            if (hl == 0) { a = (s1bot * d) + inj; s1bot = Lo; }
-            else if (hl == 10) a = nC;
-            else a = nA;
-            b = nB;
-            if (hl == 3) c3 = nC;
+        } else {
+#pragma unroll
+            for (int s = 0; s < TB; ++s) {
+                // frication band-pass recursion (TRMFilters.m:19-29), factor 2 folded into the coefficients
+                const R fr = (S.BC[s][0] + (S.BC[s][1] * y1)) - (S.BC[s][2] * y2);
+                y2 = y1; y1 = fr;
+                // throat low-pass (TRMFilters.m:72-77)
+                const R th = S.BC[s][3] + (tb1 * thy);
+                thy = th;
+                if (s == hl) th_mine = th;
+
+                const R kq = S.KQ[s][kq_col];
+                const R k = kvar ? kq : kconst;
+                const R inj = S.TAPV[s][tap_col];
+                R Rr, Lo, X3;
+                if (role == 0) {
+                    const R delta = k * (a - b);
+                    Rr = (a + delta) * d;
+                    if (has_tap) Rr = Rr + (inj * fr);
+                    Lo = (b + delta) * d;
+                    X3 = Lo;
+                } else if (role == 1) {
+                    const R aU = S.KQ[s][11];
+                    const R p = ((k * a) + (k * b)) + (aU * c3);
+                    Lo = (p - a) * d;
+                    Rr = ((p - b) * d) + (inj * fr);
+                    X3 = (p - c3) * d;
+                } else {
+                    const R x = k * a;
+                    const R refl = (f_a10 * x) - (f_b11 * ry);
+                    ry = refl;
+                    Lo = d * refl;
+                    const R xr = ((R)1 + k) * a;
+                    const R rad = ((f_a20 * xr) + (f_a21 * rx)) - (f_b21 * rY);
+                    rx = xr; rY = rad;
+                    if (hl == 9) S.a.v.OUTM[s] = rad; else S.a.v.OUTN[s] = rad;
+                    Rr = (R)0; X3 = (R)0;
+                }
+                const R nA = __shfl_sync(FULL, Rr, srcA);
+                const R nB = __shfl_sync(FULL, Lo, srcB);
+                const R nC = __shfl_sync(FULL, X3, srcC);
+                if (hl == 0) { a = (s1bot * d) + inj; s1bot = Lo; }
+                else if (hl == 10) a = nC;
+                else a = nA;
+                b = nB;
+                if (hl == 3) c3 = nC;
+            }
         }
-        __syncwarp(hmask);
+        __syncwarp(FULL);
 
         // =========================================================================================
         // A4  lane = sample t: sum mouth + nose + throat (m:835,849,341); 128-bit coalesced store
         // =========================================================================================
-        if (active) S.a.v.YB[hl] = (S.a.v.OUTM[hl] + S.a.v.OUTN[hl]) + (th_mine * throatGain);
-        __syncwarp(hmask);
+        S.a.v.YB[hl] = (S.a.v.OUTM[hl] + S.a.v.OUTN[hl]) + (th_mine * (R)D->throatGain);
+        __syncwarp(FULL);
         {
             constexpr int VEC = 16 / (int)sizeof(R);          // elements per 128-bit store
             R *dst = out + n0;                                // n0 and tube_offset are multiples of 16
@@ -499,7 +584,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8) tube_kernel(TubeArgs ar
                 dst[hl] = S.a.v.YB[hl];
             }
         }
-        __syncwarp(hmask);                                    // v.* is reused as P by the next block
+        __syncwarp(FULL);                                     // v.* is reused as P by the next block
     }
 }
 

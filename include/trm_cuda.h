@@ -119,6 +119,9 @@ int  trm_cuda_resident_run(trm_cuda_resident *res, void *stream);               
 int  trm_cuda_resident_fetch(trm_cuda_resident *res, int16_t *pcm_host, void *samples_host,
                              double *max_host, void *tube_host);                 /* blocking D2H          */
 int  trm_cuda_stage_launches(int stage);     /* kernel launches one stage issues */
+/* Measures the device's FMA peak (TFLOP/s, 2 flops per FMA) with a register-resident FMA chain:
+ * precision 0 = FP64, 1 = FP32.  The waveguide kernel's roofline denominator. */
+int  trm_cuda_fp_peak(int device, int precision, int reps, double *tflops);
 
 #ifdef __cplusplus
 }
