@@ -15,8 +15,9 @@ constexpr int WARPS_PER_CTA = 2;
 constexpr int UTT_PER_CTA = WARPS_PER_CTA * 2;
 
 constexpr int SRC_THREADS = 256;
-constexpr int SRC_TILE = 1024;       // outputs per tile
-constexpr int SRC_XW = 4096;         // staged input window (elements)
+constexpr int SRC_ROWS = 256;        // staged input rows per work item
+constexpr int SRC_LD = 33;           // padded leading dimension of the transposed tiles (32 utterances + 1)
+constexpr int SRC_CHUNK = 16;        // consecutive outputs a warp finishes before the transposed write-back
 constexpr int SRC_ZC = 13;           // zero crossings -> 13 taps per wing when up-sampling
 constexpr int PCM_THREADS = 256;
 constexpr int PCM_PER_THREAD = 8;
@@ -40,8 +41,13 @@ struct SrcArgs {
     void *out;                       // Real[]
     unsigned long long *maxbits;     // [n_utt] bit pattern of the running max |y| as double
     const void *table;               // HD<Real>[3328]
-    const long long *tile_base;      // [n_utt+1] prefix sum of tiles per utterance
-    long long total_tiles;
+    // work decomposition: tiles of <= 32 utterances that share the converter signature
+    const int *tile_utt;             // [n_tiles][32] utterance index or -1
+    const int *tile_nt;              // [n_tiles] outputs per work item of that tile (window fits SRC_ROWS)
+    const long long *tile_max_out;   // [n_tiles] longest utterance of the tile
+    const long long *item_base;      // [n_tiles+1] prefix sum of work items
+    int n_tiles;
+    long long total_items;
 };
 
 struct PcmArgs {

@@ -8,10 +8,15 @@
 
 namespace trm {
 
+template <typename R> constexpr int src_smem_bytes()
+{
+    return TRM_SRC_FILTER_LEN * (int)sizeof(HD<R>) + (SRC_ROWS + (SRC_THREADS / 32) * SRC_CHUNK) * SRC_LD * (int)sizeof(R);
+}
+
 template <typename R> static int configure_kernels(KernelInfo *info)
 {
     const int tube_smem = UTT_PER_CTA * (int)sizeof(UttSmem<R>);
-    const int src_smem = TRM_SRC_FILTER_LEN * (int)sizeof(HD<R>) + SRC_XW * (int)sizeof(R);
+    const int src_smem = src_smem_bytes<R>();
     cudaError_t e;
     e = cudaFuncSetAttribute(tube_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, tube_smem);
     if (e != cudaSuccess) return (int)e;
@@ -62,9 +67,9 @@ template <typename R> static int launch_tube(const TubeArgs &a, cudaStream_t s)
 
 template <typename R> static int launch_src(const SrcArgs &a, int grid, cudaStream_t s)
 {
-    if (a.total_tiles <= 0) return 0;
-    if ((long long)grid > a.total_tiles) grid = (int)a.total_tiles;
-    const size_t smem = TRM_SRC_FILTER_LEN * sizeof(HD<R>) + SRC_XW * sizeof(R);
+    if (a.total_items <= 0) return 0;
+    if ((long long)grid > a.total_items) grid = (int)a.total_items;
+    const size_t smem = src_smem_bytes<R>();
     src_kernel<R><<<grid, SRC_THREADS, smem, s>>>(a);
     return (int)cudaGetLastError();
 }

@@ -31,110 +31,140 @@ template <typename R> __device__ __forceinline__ R r_abs(R x);
 template <> __device__ __forceinline__ double r_abs<double>(double x) { return fabs(x); }
 template <> __device__ __forceinline__ float r_abs<float>(float x) { return fabsf(x); }
 
+// One work item = one tile of 32 utterances with the same converter signature (time-register increment, pad,
+// direction, phase increment) x one run of `nt` consecutive output samples.  Lane = utterance: every lane of a
+// warp computes the SAME output index n, so the time register, the filter phase and all 26 interpolated
+// coefficients are warp-uniform (one broadcast table read per tap), and the input window is staged transposed
+// ([input row][utterance], padded) so each tap is one conflict-free shared-memory read.  Outputs are transposed
+// back through a small per-warp tile so global stores are coalesced 128-byte rows.
 template <typename R>
 __global__ void __launch_bounds__(SRC_THREADS) src_kernel(SrcArgs args)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HD<R> *tab = reinterpret_cast<HD<R> *>(smem_raw);
-    R *xw = reinterpret_cast<R *>(tab + TRM_SRC_FILTER_LEN);
-    __shared__ int s_u;
+    R *xT = reinterpret_cast<R *>(tab + TRM_SRC_FILTER_LEN);             // [SRC_ROWS][SRC_LD]
+    R *yT = xT + SRC_ROWS * SRC_LD;                                      // [warps][SRC_CHUNK][SRC_LD]
+    __shared__ long long s_tube_off[32], s_out_off[32], s_n_in[32], s_n_out[32];
+    __shared__ int s_tile;
 
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     {
         const HD<R> *g = reinterpret_cast<const HD<R> *>(args.table);
         for (int i = threadIdx.x; i < TRM_SRC_FILTER_LEN; i += SRC_THREADS) tab[i] = g[i];
     }
 
-    for (long long tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x) {
-        __syncthreads();                       // previous tile's window no longer read; table staged
+    for (long long item = blockIdx.x; item < args.total_items; item += gridDim.x) {
+        __syncthreads();                       // previous item's window / descriptors no longer read
         if (threadIdx.x == 0) {
-            int lo = 0, hi = args.n_utt;       // largest u with tile_base[u] <= tile
+            int lo = 0, hi = args.n_tiles;     // largest tile with item_base[tile] <= item
             while (hi - lo > 1) {
-                int mid = (lo + hi) >> 1;
-                if (args.tile_base[mid] <= tile) lo = mid; else hi = mid;
+                const int mid = (lo + hi) >> 1;
+                if (args.item_base[mid] <= item) lo = mid; else hi = mid;
             }
-            s_u = lo;
+            s_tile = lo;
         }
         __syncthreads();
-        const int u = s_u;
-        const trm_cuda_utterance *__restrict__ D = args.desc + u;
-        const long long n_out = D->n_out, n_in = D->n_tube;
-        const long long n_s = (tile - args.tile_base[u]) * SRC_TILE;
-        const long long n_e = (n_s + SRC_TILE < n_out) ? n_s + SRC_TILE : n_out;
-        const unsigned long long tri = D->tri;
-        const int pad = D->padSize;
-        const int reach = pad + 1;
-        const long long P_lo = (long long)(((unsigned long long)n_s * tri) >> 16);
-        const long long P_hi = (long long)(((unsigned long long)(n_e - 1) * tri) >> 16);
-        const long long win_lo = P_lo - reach;
-        const int win_len = (int)(P_hi + reach + 1 - win_lo + 1);
-        const R *__restrict__ x = reinterpret_cast<const R *>(args.tube) + D->tube_offset;
-        R *__restrict__ y = reinterpret_cast<R *>(args.out) + D->out_offset;
+        const int tile = s_tile;
+        if (threadIdx.x < 32) {
+            const int u = args.tile_utt[tile * 32 + threadIdx.x];
+            const trm_cuda_utterance *D = args.desc + (u >= 0 ? u : 0);
+            s_tube_off[threadIdx.x] = D->tube_offset;
+            s_out_off[threadIdx.x] = D->out_offset;
+            s_n_in[threadIdx.x] = u >= 0 ? D->n_tube : -1;
+            s_n_out[threadIdx.x] = u >= 0 ? D->n_out : 0;
+        }
+        // signature of the tile (row 0 is always a real utterance)
+        const trm_cuda_utterance *__restrict__ D0 = args.desc + args.tile_utt[tile * 32];
+        const unsigned long long tri = D0->tri;
+        const int pad = D0->padSize, reach = pad + 1;
+        const bool up = D0->upsample != 0;
+        const double ratio = D0->sampleRateRatio;
+        const unsigned phaseIncrement = D0->phaseIncrement;
+        const int nt = args.tile_nt[tile];
+        const long long n_s = (item - args.item_base[tile]) * nt;
+        const long long tile_max = args.tile_max_out[tile];
+        const long long n_e = (n_s + nt < tile_max) ? n_s + nt : tile_max;
+        const long long win_lo = (long long)(((unsigned long long)n_s * tri) >> 16) - reach;
+        const int rows = (int)((long long)(((unsigned long long)(n_e - 1) * tri) >> 16) + reach + 2 - win_lo);
+        __syncthreads();
 
-        for (int i = threadIdx.x; i < win_len && i < SRC_XW; i += SRC_THREADS) {
-            const long long q = win_lo + i - pad;
-            xw[i] = (q >= 0 && q < n_in) ? x[q] : (R)0;
+        // stage the input window transposed: xT[i][r] = xb_r[win_lo + i], xb[p] = x[p - pad] (0 outside)
+        for (int r = warp; r < 32; r += SRC_THREADS / 32) {
+            const long long n_in = s_n_in[r];
+            const R *__restrict__ x = reinterpret_cast<const R *>(args.tube) + s_tube_off[r];
+            for (int i = lane; i < rows; i += 32) {
+                const long long q = win_lo + i - pad;
+                xT[i * SRC_LD + r] = (q >= 0 && q < n_in) ? x[q] : (R)0;
+            }
         }
         __syncthreads();
 
+        const long long my_n_out = s_n_out[lane];
         R local_max = (R)0;
-        const bool up = D->upsample != 0;
-        const double ratio = D->sampleRateRatio;
-        const unsigned phaseIncrement = D->phaseIncrement;
-        for (long long n = n_s + threadIdx.x; n < n_e; n += SRC_THREADS) {
-            const unsigned long long T = (unsigned long long)n * tri;
-            const int base = (int)((long long)(T >> 16) - win_lo);
-            const unsigned F = (unsigned)(T & 0xFFFFull);
-            R acc = (R)0;
-            if (up) {
-                R interp = (R)(F & 255u) / (R)256;
-                unsigned fi = F >> 8;
+        R *yw = yT + warp * (SRC_CHUNK * SRC_LD);
+        for (long long n0 = n_s + (long long)warp * SRC_CHUNK; n0 < n_e; n0 += (SRC_THREADS / 32) * SRC_CHUNK) {
+#pragma unroll 2
+            for (int j = 0; j < SRC_CHUNK; ++j) {
+                const unsigned long long T = (unsigned long long)(n0 + j) * tri;
+                const int base = (int)((long long)(T >> 16) - win_lo);
+                const unsigned F = (unsigned)(T & 0xFFFFull);
+                const R *xp = xT + base * SRC_LD + lane;
+                R acc = (R)0;
+                if (up) {
+                    R interp = (R)(F & 255u) / (R)256;
+                    unsigned fi = F >> 8;
 #pragma unroll
-                for (int k = 0; k < SRC_ZC; ++k) {
-                    const HD<R> c = tab[fi + 256u * k];
-                    acc += xw[base - k] * (c.h + c.dh * interp);
-                }
-                const unsigned G = (~F) & 0xFFFFu;
-                interp = (R)(G & 255u) / (R)256;
-                fi = G >> 8;
+                    for (int k = 0; k < SRC_ZC; ++k) {
+                        const HD<R> c = tab[fi + 256u * k];
+                        acc += xp[-k * SRC_LD] * (c.h + c.dh * interp);
+                    }
+                    const unsigned G = (~F) & 0xFFFFu;
+                    interp = (R)(G & 255u) / (R)256;
+                    fi = G >> 8;
 #pragma unroll
-                for (int k = 0; k < SRC_ZC; ++k) {
-                    const HD<R> c = tab[fi + 256u * k];
-                    acc += xw[base + 1 + k] * (c.h + c.dh * interp);
+                    for (int k = 0; k < SRC_ZC; ++k) {
+                        const HD<R> c = tab[fi + 256u * k];
+                        acc += xp[(1 + k) * SRC_LD] * (c.h + c.dh * interp);
+                    }
+                } else {
+                    unsigned ph = (unsigned)rint((double)F * ratio), ii;
+                    const R *xq = xp;
+                    while ((ii = (ph >> 8)) < (unsigned)TRM_SRC_FILTER_LEN) {
+                        const HD<R> c = tab[ii];
+                        const R impulse = c.h + (c.dh * ((R)(ph & 255u) / (R)256));
+                        acc += (*xq * impulse);
+                        xq -= SRC_LD;
+                        ph += phaseIncrement;
+                    }
+                    ph = (unsigned)rint((double)((~F) & 0xFFFFu) * ratio);
+                    xq = xp + SRC_LD;
+                    while ((ii = (ph >> 8)) < (unsigned)TRM_SRC_FILTER_LEN) {
+                        const HD<R> c = tab[ii];
+                        const R impulse = c.h + (c.dh * ((R)(ph & 255u) / (R)256));
+                        acc += (*xq * impulse);
+                        xq += SRC_LD;
+                        ph += phaseIncrement;
+                    }
                 }
-            } else {
-                unsigned ph = (unsigned)rint((double)F * ratio), ii;
-                int idx = base;
-                while ((ii = (ph >> 8)) < (unsigned)TRM_SRC_FILTER_LEN) {
-                    const HD<R> c = tab[ii];
-                    const R impulse = c.h + (c.dh * ((R)(ph & 255u) / (R)256));
-                    acc += (xw[idx] * impulse);
-                    --idx;
-                    ph += phaseIncrement;
-                }
-                ph = (unsigned)rint((double)((~F) & 0xFFFFu) * ratio);
-                idx = base + 1;
-                while ((ii = (ph >> 8)) < (unsigned)TRM_SRC_FILTER_LEN) {
-                    const HD<R> c = tab[ii];
-                    const R impulse = c.h + (c.dh * ((R)(ph & 255u) / (R)256));
-                    acc += (xw[idx] * impulse);
-                    ++idx;
-                    ph += phaseIncrement;
-                }
+                yw[j * SRC_LD + lane] = acc;
+                const R av = r_abs<R>(acc);
+                if (n0 + j < my_n_out && av > local_max) local_max = av;     // NaN never wins, like the reference
             }
-            y[n] = acc;
-            const R av = r_abs<R>(acc);
-            if (av > local_max) local_max = av;          // NaN never wins, like the reference's compare
+            __syncwarp();
+            // transposed write-back: each half-warp stores SRC_CHUNK consecutive samples of one utterance
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+                const int r = 2 * i + (lane >> 4), cc = lane & 15;
+                if (n0 + cc < s_n_out[r])
+                    (reinterpret_cast<R *>(args.out) + s_out_off[r])[n0 + cc] = yw[cc * SRC_LD + r];
+            }
+            __syncwarp();
         }
-        // per-utterance maximum: warp max, then one integer atomic per warp (bit order == value order for
-        // non-negative doubles, so the result does not depend on the order of the atomics)
-        double m = (double)local_max;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double other = __shfl_xor_sync(0xFFFFFFFFu, m, o);
-            m = (other > m) ? other : m;
+        // per-utterance maximum: integer atomicMax on the bit pattern (order independent for non-negative doubles)
+        if (local_max > (R)0) {
+            const int u = args.tile_utt[tile * 32 + lane];
+            if (u >= 0) atomicMax(args.maxbits + u, (unsigned long long)__double_as_longlong((double)local_max));
         }
-        if ((threadIdx.x & 31) == 0 && m > 0.0)
-            atomicMax(args.maxbits + u, (unsigned long long)__double_as_longlong(m));
     }
 }
 

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "kernel_args.h"
@@ -122,12 +123,14 @@ struct DeviceChunk {
     int n = 0;
     trm_cuda_utterance *desc = nullptr;
     int *order = nullptr;
-    long long *tile_base = nullptr;
+    int *tile_utt = nullptr, *tile_nt = nullptr;
+    long long *tile_max_out = nullptr, *item_base = nullptr;
     unsigned long long *maxbits = nullptr;
     double *frames = nullptr;
     void *tube = nullptr, *out = nullptr;
     int16_t *pcm = nullptr;
-    long long total_tiles = 0, max_n_out = 0;
+    long long total_items = 0, max_n_out = 0;
+    int n_tiles = 0;
     size_t tube_elems = 0, out_elems = 0, pcm_elems = 0, frame_rows = 0;
 };
 
@@ -136,20 +139,26 @@ struct ChunkPlan {
     int u0 = 0, u1 = 0;
     std::vector<trm_cuda_utterance> desc;   // rebased to chunk-local offsets
     std::vector<int> order;
-    std::vector<long long> tile_base;
+    // resampler work decomposition (src_kernel.cuh): tiles of <= 32 utterances with one converter signature
+    std::vector<int> tile_utt, tile_nt;
+    std::vector<long long> tile_max_out, item_base;
     bool frames_dense = true;
     long long frames_lo = 0;                // host frame index of the span start (dense case)
     size_t frame_rows = 0;
     long long tube_lo = 0, out_lo = 0, pcm_lo = 0;   // host element offsets of the spans
     size_t tube_elems = 0, out_elems = 0, pcm_elems = 0;
-    long long total_tiles = 0, max_n_out = 0;
+    long long total_items = 0, max_n_out = 0;
+    size_t n_tiles() const { return tile_nt.size(); }
     size_t arena_bytes(size_t esz, bool want_pcm) const
     {
         size_t n = desc.size(), b = 0;
         auto add = [&](size_t x) { b = align_up(b, 256) + x; };
         add(n * sizeof(trm_cuda_utterance));
         add(n * sizeof(int));
-        add((n + 1) * sizeof(long long));
+        add(tile_utt.size() * sizeof(int));
+        add(tile_nt.size() * sizeof(int));
+        add(tile_max_out.size() * sizeof(long long));
+        add(item_base.size() * sizeof(long long));
         add(n * sizeof(unsigned long long));
         add(frame_rows * 128);
         add(tube_elems * esz);
@@ -161,7 +170,9 @@ struct ChunkPlan {
     {
         size_t n = desc.size();
         return align_up(n * sizeof(trm_cuda_utterance), 256) + align_up(n * sizeof(int), 256) +
-               align_up((n + 1) * sizeof(long long), 256) + align_up(n * sizeof(unsigned long long), 256);
+               align_up(tile_utt.size() * sizeof(int), 256) + align_up(tile_nt.size() * sizeof(int), 256) +
+               align_up(tile_max_out.size() * sizeof(long long), 256) + align_up(item_base.size() * sizeof(long long), 256) +
+               align_up(n * sizeof(unsigned long long), 256);
     }
 };
 
@@ -219,7 +230,6 @@ void plan_chunk(const trm_cuda_utterance *desc, int u0, int u1, ChunkPlan &p)
     p.pcm_elems = (size_t)align_up((size_t)(c_hi - c_lo), TRM_ALIGN_ELEMS);
     long long compact = 0;
     p.max_n_out = 0;
-    p.tile_base.assign(n + 1, 0);
     for (int i = 0; i < n; ++i) {
         auto &d = p.desc[i];
         if (p.frames_dense) d.frame_offset -= f_lo;
@@ -228,9 +238,41 @@ void plan_chunk(const trm_cuda_utterance *desc, int u0, int u1, ChunkPlan &p)
         d.out_offset -= o_lo;
         d.pcm_offset -= c_lo;
         p.max_n_out = std::max<long long>(p.max_n_out, d.n_out);
-        p.tile_base[i + 1] = p.tile_base[i] + (d.n_out + trm::SRC_TILE - 1) / trm::SRC_TILE;
     }
-    p.total_tiles = p.tile_base[n];
+    {
+        // resampler tiles: utterances that share (time-register increment, pad, direction, phase increment,
+        // ratio) share every filter coefficient; longest first so the 32 lanes of a tile finish together
+        std::vector<int> idx(n);
+        std::iota(idx.begin(), idx.end(), 0);
+        auto key = [&](int a) {
+            const auto &d = p.desc[a];
+            unsigned long long rb;
+            memcpy(&rb, &d.sampleRateRatio, sizeof rb);
+            return std::make_tuple(d.tri, d.padSize, d.upsample, d.phaseIncrement, rb);
+        };
+        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
+            const auto ka = key(a), kb = key(b);
+            if (ka != kb) return ka < kb;
+            return p.desc[a].n_out > p.desc[b].n_out;
+        });
+        p.tile_utt.clear(); p.tile_nt.clear(); p.tile_max_out.clear(); p.item_base.assign(1, 0);
+        for (int at = 0; at < n;) {
+            int end = at;
+            while (end < n && end - at < 32 && key(idx[end]) == key(idx[at])) ++end;
+            const auto &d0 = p.desc[idx[at]];
+            if (d0.n_out > 0) {
+                const int reach = d0.padSize + 1;
+                long long nt = (long long)((double)(trm::SRC_ROWS - 3 - 2 * reach) * 65536.0 / (double)d0.tri);
+                nt = std::max<long long>(trm::SRC_CHUNK, nt / trm::SRC_CHUNK * trm::SRC_CHUNK);
+                for (int r = 0; r < 32; ++r) p.tile_utt.push_back(at + r < end ? idx[at + r] : -1);
+                p.tile_nt.push_back((int)nt);
+                p.tile_max_out.push_back(d0.n_out);
+                p.item_base.push_back(p.item_base.back() + (d0.n_out + nt - 1) / nt);
+            }
+            at = end;
+        }
+        p.total_items = p.item_base.back();
+    }
     p.frame_rows = (size_t)(p.frames_dense ? (f_hi - f_lo) : compact);
     // longest utterances first, so the two utterances of a warp (and the warps of a CTA) finish together
     p.order.resize(n);
@@ -246,13 +288,17 @@ void carve(Arena &a, const ChunkPlan &p, size_t esz, bool want_pcm, DeviceChunk 
     dc.n = (int)n;
     dc.desc = (trm_cuda_utterance *)a.take(n * sizeof(trm_cuda_utterance));
     dc.order = (int *)a.take(n * sizeof(int));
-    dc.tile_base = (long long *)a.take((n + 1) * sizeof(long long));
+    dc.tile_utt = (int *)a.take(p.tile_utt.size() * sizeof(int));
+    dc.tile_nt = (int *)a.take(p.tile_nt.size() * sizeof(int));
+    dc.tile_max_out = (long long *)a.take(p.tile_max_out.size() * sizeof(long long));
+    dc.item_base = (long long *)a.take(p.item_base.size() * sizeof(long long));
     dc.maxbits = (unsigned long long *)a.take(n * sizeof(unsigned long long));
     dc.frames = (double *)a.take(p.frame_rows * 128);
     dc.tube = a.take(p.tube_elems * esz);
     dc.out = a.take(p.out_elems * esz);
     dc.pcm = want_pcm ? (int16_t *)a.take(p.pcm_elems * sizeof(int16_t)) : nullptr;
-    dc.total_tiles = p.total_tiles;
+    dc.total_items = p.total_items;
+    dc.n_tiles = (int)p.n_tiles();
     dc.max_n_out = p.max_n_out;
     dc.tube_elems = p.tube_elems; dc.out_elems = p.out_elems; dc.pcm_elems = p.pcm_elems; dc.frame_rows = p.frame_rows;
 }
@@ -262,16 +308,25 @@ int upload_plan(const ChunkPlan &p, const DeviceChunk &dc, unsigned char *stage,
 {
     const size_t n = p.desc.size();
     if (n == 0) return 0;
-    const void *src_desc = p.desc.data(), *src_order = p.order.data(), *src_tb = p.tile_base.data();
-    if (stage) {
-        unsigned char *q = stage;
-        memcpy(q, p.desc.data(), n * sizeof(trm_cuda_utterance)); src_desc = q; q += align_up(n * sizeof(trm_cuda_utterance), 256);
-        memcpy(q, p.order.data(), n * sizeof(int)); src_order = q; q += align_up(n * sizeof(int), 256);
-        memcpy(q, p.tile_base.data(), (n + 1) * sizeof(long long)); src_tb = q;
-    }
-    CK(cudaMemcpyAsync(dc.desc, src_desc, n * sizeof(trm_cuda_utterance), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(dc.order, src_order, n * sizeof(int), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(dc.tile_base, src_tb, (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, s));
+    unsigned char *q = stage;
+    auto put = [&](void *dst, const void *src, size_t bytes) -> int {
+        if (bytes == 0) return 0;
+        const void *from = src;
+        if (stage) {                       // pinned staging keeps the copy asynchronous
+            memcpy(q, src, bytes);
+            from = q;
+            q += align_up(bytes, 256);
+        }
+        CK(cudaMemcpyAsync(dst, from, bytes, cudaMemcpyHostToDevice, s));
+        return 0;
+    };
+    int rc;
+    if ((rc = put(dc.desc, p.desc.data(), n * sizeof(trm_cuda_utterance))) != 0) return rc;
+    if ((rc = put(dc.order, p.order.data(), n * sizeof(int))) != 0) return rc;
+    if ((rc = put(dc.tile_utt, p.tile_utt.data(), p.tile_utt.size() * sizeof(int))) != 0) return rc;
+    if ((rc = put(dc.tile_nt, p.tile_nt.data(), p.tile_nt.size() * sizeof(int))) != 0) return rc;
+    if ((rc = put(dc.tile_max_out, p.tile_max_out.data(), p.tile_max_out.size() * sizeof(long long))) != 0) return rc;
+    if ((rc = put(dc.item_base, p.item_base.data(), p.item_base.size() * sizeof(long long))) != 0) return rc;
     return 0;
 }
 
@@ -304,7 +359,9 @@ int launch_stage(trm_cuda_ctx *ctx, int precision, int stage, const DeviceChunk 
         CK(cudaMemsetAsync(dc.maxbits, 0, (size_t)dc.n * sizeof(unsigned long long), s));
         trm::SrcArgs a{};
         a.desc = dc.desc; a.n_utt = dc.n; a.tube = dc.tube; a.out = dc.out; a.maxbits = dc.maxbits;
-        a.table = f64 ? ctx->d_tab_f64 : ctx->d_tab_f32; a.tile_base = dc.tile_base; a.total_tiles = dc.total_tiles;
+        a.table = f64 ? ctx->d_tab_f64 : ctx->d_tab_f32;
+        a.tile_utt = dc.tile_utt; a.tile_nt = dc.tile_nt; a.tile_max_out = dc.tile_max_out; a.item_base = dc.item_base;
+        a.n_tiles = dc.n_tiles; a.total_items = dc.total_items;
         const trm::KernelInfo &ki = f64 ? ctx->info64 : ctx->info32;
         const int grid = ctx->sm_count * std::max(1, ki.src_ctas_per_sm);
         rc = f64 ? trm_k_src_f64(&a, grid, s) : trm_k_src_f32(&a, grid, s);

@@ -350,8 +350,7 @@ static int voice_lookup(voice_set *vs, const TRMInputParameters *ip, voice_key *
 /* ------------------------------------------------------------------------------------------------
  * per-utterance descriptor: -initWithInputData: (TRMTubeModel.m:196-241)
  * ---------------------------------------------------------------------------------------------- */
-#define SRC_TILE_OUT 1024
-#define SRC_WINDOW   4096
+#define SRC_ROWS 256          /* input rows the resampler stages per work item (kernel_args.h) */
 
 static void radrefl_coefficients(double coeff, double *f)
 {
@@ -370,7 +369,7 @@ static int describe(const TRMInputParameters *ip, int32_t n_frames, voice_set *v
     if (n_frames < 0) return set_err(TRM_ERR_PARAM, "negative frame count%s", "");
     if (ip->channels != 1 && ip->channels != 2) return set_err(TRM_ERR_PARAM, "channels must be 1 or 2%s", "");
     /* the resampler stages a bounded input window per output tile */
-    if ((double)SRC_TILE_OUT / r.ratio + 2.0 * (r.padSize + 2) + 8.0 > (double)SRC_WINDOW)
+    if ((double)(SRC_ROWS - 3 - 2 * (r.padSize + 1)) * r.ratio < 16.0)
         return set_err(TRM_ERR_PARAM, "outputRate / tube sample rate below the supported ratio%s", "");
     voice_key vk;
     const int voice = voice_lookup(vs, ip, &vk);

@@ -190,7 +190,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) tube_kernel(TubeArgs ar
     const R d = (R)D->dampingFactor;
 
     // ---- lane roles for the section-parallel phase ----------------------------------------------
-    const int role = (hl == 3) ? 1 : ((hl == 9 || hl == 15) ? 2 : 0);
+    const bool is3 = hl == 3, is_end = (hl == 9 || hl == 15);
+    R *const out_sm = (hl == 9) ? S.a.v.OUTM : S.a.v.OUTN;
     const bool kvar = (hl <= 10) && (hl != 5);
     const R kconst = (hl >= 11) ? (R)D->nasal_coeff[hl - 11] : (R)0;
     const bool has_tap = (hl >= 1 && hl <= 8);
@@ -395,10 +396,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) tube_kernel(TubeArgs ar
         for (int s = 0; s < TB; ++s) {
             const double di = S.INC[s];
             pos = pos + di;
-            if (pos > 511.0) pos -= 512.0;
+            pos = pos - ((pos > 511.0) ? 512.0 : 0.0);     // mod0: wraps only above 511 (TRMWavetable.m:28-34)
             const double pa = pos;
             pos = pos + di;
-            if (pos > 511.0) pos -= 512.0;
+            pos = pos - ((pos > 511.0) ? 512.0 : 0.0);
             if (hl == 0) *reinterpret_cast<double2 *>(&S.a.v.POS[2 * s]) = make_double2(pa, pos);
         }
         __syncwarp(FULL);
@@ -478,6 +479,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) tube_kernel(TubeArgs ar
         //     of an utterance compute on stale data and are never stored.
         // =========================================================================================
         R th_mine = (R)0;
+        // The three junction roles (two-port, 3-way, mouth/nose termination) are evaluated as straight-line
+        // predicated code: a divergent branch would execute the same instructions plus reconvergence overhead.
         if constexpr (FAST) {
 #pragma unroll
             for (int s = 0; s < TB; ++s) {
@@ -486,39 +489,34 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) tube_kernel(TubeArgs ar
                 y2 = y1; y1 = fr;
                 const float th = bc.w + (tb1 * thy);
                 thy = th;
-                if (s == hl) th_mine = th;
+                th_mine = (s == hl) ? th : th_mine;
 
                 float4 c = S.KF[s][kf_col];
+                const float4 c5 = S.KF[s][5];                    // .w = FC3, the 3-way lane's tap
                 if (!kvar) c = make_float4(fc0, fc1, fc2, (hl == 5) ? c.w : 0.0f);
-                float Rr, Lo, X3;
-                if (role == 0) {
-                    Rr = (c.x * a) - (c.y * b);                  // d(1+k) a - d k b
-                    Rr = Rr + (c.w * ((hl == 0) ? 0.0f : fr));
-                    Lo = (c.y * a) + (c.z * b);                  // d k a + d(1-k) b
-                    X3 = Lo;
-                } else if (role == 1) {
-                    const float tap3 = S.KF[s][5].w;
-                    Lo = ((c.y * a) + (c.x * b)) + (c.z * c3);   // d(aL-1) a + d aL b + d aU c
-                    Rr = (((c.x * a) + (c.y * b)) + (c.z * c3)) + (tap3 * fr);
-                    X3 = ((c.x * a) + (c.x * b)) + (c.w * c3);   // d aL (a+b) + d(aU-1) c
-                } else {
-                    const float refl = (c.x * a) - (f_b11 * ry); // a10 k a - b11 y
-                    ry = refl;
-                    Lo = d * refl;
-                    const float xr = c.y * a;                    // (1+k) a
-                    const float rad = ((f_a20 * xr) + (f_a21 * rx)) - (f_b21 * rY);
-                    rx = xr; rY = rad;
-                    if (hl == 9) S.a.v.OUTM[s] = rad; else S.a.v.OUTN[s] = rad;
-                    Rr = 0.0f; X3 = 0.0f;
-                }
+                // two-port:  Rr = d(1+k) a - d k b (+tap*fr),  Lo = d k a + d(1-k) b
+                // 3-way   :  Lo = d(aL-1) a + d aL b + d aU c,  Rr = d aL a + d(aL-1) b + d aU c + tap*fr,
+                //            X3 = d aL (a+b) + d(aU-1) c
+                // end     :  refl = a10 k a - b11 y;  Lo = d refl;  rad = a20 (1+k) a + a21 x1 - b21 y1
+                const float m0 = is3 ? c.y : (is_end ? 0.0f : c.y);
+                const float inj = is3 ? c5.w : ((hl == 0) ? 0.0f : c.w);
+                float Rr = is3 ? (((c.x * a) + (c.y * b)) + (c.z * c3)) : ((c.x * a) - (c.y * b));
+                Rr = Rr + (inj * fr);
+                const float lo2 = is3 ? (((c.y * a) + (c.x * b)) + (c.z * c3)) : ((m0 * a) + (c.z * b));
+                const float refl = (c.x * a) - (f_b11 * ry);
+                const float Lo = is_end ? (d * refl) : lo2;
+                const float X3 = is3 ? (((c.x * a) + (c.x * b)) + (c.w * c3)) : Lo;
+                const float xr = c.y * a;
+                const float rad = ((f_a20 * xr) + (f_a21 * rx)) - (f_b21 * rY);
+                if (is_end) { ry = refl; rx = xr; rY = rad; out_sm[s] = rad; }
                 const float nA = __shfl_sync(FULL, Rr, srcA);
                 const float nB = __shfl_sync(FULL, Lo, srcB);
                 const float nC = __shfl_sync(FULL, X3, srcC);
-                if (hl == 0) { a = (s1bot * d) + c.w; s1bot = Lo; }
-                else if (hl == 10) a = nC;
-                else a = nA;
+                const float a0 = (s1bot * d) + c.w;
+                a = (hl == 0) ? a0 : ((hl == 10) ? nC : nA);
+                s1bot = Lo;
                 b = nB;
-                if (hl == 3) c3 = nC;
+                c3 = nC;
             }
         } else {
 #pragma unroll
@@ -529,43 +527,36 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) tube_kernel(TubeArgs ar
                 // throat low-pass (TRMFilters.m:72-77)
                 const R th = S.BC[s][3] + (tb1 * thy);
                 thy = th;
-                if (s == hl) th_mine = th;
+                th_mine = (s == hl) ? th : th_mine;
 
                 const R kq = S.KQ[s][kq_col];
+                const R aU = S.KQ[s][11];
                 const R k = kvar ? kq : kconst;
                 const R inj = S.TAPV[s][tap_col];
-                R Rr, Lo, X3;
-                if (role == 0) {
-                    const R delta = k * (a - b);
-                    Rr = (a + delta) * d;
-                    if (has_tap) Rr = Rr + (inj * fr);
-                    Lo = (b + delta) * d;
-                    X3 = Lo;
-                } else if (role == 1) {
-                    const R aU = S.KQ[s][11];
-                    const R p = ((k * a) + (k * b)) + (aU * c3);
-                    Lo = (p - a) * d;
-                    Rr = ((p - b) * d) + (inj * fr);
-                    X3 = (p - c3) * d;
-                } else {
-                    const R x = k * a;
-                    const R refl = (f_a10 * x) - (f_b11 * ry);
-                    ry = refl;
-                    Lo = d * refl;
-                    const R xr = ((R)1 + k) * a;
-                    const R rad = ((f_a20 * xr) + (f_a21 * rx)) - (f_b21 * rY);
-                    rx = xr; rY = rad;
-                    if (hl == 9) S.a.v.OUTM[s] = rad; else S.a.v.OUTN[s] = rad;
-                    Rr = (R)0; X3 = (R)0;
-                }
+                // two-port junction (m:796-829); a termination is the same expression with no right neighbour
+                const R bb = is_end ? (R)0 : b;
+                const R delta = k * (a - bb);
+                // 3-way junction (m:810-813)
+                const R p = ((k * a) + (k * b)) + (aU * c3);
+                // termination: reflection + radiation filter pair (m:832-835,846-849; TRMFilters.m:47-60)
+                const R refl = (f_a10 * delta) - (f_b11 * ry);
+                const R xr = ((R)1 + k) * a;
+                const R rad = ((f_a20 * xr) + (f_a21 * rx)) - (f_b21 * rY);
+                if (is_end) { ry = refl; rx = xr; rY = rad; out_sm[s] = rad; }
+
+                R Rr = (is3 ? (p - b) : (a + delta)) * d;
+                if (has_tap) Rr = Rr + (inj * fr);
+                const R Lo = (is3 ? (p - a) : (is_end ? refl : (b + delta))) * d;
+                const R X3 = is3 ? ((p - c3) * d) : Lo;
+
                 const R nA = __shfl_sync(FULL, Rr, srcA);
                 const R nB = __shfl_sync(FULL, Lo, srcB);
                 const R nC = __shfl_sync(FULL, X3, srcC);
-                if (hl == 0) { a = (s1bot * d) + inj; s1bot = Lo; }
-                else if (hl == 10) a = nC;
-                else a = nA;
+                const R a0 = (s1bot * d) + inj;
+                a = (hl == 0) ? a0 : ((hl == 10) ? nC : nA);
+                s1bot = Lo;
                 b = nB;
-                if (hl == 3) c3 = nC;
+                c3 = nC;
             }
         }
         __syncwarp(FULL);
