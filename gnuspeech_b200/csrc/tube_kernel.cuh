@@ -136,6 +136,15 @@ __device__ __forceinline__ double amplitude_db(double dB)
     if (x >= 0.0) return 1.0;
     return exp10(x / 20.0);
 }
+// fast-mode amplitude(): 10^((dB-60)/20) as 2^(..), FP32 (relative error ~5e-7, i.e. -126 dB on a linear gain)
+__device__ __forceinline__ float amplitude_f(float dB)
+{
+    const float x = dB - 60.0f;
+    if (x <= -60.0f) return 0.0f;
+    if (x >= 0.0f) return 1.0f;
+    return exp2f(x * 0.16609640474436813f);
+}
+
 // Glottal table value at integer index i for the current closure point (TRMWavetable.m:78-102 init,
 // :117-162 update, vDSP order 1 - (j*j)*(1/(L*L))).  The reference rewrites the table every sample; the
 // table is a pure function of the current amplitude, so it is evaluated on look-up instead.
@@ -302,81 +311,137 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) tube_kernel(TubeArgs ar
         //     so it costs issue slots but no serial latency, and FP32 here is the dominant error source).
         // =========================================================================================
         const double *prm = S.a.P[hl];
-        const double ax_d = amplitude_db(prm[1]);
-        const R ax = (R)ax_d;
-        const R ah1 = (R)amplitude_db(prm[2]);
         {
-            // pitch -> f0 -> increment
+            // pitch -> f0 -> increment: always double (a relative error here is a frequency error whose phase
+            // drift grows with the length of the utterance)
             const double f0 = 220.0 * exp2((prm[0] + 3.0) / 12.0);
             S.INC[hl] = (f0 / 2.0) * D->basicIncrement;
         }
-        {
+        double ax_d;
+        R ax, ah1;
+        R bp_alpha2;
+        if constexpr (FAST) {
+            // ---- fast mode: FP32 coefficient math in cancellation-free form -----------------------------------
+            // amplitude(): 10^((dB-60)/20) = 2^((dB-60)*log2(10)/20)
+            const float axf = amplitude_f((float)prm[1]);
+            ax_d = (double)axf;
+            {
+                // the glottal closure point rint(ax*tnDelta) is the one discontinuous function of a parameter on
+                // the path: when the FP32 product is near a rounding boundary, decide with the FP64 amplitude
+                const float tq = axf * (float)D->tnDelta;
+                const float fr = tq - floorf(tq);
+                if (fabsf(fr - 0.5f) < 2e-3f) ax_d = amplitude_db(prm[1]);
+            }
+            ax = axf;
+            ah1 = amplitude_f((float)prm[2]);
+            const float fa = amplitude_f((float)prm[3]);
+            const float dd = (float)D->dampingFactor;
+            float r2[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { const float r = (float)prm[7 + q]; r2[q] = r * r; }
+            float tap[8];
+            {
+                const double fpos = prm[4];
+                const int ipos = (int)fpos;
+                const float comp = (float)(fpos - (double)ipos);
+                const float t0 = (1.0f - comp) * fa, t1 = comp * fa;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) tap[q] = (q == ipos) ? t0 : ((ipos >= 0 && q == ipos + 1) ? t1 : 0.0f);
+            }
+            float4 *kf = S.KF[hl];
+            // two-port junction between squared radii (ra2, rb2): k = (ra2-rb2)/(ra2+rb2),
+            // 1+k = 2 ra2/(ra2+rb2), 1-k = 2 rb2/(ra2+rb2): no cancellation next to k = +-1
+            auto two_port = [&](float ra2, float rb2, float tapv) {
+                const float inv = dd / (ra2 + rb2);
+                return make_float4(2.0f * ra2 * inv, (ra2 - rb2) * inv, 2.0f * rb2 * inv, tapv);
+            };
+            {
+                const float4 c0 = two_port(r2[0], r2[1], 0.0f);
+                kf[0].x = c0.x; kf[0].y = c0.y; kf[0].z = c0.z;          // .w (glottal input) is written by A2
+            }
+            kf[1] = two_port(r2[1], r2[2], tap[0]);
+            kf[2] = two_port(r2[2], r2[3], tap[1]);
+            kf[4] = two_port(r2[3], r2[4], tap[3]);
+            kf[6] = two_port(r2[4], r2[5], tap[5]);
+            kf[7] = two_port(r2[5], r2[6], tap[6]);
+            kf[8] = two_port(r2[6], r2[7], tap[7]);
+            {
+                // 3-way junction: aL = 2 r4^2/s, aL-1 = -v^2/s, aU = 2 v^2/s, aU-1 = (v^2 - 2 r4^2)/s, s = 2 r4^2 + v^2
+                const float vel = (float)prm[15], v2 = vel * vel;
+                const float inv = dd / ((r2[3] + r2[3]) + v2);
+                kf[3] = make_float4(2.0f * r2[3] * inv, -v2 * inv, 2.0f * v2 * inv, (v2 - (r2[3] + r2[3])) * inv);
+                kf[5] = make_float4(0.0f, 0.0f, 0.0f, tap[2]);            // FC3 for the 3-way lane
+                kf[10] = two_port(v2, (float)D->nr1sq, 0.0f);
+                kf[11] = make_float4(0.0f, 0.0f, 0.0f, tap[4]);           // FC5 for the pure-delay lane 5
+            }
+            {
+                // mouth termination: {a10 k8, 1+k8}
+                const float ap2 = (float)D->apScale2;
+                const float inv = 1.0f / (r2[7] + ap2);
+                kf[9] = make_float4((float)D->mouth[0] * ((r2[7] - ap2) * inv), 2.0f * r2[7] * inv, 0.0f, 0.0f);
+            }
+            {
+                // band-pass coefficients with the output factor 2 folded in:
+                // beta = (1-tan u)/(2(1+tan u)) = (cos u - sin u)/(2(cos u + sin u))
+                const float sr = (float)D->sampleRate;
+                const float pi = 3.14159265358979323846f;
+                float su, cu;
+                sincosf((pi * (float)prm[6]) / sr, &su, &cu);
+                const float cosv = cosf(((2.0f * pi) * (float)prm[5]) / sr);
+                const float beta2 = (cu - su) / (cu + su);                 // 2*beta
+                S.BC[hl][2] = beta2;
+                S.BC[hl][1] = (1.0f + beta2) * cosv;                       // 2*gamma = 2(0.5+beta) cos v
+                bp_alpha2 = 0.5f - 0.5f * beta2;                           // 2*alpha = (0.5-beta)
+            }
+        } else {
+            // ---- conformance mode: the reference's operations in the reference's order, FP64 ----------------
+            ax_d = amplitude_db(prm[1]);
+            ax = (R)ax_d;
+            ah1 = (R)amplitude_db(prm[2]);
             double r2[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) { const double r = prm[7 + q]; r2[q] = r * r; }
-            double kk[10];                   // k of lanes 0,1,2,(3 unused),4,(5 unused),6,7,8,9
-            kk[0] = (r2[0] - r2[1]) / (r2[0] + r2[1]);
-            kk[1] = (r2[1] - r2[2]) / (r2[1] + r2[2]);
-            kk[2] = (r2[2] - r2[3]) / (r2[2] + r2[3]);
-            kk[4] = (r2[3] - r2[4]) / (r2[3] + r2[4]);
-            kk[6] = (r2[4] - r2[5]) / (r2[4] + r2[5]);
-            kk[7] = (r2[5] - r2[6]) / (r2[5] + r2[6]);
-            kk[8] = (r2[6] - r2[7]) / (r2[6] + r2[7]);
+            R *kq = S.KQ[hl];
+            kq[0] = (R)((r2[0] - r2[1]) / (r2[0] + r2[1]));
+            kq[1] = (R)((r2[1] - r2[2]) / (r2[1] + r2[2]));
+            kq[2] = (R)((r2[2] - r2[3]) / (r2[2] + r2[3]));
+            kq[4] = (R)((r2[3] - r2[4]) / (r2[3] + r2[4]));
+            kq[6] = (R)((r2[4] - r2[5]) / (r2[4] + r2[5]));
+            kq[7] = (R)((r2[5] - r2[6]) / (r2[5] + r2[6]));
+            kq[8] = (R)((r2[6] - r2[7]) / (r2[6] + r2[7]));
             const double ap2 = D->apScale2;
-            kk[9] = (r2[7] - ap2) / (r2[7] + ap2);
+            kq[9] = (R)((r2[7] - ap2) / (r2[7] + ap2));
             const double vel = prm[15];
             const double v2 = vel * vel;
             const double sum = 2.0 / ((r2[3] + r2[3]) + v2);
-            const double aL = sum * r2[3], aU = sum * v2;
+            kq[3] = (R)(sum * r2[3]);
+            kq[11] = (R)(sum * v2);
             const double n2 = D->nr1sq;
-            const double nc1 = (v2 - n2) / (v2 + n2);
-            // frication taps (m:748-765)
-            const double fa = amplitude_db(prm[3]);
-            const double fpos = prm[4];
-            const int ipos = (int)fpos;
-            const double comp = fpos - (double)ipos;
-            const double rem = 1.0 - comp;
-            const R t0 = (R)(rem * fa), t1 = (R)(comp * fa);
-            if constexpr (FAST) {
-                const double dd = D->dampingFactor;
-                float4 *kf = S.KF[hl];
-                float tap[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) tap[q] = (q == ipos) ? t0 : ((ipos >= 0 && q == ipos + 1) ? t1 : 0.0f);
-#pragma unroll
-                for (int j = 0; j <= 8; ++j) {
-                    if (j == 3 || j == 5) continue;
-                    const double k = kk[j];
-                    // .w of lane 0 (glottal input) is written by phase A2
-                    if (j == 0) { kf[0].x = (float)(dd * (1.0 + k)); kf[0].y = (float)(dd * k); kf[0].z = (float)(dd * (1.0 - k)); }
-                    else kf[j] = make_float4((float)(dd * (1.0 + k)), (float)(dd * k), (float)(dd * (1.0 - k)), tap[j - 1]);
-                }
-                kf[3] = make_float4((float)(dd * aL), (float)(dd * (aL - 1.0)), (float)(dd * aU), (float)(dd * (aU - 1.0)));
-                kf[5] = make_float4(0.0f, 0.0f, 0.0f, tap[2]);            // FC3 for the 3-way lane
-                kf[9] = make_float4((float)(D->mouth[0] * kk[9]), (float)(1.0 + kk[9]), 0.0f, 0.0f);
-                kf[10] = make_float4((float)(dd * (1.0 + nc1)), (float)(dd * nc1), (float)(dd * (1.0 - nc1)), 0.0f);
-                kf[11] = make_float4(0.0f, 0.0f, 0.0f, tap[4]);           // FC5 for the pure-delay lane 5
-            } else {
-                R *kq = S.KQ[hl];
-                kq[0] = kk[0]; kq[1] = kk[1]; kq[2] = kk[2]; kq[3] = aL; kq[4] = kk[4];
-                kq[6] = kk[6]; kq[7] = kk[7]; kq[8] = kk[8]; kq[9] = kk[9]; kq[10] = nc1; kq[11] = aU;
+            kq[10] = (R)((v2 - n2) / (v2 + n2));
+            {
+                // frication taps (m:748-765)
+                const double fa = amplitude_db(prm[3]);
+                const double fpos = prm[4];
+                const int ipos = (int)fpos;
+                const double comp = fpos - (double)ipos;
+                const double rem = 1.0 - comp;
+                const R t0 = (R)(rem * fa), t1 = (R)(comp * fa);
                 R *tv = S.TAPV[hl];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) tv[q + 1] = (q == ipos) ? t0 : ((ipos >= 0 && q == ipos + 1) ? t1 : (R)0);
             }
-        }
-        R bp_alpha2;
-        {
-            // band-pass coefficients (TRMFilters.m:9-17).  The filter output is 2*(...): the factor is folded
-            // into the coefficients, which is exact (scaling by 2 commutes with rounding).
-            const double sr = D->sampleRate;
-            const double pi = 3.14159265358979323846;
-            const double tanv = tan((pi * prm[6]) / sr);
-            const double cosv = cos(((2.0 * pi) * prm[5]) / sr);
-            const double beta = (1.0 - tanv) / (2.0 * (1.0 + tanv));
-            S.BC[hl][2] = (R)(2.0 * beta);
-            S.BC[hl][1] = (R)(2.0 * ((0.5 + beta) * cosv));
-            bp_alpha2 = (R)(2.0 * ((0.5 - beta) / 2.0));
+            {
+                // band-pass coefficients (TRMFilters.m:9-17).  The filter output is 2*(...): the factor is folded
+                // into the coefficients, which is exact (scaling by 2 commutes with rounding).
+                const double sr = D->sampleRate;
+                const double pi = 3.14159265358979323846;
+                const double tanv = tan((pi * prm[6]) / sr);
+                const double cosv = cos(((2.0 * pi) * prm[5]) / sr);
+                const double beta = (1.0 - tanv) / (2.0 * (1.0 + tanv));
+                S.BC[hl][2] = (R)(2.0 * beta);
+                S.BC[hl][1] = (R)(2.0 * ((0.5 + beta) * cosv));
+                bp_alpha2 = (R)(2.0 * ((0.5 - beta) / 2.0));
+            }
         }
         // noise (TRMUtility.m:71-85 as the equivalent MCG mod 2^44) + one-zero low-pass (TRMFilters.m:81-86)
         R lp_noise;
