@@ -10,7 +10,7 @@ namespace trm {
 constexpr int TB = 16;           // samples per block == lanes per utterance
 constexpr int FIR_TAPS = 49;     // TRMFIRFilter.h:7-9 fixed design -> 49 taps (checked on the host)
 constexpr int FIR_HIST = 24;     // (FIR_TAPS-1)/2 previous even / odd oscillator values
-constexpr int FRAME_CHUNK = 4;   // control frames per bulk copy
+constexpr int FRAME_CHUNK = 2;   // control frames per bulk copy (256 B)
 constexpr int WARPS_PER_CTA = 2;
 constexpr int UTT_PER_CTA = WARPS_PER_CTA * 2;
 

@@ -242,9 +242,9 @@ static int derive_rates(const TRMInputParameters *ip, rates_t *r)
     const double c = sound_speed(ip->temperature);
     r->controlPeriod = rint((c * 10 * 100.0) / (ip->length * ip->controlRate));
     r->sampleRate = ip->controlRate * r->controlPeriod;
-    /* the waveguide kernel stages 4 frames per bulk copy and consumes 16 samples per block: at most one
-     * staging-buffer switch per block needs controlPeriod >= 4 (the reference's range gives >= 17) */
-    if (r->controlPeriod < 4 || r->sampleRate < 1) return set_err(TRM_ERR_PARAM, "control period < 4 samples%s", "");
+    /* the waveguide kernel stages 2 frames per bulk copy and consumes 16 samples per block: at most one
+     * staging-buffer switch per block needs controlPeriod >= 8 (the reference's range gives >= 17) */
+    if (r->controlPeriod < 8 || r->sampleRate < 1) return set_err(TRM_ERR_PARAM, "control period < 8 samples%s", "");
     r->actualTubeLength = (c * 10 * 100.0) / r->sampleRate;
     /* TRMSampleRateConverter.m:80-96 */
     r->ratio = (double)ip->outputRate / (double)r->sampleRate;

@@ -65,7 +65,9 @@ struct alignas(16) UttSmem {
         struct {
             double POS[2 * TB];              // oscillator positions of the two 2x-rate steps of each sample
             R OUTM[TB], OUTN[TB];            // mouth / nose radiation outputs
+            R TH[TB];                        // throat low-pass output
             R YB[TB];                        // finished tube-rate samples, for the vector store
+            R SCR[TB];                       // scratch: where non-terminal lanes dump their (unused) radiation value
         } v;
     } a;
     double INC[TB];                          // oscillator increment (f0/2)*basicIncrement
@@ -73,12 +75,15 @@ struct alignas(16) UttSmem {
                                              //   [0] 2*alpha*(x[n]-x[n-2])  [1] 2*gamma  [2] 2*beta  (band-pass)
                                              //   [3] ta0*(pulse*VT_SCALE)                           (throat)
     // conformance mode (R = double): reference-order arithmetic needs one coefficient per junction
-    R KQ[sizeof(R) == 8 ? TB : 1][13];       // junction coefficient per lane (cols 0..10), alphaU (11)
-    R TAPV[sizeof(R) == 8 ? TB : 1][9];      // col 0: glottal input; cols 1..8: frication taps FC1..FC8
-    // fast mode (R = float): cancellation-free forms with the damping folded in, one 128-bit load per lane
-    //   two-port lanes : {d(1+k), d k, d(1-k), injection}      mouth lane 9 : {a10 k, 1+k, -, -}
-    //   3-way lane 3   : {d aL, d(aL-1), d aU, d(aU-1)}, its tap in column 5 (.w)
-    float4 KF[sizeof(R) == 4 ? TB : 1][13];
+    R KQ[sizeof(R) == 8 ? TB : 1][sizeof(R) == 8 ? 17 : 1];   // junction coefficient per lane (cols 0..15), alphaU (16)
+    R TAPV[sizeof(R) == 8 ? TB : 1][sizeof(R) == 8 ? 9 : 1];  // col 0: glottal input; cols 1..8: taps FC1..FC8
+    // fast mode (R = float): cancellation-free forms with the damping d folded in, one 128-bit load per lane.
+    // Every lane evaluates   Rr = x*a + (+-y)*b + rc*c + inj*fr,   Lo = y*a + z*b + rc*c   on its own tuple {x,y,z,w}:
+    //   two-port lanes : {d(1+k), d k, d(1-k), tap}     (lane 0: w = glottal input; constant lanes are pre-filled)
+    //   3-way lane 3   : {d aL, d(aL-1), d aL, d(aU-1)}, rc = d aU and its tap come from Z3
+    //   termination    : {0, d a10 k, -b11, 1+k}        (its b register carries the previous Lo)
+    float4 KF[sizeof(R) == 4 ? TB : 1][sizeof(R) == 4 ? 17 : 1];
+    float2 Z3[sizeof(R) == 4 ? TB : 1];      // {d aU, FC3 tap} for the 3-way lane
     R HE[FIR_HIST + TB], HO[FIR_HIST + TB];  // oscillator history, even / odd 2x-rate samples
 };
 
@@ -136,6 +141,20 @@ __device__ __forceinline__ double amplitude_db(double dB)
     if (x >= 0.0) return 1.0;
     return exp10(x / 20.0);
 }
+// Bit-wise select (one LOP3 per 32 bits): m = all ones -> x, m = 0 -> y.  Used instead of ?: in the junction
+// loop so that the per-lane roles stay straight-line code (the compiler turns lane-dependent ternaries into
+// divergent branch regions with reconvergence barriers and a divergence check before every shuffle).
+__device__ __forceinline__ float blend(unsigned m, float x, float y)
+{
+    return __uint_as_float((__float_as_uint(x) & m) | (__float_as_uint(y) & ~m));
+}
+__device__ __forceinline__ double blend(unsigned m, double x, double y)
+{
+    const unsigned lo = ((unsigned)__double2loint(x) & m) | ((unsigned)__double2loint(y) & ~m);
+    const unsigned hi = ((unsigned)__double2hiint(x) & m) | ((unsigned)__double2hiint(y) & ~m);
+    return __hiloint2double((int)hi, (int)lo);
+}
+
 // fast-mode amplitude(): 10^((dB-60)/20) as 2^(..), FP32 (relative error ~5e-7, i.e. -126 dB on a linear gain)
 __device__ __forceinline__ float amplitude_f(float dB)
 {
@@ -199,28 +218,24 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) tube_kernel(TubeArgs ar
     const R d = (R)D->dampingFactor;
 
     // ---- lane roles for the section-parallel phase ----------------------------------------------
-    const bool is3 = hl == 3, is_end = (hl == 9 || hl == 15);
-    R *const out_sm = (hl == 9) ? S.a.v.OUTM : S.a.v.OUTN;
-    const bool kvar = (hl <= 10) && (hl != 5);
-    const R kconst = (hl >= 11) ? (R)D->nasal_coeff[hl - 11] : (R)0;
-    const bool has_tap = (hl >= 1 && hl <= 8);
-    const int tap_col = (hl <= 8) ? hl : 0;
-    const int kq_col = kvar ? hl : 12;
     constexpr bool FAST = sizeof(R) == 4;
-    // fast mode: constant-coefficient lanes (pure delay 5, nasal 11..14, nose 15) keep their forms in registers;
-    // lane 5 still reads its frication tap (FC5) from column 11
-    const int kf_col = kvar ? hl : 11;
-    float fc0 = 0.0f, fc1 = 0.0f, fc2 = 0.0f;
-    if (FAST && !kvar) {
-        const double dd = D->dampingFactor;
-        const double k = (hl >= 11) ? D->nasal_coeff[hl - 11] : 0.0;
-        if (hl == 15) { fc0 = (float)(D->nose[0] * k); fc1 = (float)(1.0 + k); }
-        else { fc0 = (float)(dd * (1.0 + k)); fc1 = (float)(dd * k); fc2 = (float)(dd * (1.0 - k)); }
-    }
+    const bool is3 = hl == 3, is_end = (hl == 9 || hl == 15);
+    const bool kvar = (hl <= 10) && (hl != 5);            // coefficient changes every sample
+    const bool has_tap = (hl >= 1 && hl <= 8);
+    const unsigned m3 = is3 ? 0xFFFFFFFFu : 0u, me = is_end ? 0xFFFFFFFFu : 0u;
+    const unsigned m0 = (hl == 0) ? 0xFFFFFFFFu : 0u, m10 = (hl == 10) ? 0xFFFFFFFFu : 0u;
+    const int tap_col = (hl <= 8) ? hl : 0;
     const int srcA = (lane & 16) | ((hl - 1) & 15), srcB = (lane & 16) | ((hl + 1) & 15);
     const int srcC = (lane & 16) | ((hl == 3) ? 10 : 3);
     const double *fc = (hl == 9) ? D->mouth : D->nose;
     const R f_a10 = (R)fc[0], f_b11 = (R)fc[1], f_a20 = (R)fc[2], f_a21 = (R)fc[3], f_b21 = (R)fc[4];
+    // terminal lanes write their radiation output to OUTM / OUTN, everyone else to a scratch word
+    R *const out_sm = (hl == 9) ? S.a.v.OUTM : ((hl == 15) ? S.a.v.OUTN : &S.a.v.SCR[hl]);
+    const int out_step = is_end ? 1 : 0;
+    // fast mode: sign of the y*b term of Rr, gate of the 3-way terms, gate of the frication tap
+    const float sgn_y = is3 ? 1.0f : -1.0f, gate3 = is3 ? 1.0f : 0.0f;
+    const float gate_tap = (has_tap && !is3) ? 1.0f : 0.0f;
+    const R gate_inj = has_tap ? (R)1 : (R)0;
 
     // ---- shared-memory init + first two frame chunks ---------------------------------------------
     {
@@ -229,6 +244,19 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) tube_kernel(TubeArgs ar
         uint32_t *w = reinterpret_cast<uint32_t *>(&S.a);
         constexpr int NW = (int)((sizeof(UttSmem<R>) - offsetof(UttSmem<R>, a)) / 4);
         for (int i = hl; i < NW; i += 16) w[i] = 0u;
+    }
+    __syncwarp(FULL);
+    if (!kvar) {
+        // junctions whose coefficient never changes (pure delay 5, nasal 11..14, nose 15): fill their column once
+        const double dd = D->dampingFactor;
+        const double k = (hl >= 11) ? D->nasal_coeff[hl - 11] : 0.0;
+        if constexpr (FAST) {
+            const float4 c = (hl == 15) ? make_float4(0.0f, (float)(dd * D->nose[0] * k), (float)(-D->nose[1]), (float)(1.0 + k))
+                                        : make_float4((float)(dd * (1.0 + k)), (float)(dd * k), (float)(dd * (1.0 - k)), 0.0f);
+            for (int t = 0; t < TB; ++t) S.KF[t][hl] = c;
+        } else {
+            for (int t = 0; t < TB; ++t) S.KQ[t][hl] = (R)k;
+        }
     }
     __syncwarp(FULL);
     const bool feeds = n_tube > 0;                        // this half stages frames
@@ -362,6 +390,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) tube_kernel(TubeArgs ar
             kf[1] = two_port(r2[1], r2[2], tap[0]);
             kf[2] = two_port(r2[2], r2[3], tap[1]);
             kf[4] = two_port(r2[3], r2[4], tap[3]);
+            kf[5].w = tap[4];                                             // pure-delay lane: only its tap varies
             kf[6] = two_port(r2[4], r2[5], tap[5]);
             kf[7] = two_port(r2[5], r2[6], tap[6]);
             kf[8] = two_port(r2[6], r2[7], tap[7]);
@@ -369,16 +398,16 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) tube_kernel(TubeArgs ar
                 // 3-way junction: aL = 2 r4^2/s, aL-1 = -v^2/s, aU = 2 v^2/s, aU-1 = (v^2 - 2 r4^2)/s, s = 2 r4^2 + v^2
                 const float vel = (float)prm[15], v2 = vel * vel;
                 const float inv = dd / ((r2[3] + r2[3]) + v2);
-                kf[3] = make_float4(2.0f * r2[3] * inv, -v2 * inv, 2.0f * v2 * inv, (v2 - (r2[3] + r2[3])) * inv);
-                kf[5] = make_float4(0.0f, 0.0f, 0.0f, tap[2]);            // FC3 for the 3-way lane
+                const float daL = 2.0f * r2[3] * inv;
+                kf[3] = make_float4(daL, -v2 * inv, daL, (v2 - (r2[3] + r2[3])) * inv);
+                S.Z3[hl] = make_float2(2.0f * v2 * inv, tap[2]);
                 kf[10] = two_port(v2, (float)D->nr1sq, 0.0f);
-                kf[11] = make_float4(0.0f, 0.0f, 0.0f, tap[4]);           // FC5 for the pure-delay lane 5
             }
             {
-                // mouth termination: {a10 k8, 1+k8}
+                // mouth termination: Lo = d a10 k8 a - b11 Lo_prev, radiation input (1+k8) a
                 const float ap2 = (float)D->apScale2;
                 const float inv = 1.0f / (r2[7] + ap2);
-                kf[9] = make_float4((float)D->mouth[0] * ((r2[7] - ap2) * inv), 2.0f * r2[7] * inv, 0.0f, 0.0f);
+                kf[9] = make_float4(0.0f, dd * (float)D->mouth[0] * ((r2[7] - ap2) * inv), -(float)D->mouth[1], 2.0f * r2[7] * inv);
             }
             {
                 // band-pass coefficients with the output factor 2 folded in:
@@ -415,7 +444,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) tube_kernel(TubeArgs ar
             const double v2 = vel * vel;
             const double sum = 2.0 / ((r2[3] + r2[3]) + v2);
             kq[3] = (R)(sum * r2[3]);
-            kq[11] = (R)(sum * v2);
+            kq[16] = (R)(sum * v2);
             const double n2 = D->nr1sq;
             kq[10] = (R)((v2 - n2) / (v2 + n2));
             {
@@ -543,44 +572,38 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) tube_kernel(TubeArgs ar
         //     Always TB iterations (fully unrolled, constant shared-memory offsets); samples past the end
         //     of an utterance compute on stale data and are never stored.
         // =========================================================================================
-        R th_mine = (R)0;
-        // The three junction roles (two-port, 3-way, mouth/nose termination) are evaluated as straight-line
-        // predicated code: a divergent branch would execute the same instructions plus reconvergence overhead.
+        // The three junction roles (two-port, 3-way, mouth/nose termination) run as ONE straight-line instruction
+        // stream: every lane evaluates the same expressions on role-routed operands (LOP3 blends / 0-1 gates), so
+        // there is no divergent region, no reconvergence barrier and no divergence check before the shuffles.
         if constexpr (FAST) {
 #pragma unroll
             for (int s = 0; s < TB; ++s) {
                 const float4 bc = *reinterpret_cast<const float4 *>(S.BC[s]);
-                const float fr = (bc.x + (bc.y * y1)) - (bc.z * y2);
+                const float fr = (bc.x + (bc.y * y1)) - (bc.z * y2);       // frication band-pass (TRMFilters.m:19-29)
                 y2 = y1; y1 = fr;
-                const float th = bc.w + (tb1 * thy);
+                const float th = bc.w + (tb1 * thy);                       // throat low-pass (TRMFilters.m:72-77)
                 thy = th;
-                th_mine = (s == hl) ? th : th_mine;
+                S.a.v.TH[s] = th;
 
-                float4 c = S.KF[s][kf_col];
-                const float4 c5 = S.KF[s][5];                    // .w = FC3, the 3-way lane's tap
-                if (!kvar) c = make_float4(fc0, fc1, fc2, (hl == 5) ? c.w : 0.0f);
-                // two-port:  Rr = d(1+k) a - d k b (+tap*fr),  Lo = d k a + d(1-k) b
-                // 3-way   :  Lo = d(aL-1) a + d aL b + d aU c,  Rr = d aL a + d(aL-1) b + d aU c + tap*fr,
-                //            X3 = d aL (a+b) + d(aU-1) c
-                // end     :  refl = a10 k a - b11 y;  Lo = d refl;  rad = a20 (1+k) a + a21 x1 - b21 y1
-                const float m0 = is3 ? c.y : (is_end ? 0.0f : c.y);
-                const float inj = is3 ? c5.w : ((hl == 0) ? 0.0f : c.w);
-                float Rr = is3 ? (((c.x * a) + (c.y * b)) + (c.z * c3)) : ((c.x * a) - (c.y * b));
-                Rr = Rr + (inj * fr);
-                const float lo2 = is3 ? (((c.y * a) + (c.x * b)) + (c.z * c3)) : ((m0 * a) + (c.z * b));
-                const float refl = (c.x * a) - (f_b11 * ry);
-                const float Lo = is_end ? (d * refl) : lo2;
-                const float X3 = is3 ? (((c.x * a) + (c.x * b)) + (c.w * c3)) : Lo;
-                const float xr = c.y * a;
+                const float4 c = S.KF[s][hl];
+                const float2 z3 = S.Z3[s];
+                const float rc = z3.x * gate3;                             // d aU on the 3-way lane, 0 elsewhere
+                const float inj = (c.w * gate_tap) + (z3.y * gate3);
+                const float Rr = (((c.x * a) + ((c.y * sgn_y) * b)) + (rc * c3)) + (inj * fr);
+                const float Lo = ((c.y * a) + (c.z * b)) + (rc * c3);
+                const float x3 = ((c.x * a) + (c.x * b)) + (c.w * c3);     // 3-way: d aL (a+b) + d(aU-1) c
+                const float X3 = blend(m3, x3, Lo);
+                const float xr = c.w * a;                                  // termination: (1+k) a
                 const float rad = ((f_a20 * xr) + (f_a21 * rx)) - (f_b21 * rY);
-                if (is_end) { ry = refl; rx = xr; rY = rad; out_sm[s] = rad; }
+                rx = xr; rY = rad;
+                out_sm[s * out_step] = rad;
                 const float nA = __shfl_sync(FULL, Rr, srcA);
                 const float nB = __shfl_sync(FULL, Lo, srcB);
                 const float nC = __shfl_sync(FULL, X3, srcC);
-                const float a0 = (s1bot * d) + c.w;
-                a = (hl == 0) ? a0 : ((hl == 10) ? nC : nA);
+                const float a0 = (s1bot * d) + c.w;                        // glottis end (m:792)
+                a = blend(m0, a0, blend(m10, nC, nA));
                 s1bot = Lo;
-                b = nB;
+                b = blend(me, Lo, nB);                                     // a termination feeds back its own Lo
                 c3 = nC;
             }
         } else {
@@ -592,33 +615,33 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) tube_kernel(TubeArgs ar
                 // throat low-pass (TRMFilters.m:72-77)
                 const R th = S.BC[s][3] + (tb1 * thy);
                 thy = th;
-                th_mine = (s == hl) ? th : th_mine;
+                S.a.v.TH[s] = th;
 
-                const R kq = S.KQ[s][kq_col];
-                const R aU = S.KQ[s][11];
-                const R k = kvar ? kq : kconst;
+                const R k = S.KQ[s][hl];
+                const R aU = S.KQ[s][16];
                 const R inj = S.TAPV[s][tap_col];
                 // two-port junction (m:796-829); a termination is the same expression with no right neighbour
-                const R bb = is_end ? (R)0 : b;
+                const R bb = blend(me, (R)0, b);
                 const R delta = k * (a - bb);
                 // 3-way junction (m:810-813)
                 const R p = ((k * a) + (k * b)) + (aU * c3);
                 // termination: reflection + radiation filter pair (m:832-835,846-849; TRMFilters.m:47-60)
                 const R refl = (f_a10 * delta) - (f_b11 * ry);
+                ry = refl;
                 const R xr = ((R)1 + k) * a;
                 const R rad = ((f_a20 * xr) + (f_a21 * rx)) - (f_b21 * rY);
-                if (is_end) { ry = refl; rx = xr; rY = rad; out_sm[s] = rad; }
+                rx = xr; rY = rad;
+                out_sm[s * out_step] = rad;
 
-                R Rr = (is3 ? (p - b) : (a + delta)) * d;
-                if (has_tap) Rr = Rr + (inj * fr);
-                const R Lo = (is3 ? (p - a) : (is_end ? refl : (b + delta))) * d;
-                const R X3 = is3 ? ((p - c3) * d) : Lo;
+                const R Rr = (blend(m3, p - b, a + delta) * d) + ((inj * gate_inj) * fr);
+                const R Lo = blend(m3, p - a, blend(me, refl, b + delta)) * d;
+                const R X3 = blend(m3, (p - c3) * d, Lo);
 
                 const R nA = __shfl_sync(FULL, Rr, srcA);
                 const R nB = __shfl_sync(FULL, Lo, srcB);
                 const R nC = __shfl_sync(FULL, X3, srcC);
-                const R a0 = (s1bot * d) + inj;
-                a = (hl == 0) ? a0 : ((hl == 10) ? nC : nA);
+                const R a0 = (s1bot * d) + inj;                            // glottis end (m:792)
+                a = blend(m0, a0, blend(m10, nC, nA));
                 s1bot = Lo;
                 b = nB;
                 c3 = nC;
@@ -629,7 +652,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) tube_kernel(TubeArgs ar
         // =========================================================================================
         // A4  lane = sample t: sum mouth + nose + throat (m:835,849,341); 128-bit coalesced store
         // =========================================================================================
-        S.a.v.YB[hl] = (S.a.v.OUTM[hl] + S.a.v.OUTN[hl]) + (th_mine * (R)D->throatGain);
+        S.a.v.YB[hl] = (S.a.v.OUTM[hl] + S.a.v.OUTN[hl]) + (S.a.v.TH[hl] * (R)D->throatGain);
         __syncwarp(FULL);
         {
             constexpr int VEC = 16 / (int)sizeof(R);          // elements per 128-bit store
