@@ -159,9 +159,22 @@ __device__ __forceinline__ double blend(unsigned m, double x, double y)
 __device__ __forceinline__ float amplitude_f(float dB)
 {
     const float x = dB - 60.0f;
-    if (x <= -60.0f) return 0.0f;
-    if (x >= 0.0f) return 1.0f;
-    return exp2f(x * 0.16609640474436813f);
+    const float v = exp2f(fminf(x, 0.0f) * 0.16609640474436813f);    // x >= 0 -> exactly 1
+    return (x <= -60.0f) ? 0.0f : v;
+}
+
+// fast-mode glottal table: rise 3x^2 - 2x^3 (x = i/div1), fall 1 - (j*j)/L^2, closed 0 -- evaluated, never loaded
+// (TRMWavetable.m:78-96, 117-162).  The sine waveform (rare) still reads the 512-entry table.
+__device__ __forceinline__ float table_value_fast(const double *__restrict__ base, int i, int div1, float inv_div1,
+                                                  double newDiv2, float scale, bool pulse)
+{
+    if (!pulse) return (float)__ldg(base + i);
+    const float x = (float)i * inv_div1;
+    const float rise = (x * x) * (3.0f - 2.0f * x);
+    const float j = (float)(i - div1);
+    const float fall = 1.0f - ((j * j) * scale);
+    const float v = (i < div1) ? rise : fall;
+    return ((double)i >= newDiv2) ? 0.0f : v;
 }
 
 // Glottal table value at integer index i for the current closure point (TRMWavetable.m:78-102 init,
@@ -282,6 +295,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) tube_kernel(TubeArgs ar
     int f_idx = 0, jc = 0;                 // current interval, sample inside it
     // oscillator position (all lanes carry the same value)
     double pos = 0.0;
+    unsigned long long pos_fx = 0ull;      // fast mode: the same position in 2^-55 table entries
     // noise MCG: state after the previous block's last draw; per-lane jump multipliers
     unsigned long long kb = args.noise_k0;
     const unsigned long long MASK44 = (1ull << 44) - 1ull;
@@ -380,7 +394,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) tube_kernel(TubeArgs ar
             // two-port junction between squared radii (ra2, rb2): k = (ra2-rb2)/(ra2+rb2),
             // 1+k = 2 ra2/(ra2+rb2), 1-k = 2 rb2/(ra2+rb2): no cancellation next to k = +-1
             auto two_port = [&](float ra2, float rb2, float tapv) {
-                const float inv = dd / (ra2 + rb2);
+                const float inv = __fdividef(dd, ra2 + rb2);     // one common factor for all three forms
                 return make_float4(2.0f * ra2 * inv, (ra2 - rb2) * inv, 2.0f * rb2 * inv, tapv);
             };
             {
@@ -397,7 +411,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) tube_kernel(TubeArgs ar
             {
                 // 3-way junction: aL = 2 r4^2/s, aL-1 = -v^2/s, aU = 2 v^2/s, aU-1 = (v^2 - 2 r4^2)/s, s = 2 r4^2 + v^2
                 const float vel = (float)prm[15], v2 = vel * vel;
-                const float inv = dd / ((r2[3] + r2[3]) + v2);
+                const float inv = __fdividef(dd, (r2[3] + r2[3]) + v2);
                 const float daL = 2.0f * r2[3] * inv;
                 kf[3] = make_float4(daL, -v2 * inv, daL, (v2 - (r2[3] + r2[3])) * inv);
                 S.Z3[hl] = make_float2(2.0f * v2 * inv, tap[2]);
@@ -406,7 +420,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) tube_kernel(TubeArgs ar
             {
                 // mouth termination: Lo = d a10 k8 a - b11 Lo_prev, radiation input (1+k8) a
                 const float ap2 = (float)D->apScale2;
-                const float inv = 1.0f / (r2[7] + ap2);
+                const float inv = __fdividef(1.0f, r2[7] + ap2);
                 kf[9] = make_float4(0.0f, dd * (float)D->mouth[0] * ((r2[7] - ap2) * inv), -(float)D->mouth[1], 2.0f * r2[7] * inv);
             }
             {
@@ -414,10 +428,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) tube_kernel(TubeArgs ar
                 // beta = (1-tan u)/(2(1+tan u)) = (cos u - sin u)/(2(cos u + sin u))
                 const float sr = (float)D->sampleRate;
                 const float pi = 3.14159265358979323846f;
+                // arguments lie in [0, pi): the SFU sine / cosine have an absolute error of 2^-21.4 there
+                const float inv_sr = 1.0f / sr;
                 float su, cu;
-                sincosf((pi * (float)prm[6]) / sr, &su, &cu);
-                const float cosv = cosf(((2.0f * pi) * (float)prm[5]) / sr);
-                const float beta2 = (cu - su) / (cu + su);                 // 2*beta
+                __sincosf((pi * (float)prm[6]) * inv_sr, &su, &cu);
+                const float cosv = __cosf(((2.0f * pi) * (float)prm[5]) * inv_sr);
+                const float beta2 = __fdividef(cu - su, cu + su);          // 2*beta
                 S.BC[hl][2] = beta2;
                 S.BC[hl][1] = (1.0f + beta2) * cosv;                       // 2*gamma = 2(0.5+beta) cos v
                 bp_alpha2 = 0.5f - 0.5f * beta2;                           // 2*alpha = (0.5-beta)
@@ -484,53 +500,102 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) tube_kernel(TubeArgs ar
         __syncwarp(FULL);                                   // P is dead from here: its storage is reused
 
         // =========================================================================================
-        // S1  oscillator position (TRMWavetable.m:165-168, 28-34), sequential, replicated in all lanes
+        // S1  oscillator position (TRMWavetable.m:165-168, 28-34)
         // =========================================================================================
+        double p0, p1;
+        if constexpr (FAST) {
+            // 64-bit fixed point, 2^55 units per table entry: 512 entries are exactly 2^64, so the table wrap is
+            // the integer overflow, addition is associative and the 32 positions of a block come from a 4-step
+            // warp scan instead of a 32-step dependent chain.  (Resolution 2.8e-17 entries; the reference's own
+            // double accumulator rounds to 5.7e-14.)  mod0 quirk: values in (511, 512) are reported as negative.
+            const unsigned long long inc_fx = __double2ull_rn(S.INC[hl] * 36028797018963968.0);
+            unsigned long long incl = inc_fx + inc_fx;
 #pragma unroll
-        for (int s = 0; s < TB; ++s) {
-            const double di = S.INC[s];
-            pos = pos + di;
-            pos = pos - ((pos > 511.0) ? 512.0 : 0.0);     // mod0: wraps only above 511 (TRMWavetable.m:28-34)
-            const double pa = pos;
-            pos = pos + di;
-            pos = pos - ((pos > 511.0) ? 512.0 : 0.0);
-            if (hl == 0) *reinterpret_cast<double2 *>(&S.a.v.POS[2 * s]) = make_double2(pa, pos);
+            for (int o = 1; o < TB; o <<= 1) {
+                const unsigned long long up = __shfl_up_sync(FULL, incl, o, 16);
+                if (hl >= o) incl += up;
+            }
+            const unsigned long long ub = pos_fx + incl, ua = ub - inc_fx;
+            pos_fx += __shfl_sync(FULL, incl, (lane & 16) | (TB - 1));
+            const unsigned long long top = 511ull << 55;
+            p0 = (ua > top) ? -((double)(0ull - ua) * 2.77555756156289135e-17) : (double)ua * 2.77555756156289135e-17;
+            p1 = (ub > top) ? -((double)(0ull - ub) * 2.77555756156289135e-17) : (double)ub * 2.77555756156289135e-17;
+        } else {
+            // sequential, in the reference's order, replicated in all lanes
+#pragma unroll
+            for (int s = 0; s < TB; ++s) {
+                const double di = S.INC[s];
+                pos = pos + di;
+                pos = pos - ((pos > 511.0) ? 512.0 : 0.0);     // mod0: wraps only above 511 (TRMWavetable.m:28-34)
+                const double pa = pos;
+                pos = pos + di;
+                pos = pos - ((pos > 511.0) ? 512.0 : 0.0);
+                if (hl == 0) *reinterpret_cast<double2 *>(&S.a.v.POS[2 * s]) = make_double2(pa, pos);
+            }
+            __syncwarp(FULL);
+            const double2 pp = *reinterpret_cast<const double2 *>(&S.a.v.POS[2 * hl]);
+            p0 = pp.x; p1 = pp.y;
         }
-        __syncwarp(FULL);
 
         // =========================================================================================
         // A2  lane = sample t: table look-ups, FIR, source mixing (TRMWavetable.m:174-195, m:305-337)
         // =========================================================================================
         {
-            const double2 pp = *reinterpret_cast<const double2 *>(&S.a.v.POS[2 * hl]);
-            const double p0 = active ? pp.x : 0.0, p1 = active ? pp.y : 0.0;
+            if (!active) { p0 = 0.0; p1 = 0.0; }
             const double newDiv2 = (double)div2 - rint(ax_d * D->tnDelta);
             const double Ld = newDiv2 - (double)div1;
-            const R scale = (R)(1.0 / (Ld * Ld));
-            int lo = ((int)p0) & (TRM_TABLE_LENGTH - 1);
-            int hi = lo + 1; if (hi > 511) hi -= 512;
-            R w0 = table_value<R>(wt_base, lo, div1, div2, newDiv2, scale, pulse_wave);
-            R w1 = table_value<R>(wt_base, hi, div1, div2, newDiv2, scale, pulse_wave);
-            S.HE[FIR_HIST + hl] = w0 + ((R)(p0 - (double)lo) * (w1 - w0));
-            lo = ((int)p1) & (TRM_TABLE_LENGTH - 1);
-            hi = lo + 1; if (hi > 511) hi -= 512;
-            w0 = table_value<R>(wt_base, lo, div1, div2, newDiv2, scale, pulse_wave);
-            w1 = table_value<R>(wt_base, hi, div1, div2, newDiv2, scale, pulse_wave);
-            S.HO[FIR_HIST + hl] = w0 + ((R)(p1 - (double)lo) * (w1 - w0));
+            int lo0 = ((int)p0) & (TRM_TABLE_LENGTH - 1), lo1 = ((int)p1) & (TRM_TABLE_LENGTH - 1);
+            int hi0 = lo0 + 1, hi1 = lo1 + 1;
+            if (hi0 > 511) hi0 -= 512;
+            if (hi1 > 511) hi1 -= 512;
+            if constexpr (FAST) {
+                const float Lf = (float)Ld;
+                const float scale = __fdividef(1.0f, Lf * Lf);
+                const float inv_div1 = 1.0f / (float)div1;
+                const float w00 = table_value_fast(wt_base, lo0, div1, inv_div1, newDiv2, scale, pulse_wave);
+                const float w01 = table_value_fast(wt_base, hi0, div1, inv_div1, newDiv2, scale, pulse_wave);
+                const float w10 = table_value_fast(wt_base, lo1, div1, inv_div1, newDiv2, scale, pulse_wave);
+                const float w11 = table_value_fast(wt_base, hi1, div1, inv_div1, newDiv2, scale, pulse_wave);
+                S.HE[FIR_HIST + hl] = w00 + ((float)(p0 - (double)lo0) * (w01 - w00));
+                S.HO[FIR_HIST + hl] = w10 + ((float)(p1 - (double)lo1) * (w11 - w10));
+            } else {
+                const R scale = (R)(1.0 / (Ld * Ld));
+                R w0 = table_value<R>(wt_base, lo0, div1, div2, newDiv2, scale, pulse_wave);
+                R w1 = table_value<R>(wt_base, hi0, div1, div2, newDiv2, scale, pulse_wave);
+                S.HE[FIR_HIST + hl] = w0 + ((R)(p0 - (double)lo0) * (w1 - w0));
+                w0 = table_value<R>(wt_base, lo1, div1, div2, newDiv2, scale, pulse_wave);
+                w1 = table_value<R>(wt_base, hi1, div1, div2, newDiv2, scale, pulse_wave);
+                S.HO[FIR_HIST + hl] = w0 + ((R)(p1 - (double)lo1) * (w1 - w0));
+            }
         }
         __syncwarp(FULL);
         R sig;
         {
             // 49-tap FIR at the odd sample, newest -> oldest from 0.0 (TRMFIRFilter.m:116-131)
-            R acc = (R)0;
             const R *ho = &S.HO[FIR_HIST + hl], *he = &S.HE[FIR_HIST + hl];
+            R pulse0;
+            if constexpr (FAST) {
+                // four independent partial sums instead of one 49-long dependent chain
+                float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
 #pragma unroll
-            for (int q = 0; q < FIR_HIST; ++q) {
-                acc += ho[-q] * FirCoef<R>::at(2 * q);
-                acc += he[-q] * FirCoef<R>::at(2 * q + 1);
+                for (int q = 0; q < FIR_HIST; q += 2) {
+                    s0 += ho[-q] * FirCoef<R>::at(2 * q);
+                    s1 += he[-q] * FirCoef<R>::at(2 * q + 1);
+                    s2 += ho[-q - 1] * FirCoef<R>::at(2 * q + 2);
+                    s3 += he[-q - 1] * FirCoef<R>::at(2 * q + 3);
+                }
+                s0 += ho[-FIR_HIST] * FirCoef<R>::at(2 * FIR_HIST);
+                pulse0 = (s0 + s1) + (s2 + s3);
+            } else {
+                R acc = (R)0;
+#pragma unroll
+                for (int q = 0; q < FIR_HIST; ++q) {
+                    acc += ho[-q] * FirCoef<R>::at(2 * q);
+                    acc += he[-q] * FirCoef<R>::at(2 * q + 1);
+                }
+                acc += ho[-FIR_HIST] * FirCoef<R>::at(2 * FIR_HIST);
+                pulse0 = acc;
             }
-            acc += ho[-FIR_HIST] * FirCoef<R>::at(2 * FIR_HIST);
-            const R pulse0 = acc;
             const R bf = (R)D->breathinessFactor, one_minus_bf = (R)(1.0 - D->breathinessFactor);
             const R pulsed_noise = lp_noise * pulse0;
             const R pulse = ax * ((pulse0 * one_minus_bf) + (pulsed_noise * bf));
