@@ -63,7 +63,7 @@ int fail_msg(const char *what)
         if (_e != cudaSuccess) return fail(#call, _e);                                             \
     } while (0)
 
-constexpr int N_SLOTS = 3;   // chunks in flight (copy-in / compute / copy-out)
+constexpr int MAX_SLOTS = 16;  // upper bound of chunks in flight (each on its own stream and arena)
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -186,9 +186,10 @@ struct trm_cuda_ctx {
     void *d_tab_f64 = nullptr, *d_tab_f32 = nullptr;
     uint64_t noise_k0 = 0;
     trm::KernelInfo info64{}, info32{};
-    cudaStream_t streams[N_SLOTS]{};
-    Arena arenas[N_SLOTS];
-    HostStage stages[N_SLOTS];
+    cudaStream_t streams[MAX_SLOTS]{};
+    Arena arenas[MAX_SLOTS];
+    HostStage stages[MAX_SLOTS];
+    int n_slots = 8;              // chunks in flight: their kernels co-reside, copies overlap other chunks' kernels
 };
 
 struct trm_cuda_resident {
@@ -388,8 +389,8 @@ int chunk_utterances(int n, const trm_cuda_utterance *desc, size_t esz)
     per_utt = per_utt / std::max(probe, 1) + 1;
     const size_t budget = (size_t)16 << 30;                     // per in-flight chunk
     long long by_mem = (long long)(budget / per_utt);
-    long long want = 2048;                                      // ~7 warps per SM per chunk
-    if (n <= 1536) want = n;
+    long long want = 512;                                       // 8 chunks of configs[1] in flight
+    if (n <= 768) want = n;
     long long c = std::max<long long>(1, std::min<long long>(std::min<long long>(want, by_mem), n));
     const long long n_chunks = (n + c - 1) / c;                 // balance the chunks
     return (int)((n + n_chunks - 1) / n_chunks);
@@ -401,8 +402,15 @@ extern "C" {
 
 const char *trm_cuda_last_error(void) { return g_err.c_str(); }
 
+// The pipeline keeps up to MAX_SLOTS streams busy; with the default of 8 hardware work queues, streams alias
+// onto the same queue and one chunk's kernels wait behind another chunk's copies.  Must be set before the
+// CUDA context exists, so it is done on the first entry into the library (no effect if the host application
+// already initialised CUDA: such callers set CUDA_DEVICE_MAX_CONNECTIONS=32 themselves).
+static void want_many_connections() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+
 int trm_cuda_device_count(void)
 {
+    want_many_connections();
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess) { fail("cudaGetDeviceCount", e); return 0; }
@@ -411,6 +419,7 @@ int trm_cuda_device_count(void)
 
 void *trm_cuda_host_alloc(size_t bytes)
 {
+    want_many_connections();
     void *p = nullptr;
     cudaError_t e = cudaMallocHost(&p, bytes ? bytes : 1);
     if (e != cudaSuccess) { fail("cudaMallocHost", e); return nullptr; }
@@ -455,6 +464,7 @@ int trm_cuda_stage_launches(int stage) { return (stage >= 0 && stage < TRM_STAGE
 int trm_cuda_ctx_create(int device, const trm_cuda_tables *t, trm_cuda_ctx **out)
 {
     *out = nullptr;
+    want_many_connections();
     int ndev = 0;
     CK(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail_msg("trm_cuda_ctx_create: no such CUDA device");
@@ -489,7 +499,18 @@ int trm_cuda_ctx_create(int device, const trm_cuda_tables *t, trm_cuda_ctx **out
         CK(cudaMemcpy(c->d_tab_f64, td.data(), td.size() * sizeof(td[0]), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->d_tab_f32, tf.data(), tf.size() * sizeof(tf[0]), cudaMemcpyHostToDevice));
     }
-    for (auto &s : c->streams) CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    {
+        // earlier chunks get the higher stream priority so their resampler / PCM kernels are placed first and
+        // their PCM leaves for the host while later chunks are still in the waveguide kernel
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));          // lo = least (numerically largest)
+        const char *env = getenv("TRM_SLOTS");
+        if (env && atoi(env) > 0) c->n_slots = std::min(MAX_SLOTS, atoi(env));
+        for (int i = 0; i < MAX_SLOTS; ++i) {
+            const int prio = std::min(lo, hi + i);
+            CK(cudaStreamCreateWithPriority(&c->streams[i], cudaStreamNonBlocking, prio));
+        }
+    }
     *out = c;
     return 0;
 }
@@ -535,6 +556,19 @@ int trm_cuda_synthesize_host(trm_cuda_ctx *ctx, int precision, int n, const trm_
     const bool want_pcm = pcm_host != nullptr;
     const int per_chunk = chunk_utterances(n, desc, esz);
     const int n_chunks = (n + per_chunk - 1) / per_chunk;
+    const int N_SLOTS = ctx->n_slots;
+    // TRM_TRACE=1: per-chunk timeline of the pipeline stages (CUDA events on each chunk's stream), printed to stderr
+    const bool trace = getenv("TRM_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    cudaEvent_t t_origin = nullptr;
+    auto mark = [&](cudaStream_t st) {
+        if (!trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        tev.push_back(e);
+    };
+    if (trace) { cudaEventCreate(&t_origin); cudaEventRecord(t_origin, ctx->streams[0]); }
     std::vector<ChunkPlan> plans(std::min(n_chunks, N_SLOTS));
     std::vector<int> slot_chunk(N_SLOTS, -1);
     int64_t n_launch = 0;
@@ -569,11 +603,14 @@ int trm_cuda_synthesize_host(trm_cuda_ctx *ctx, int precision, int n, const trm_
         DeviceChunk dc;
         carve(ctx->arenas[slot], p, esz, want_pcm, dc);
         cudaStream_t s = ctx->streams[slot];
+        mark(s);
         if ((rc = upload_plan(p, dc, ctx->stages[slot].base, s)) != 0) return rc;
         if ((rc = upload_frames(p, dc, desc, frames_host, s)) != 0) return rc;
+        mark(s);
         for (int st = 0; st < TRM_STAGE_COUNT; ++st) {
-            if (st == TRM_STAGE_PCM && !want_pcm) continue;
+            if (st == TRM_STAGE_PCM && !want_pcm) { mark(s); continue; }
             if ((rc = launch_stage(ctx, precision, st, dc, s)) != 0) return rc;
+            mark(s);
             ++n_launch;
         }
         if (want_pcm && p.pcm_elems) {
@@ -595,11 +632,22 @@ int trm_cuda_synthesize_host(trm_cuda_ctx *ctx, int precision, int n, const trm_
             unsigned char *mb = ctx->stages[slot].base + p.stage_bytes() - align_up(p.desc.size() * sizeof(unsigned long long), 256);
             CK(cudaMemcpyAsync(mb, dc.maxbits, p.desc.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         }
+        mark(s);
         slot_chunk[slot] = ci;
     }
     for (int slot = 0; slot < N_SLOTS; ++slot) {
         int rc;
         if (slot_chunk[slot] >= 0 && (rc = finish_slot(slot)) != 0) return rc;
+    }
+    if (trace) {
+        fprintf(stderr, "[trm trace] chunk: start h2d_done tube_done src_done pcm_done d2h_done (ms)\n");
+        for (size_t i = 0; i + 6 <= tev.size(); i += 6) {
+            float t[6];
+            for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&t[k], t_origin, tev[i + k]);
+            fprintf(stderr, "[trm trace] %2zu: %7.2f %7.2f %7.2f %7.2f %7.2f %7.2f\n", i / 6, t[0], t[1], t[2], t[3], t[4], t[5]);
+        }
+        for (auto e : tev) cudaEventDestroy(e);
+        cudaEventDestroy(t_origin);
     }
     if (launches) *launches = n_launch;
     return 0;
