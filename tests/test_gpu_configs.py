@@ -1,0 +1,225 @@
+"""GPU parity on slices of every BASELINE.json config and on the edge cases the path has: ragged lengths, odd batch
+sizes (half-empty warps), single-frame and empty utterances, mixed voices / output rates (up- and down-sampling),
+stereo, the sine waveform, long static vowels (the worst case for an FP32 frequency path), and size-independent
+properties at full size."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+FP64_TOL = 1e-9
+FP32_SNR_DB = 80.0
+
+
+def _g():
+    import gnuspeech_b200 as g
+    return g
+
+
+def _run(ips, frames, n_frames, precision, want_tube=False):
+    g = _g()
+    b = g.TRMBatch(ips, n_frames, precision=precision)
+    lay = b.layout
+    pcm = np.zeros(max(1, lay.total_pcm_samples), np.int16)
+    smp = np.zeros(max(1, lay.total_out_samples), b.sample_dtype)
+    tube = np.zeros(max(1, b.tubeElements), b.sample_dtype) if want_tube else None
+    if want_tube:
+        b.synthesize_debug(frames, pcm, smp, tube)
+    else:
+        b.synthesize(frames, pcm_out=pcm, samples_out=smp, devices=[0])
+    return b, pcm, smp, tube
+
+
+def _check(b, pcm, smp, ips, frames, n_frames, precision, idx=None):
+    g = _g()
+    ns, po, oo, mx = b.numberSamples, b.pcmOffsets, b.outOffsets, b.maximumSampleValues
+    off = np.concatenate(([0], np.cumsum(n_frames)))
+    worst = 0.0 if precision == g.TRM_PRECISION_FP64 else 1e9
+    for u in (range(len(n_frames)) if idx is None else idx):
+        ip = ips[u] if isinstance(ips, (list, tuple)) else ips
+        ref = O.synthesize(ip, frames[off[u]:off[u + 1]], want_tube=False)
+        assert ns[u] == ref.numberSamples, "utt %d" % u
+        if ref.numberSamples == 0:
+            continue
+        ch = 2 if ip.channels == 2 else 1
+        y = smp[oo[u]:oo[u] + ns[u]].astype(np.float64)
+        p = pcm[po[u]:po[u] + ns[u] * ch].astype(np.int32)
+        peak = ref.maximumSampleValue
+        if peak == 0.0:
+            assert not y.any() and not p.any()
+            continue
+        pcm_ref = O.pcm16(ip, ref.samples, peak).astype(np.int32)
+        if precision == g.TRM_PRECISION_FP64:
+            e = np.abs(y - ref.samples).max() / peak
+            assert e <= FP64_TOL, "utt %d: FP64 error %.3e" % (u, e)
+            assert abs(mx[u] - peak) <= FP64_TOL * peak
+            worst = max(worst, e)
+        else:
+            snr = O.snr_db(ref.samples, y)
+            assert snr >= FP32_SNR_DB, "utt %d: SNR %.1f dB" % (u, snr)
+            worst = min(worst, snr)
+        d = np.abs(p - pcm_ref)
+        assert d.max() <= 1, "utt %d: %d PCM samples off by more than 1 LSB (max %d)" % (u, int((d > 1).sum()), int(d.max()))
+    return worst
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_config3_static_grid_slice(precision):
+    """Config 3: TRAcT-style static sweep (0.5 s each): 96 grid points spread over the 65,536."""
+    g = _g()
+    from gnuspeech_b200 import workloads as W
+    idx = [int(i) for i in np.linspace(0, 65535, 96)]
+    nf = 126
+    frames = W.grid(idx, nf)
+    ip = g.TRMInputParameters(44100.0)
+    b, pcm, smp, _ = _run(ip, frames, [nf] * len(idx), precision)
+    assert (b.numberSamples == 22109).all()
+    print("config3 worst", _check(b, pcm, smp, ip, frames, [nf] * len(idx), precision))
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_config4_mixed_lengths_and_rates(precision):
+    """Config 4 slice: ragged lengths, alternating 44.1 / 22.05 kHz, odd utterance count, plus the degenerate
+    single-frame (flush only) and two-frame utterances."""
+    g = _g()
+    from gnuspeech_b200 import workloads as W
+    n_frames = [751, 1, 313, 2, 1251, 126, 433, 877, 51]
+    frames = W.random_walk_ragged(n_frames, seed=21)
+    ips = [g.TRMInputParameters(44100.0 if u % 2 == 0 else 22050.0) for u in range(len(n_frames))]
+    b, pcm, smp, _ = _run(ips, frames, n_frames, precision)
+    print("config4 worst", _check(b, pcm, smp, ips, frames, n_frames, precision))
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_mixed_voices_down_sampling_stereo_sine(precision):
+    """Different tube lengths in one batch (different tube rates, control periods, converter directions and pads),
+    stereo output with balance / volume, sine glottal source, modulation off, other pulse shapes."""
+    g = _g()
+    from gnuspeech_b200 import workloads as W
+    ips = [
+        g.TRMInputParameters(44100.0, length=15.0),
+        g.TRMInputParameters(22050.0, length=15.0),                       # down-sampling, pad 14
+        g.TRMInputParameters(22050.0, length=10.0, temperature=32.0),
+        g.TRMInputParameters(44100.0, length=7.5),                        # down-sampling at 44.1 kHz
+        g.TRMInputParameters(22050.0, channels=2, balance=-0.4, volume=57.0),
+        g.TRMInputParameters(44100.0, waveform=1),
+        g.TRMInputParameters(44100.0, usesModulation=0, breathiness=4.0, lossFactor=1.5),
+        g.TRMInputParameters(44100.0, tp=30.0, tnMin=12.0, tnMax=40.0, mixOffset=48.0, throatVol=12.0),
+    ]
+    n_frames = [101] * len(ips)
+    frames = W.random_walk(len(ips), 101, seed=33)
+    b, pcm, smp, _ = _run(ips, frames, n_frames, precision)
+    print("mixed voices worst", _check(b, pcm, smp, ips, frames, n_frames, precision))
+
+
+def test_long_static_vowel_fp32_phase_accuracy():
+    """30 s static /aa/: an FP32 frequency path drifts here (19 dB at 10 s); the fast mode
+    keeps pitch -> f0 -> phase in FP64 / 64-bit fixed point."""
+    g = _g()
+    from gnuspeech_b200 import workloads as W
+    nf = 7501
+    frames = W.static_vowel(nf, 1)
+    ip = g.TRMInputParameters(44100.0)
+    b, pcm, smp, _ = _run(ip, frames, [nf], g.TRM_PRECISION_FP32)
+    print("30 s static vowel SNR", _check(b, pcm, smp, ip, frames, [nf], g.TRM_PRECISION_FP32))
+
+
+def test_long_random_walk_both_modes():
+    """One 60 s random-walk utterance (config 4's longest): 1.185e6 tube samples, 2.646e6 output samples."""
+    g = _g()
+    from gnuspeech_b200 import workloads as W
+    nf = 15001
+    frames = W.random_walk(1, nf, seed=44)
+    ip = g.TRMInputParameters(44100.0)
+    for prec in (g.TRM_PRECISION_FP64, g.TRM_PRECISION_FP32):
+        b, pcm, smp, _ = _run(ip, frames, [nf], prec)
+        assert b.numberSamples[0] == 2646061
+        print("60 s walk, precision %d:" % prec, _check(b, pcm, smp, ip, frames, [nf], prec))
+
+
+def test_noise_and_frame_indexing_are_exact():
+    """North-star: the noise sequence and frame indexing must be bit-exact.  With everything but aspiration noise
+    silenced (glottal volume 0, frication 0) the tube input is ah1 * lp_noise * 0.125: any slip in the jump-ahead
+    MCG or in which frame a sample belongs to shows at full scale; FP64 must stay at rounding level."""
+    g = _g()
+    from gnuspeech_b200 import workloads as W
+    nf = 201
+    frames = W.static_vowel(nf, 0)
+    frames[:, 1] = 0.0                      # no voicing
+    frames[:, 2] = np.linspace(0.0, 40.0, nf)   # aspiration ramps up: frame indexing matters
+    ip = g.TRMInputParameters(44100.0, usesModulation=0)
+    b, pcm, smp, tube = _run(ip, frames, [nf], g.TRM_PRECISION_FP64, want_tube=True)
+    ref = O.synthesize(ip, frames)
+    t = tube[:ref.tube.size]
+    assert np.abs(t - ref.tube).max() <= 1e-13 * np.abs(ref.tube).max()
+    # first samples: x[0] uses frame 0 exactly, the increment is applied AFTER each sample
+    assert t[0] == ref.tube[0] and t[1] == ref.tube[1] and t[79] == ref.tube[79]
+
+
+def test_config5_slice_properties_at_scale():
+    """Config 5 / config 2 at scale (2048 x 2 s, FP32 fast): results do not depend on batch composition --
+    every utterance of the big batch equals the same utterance synthesized alone -- and a sample of them matches
+    the oracle."""
+    g = _g()
+    from gnuspeech_b200 import workloads as W
+    n, nf = 2048, 501
+    frames = W.random_walk(n, nf, seed=5)
+    ip = g.TRMInputParameters(44100.0)
+    b, pcm, smp, _ = _run(ip, frames, [nf] * n, g.TRM_PRECISION_FP32)
+    ns, po = b.numberSamples, b.pcmOffsets
+    assert (ns == 88259).all()
+    pick = [0, 1, 511, 512, 1000, 2047]
+    _check(b, pcm, smp, ip, frames, [nf] * n, g.TRM_PRECISION_FP32, idx=pick)
+    for u in pick:
+        b1, pcm1, smp1, _ = _run(ip, frames[u * nf:(u + 1) * nf], [nf], g.TRM_PRECISION_FP32)
+        assert np.array_equal(pcm1[:ns[u]], pcm[po[u]:po[u] + ns[u]]), "utterance %d depends on its batch" % u
+    # every utterance is normalised to its own peak: the loudest PCM code of each is +-32767 (volume 60 dB)
+    peaks = np.array([np.abs(pcm[po[u]:po[u] + ns[u]].astype(np.int32)).max() for u in range(0, n, 37)])
+    assert (peaks == 32767).all()
+
+
+def test_multi_device_call_matches_single_device():
+    """TRMBatchSynthesize over every visible GPU (one host thread and context per device, contiguous shards, no
+    collectives) gives the same bytes as one device."""
+    import torch
+    g = _g()
+    from gnuspeech_b200 import workloads as W
+    n, nf = 37, 126
+    frames = W.random_walk(n, nf, seed=8)
+    ip = g.TRMInputParameters(44100.0)
+    b, pcm, smp, _ = _run(ip, frames, [nf] * n, g.TRM_PRECISION_FP64)
+    nd = torch.cuda.device_count()
+    b2 = g.TRMBatch(ip, [nf] * n, precision=g.TRM_PRECISION_FP64)
+    pcm2 = np.zeros_like(pcm)
+    b2.synthesize(frames, pcm_out=pcm2, devices=list(range(nd)))
+    assert np.array_equal(pcm, pcm2)
+    assert np.array_equal(b.maximumSampleValues, b2.maximumSampleValues)
+
+
+def test_synthesizer_adapter_and_file_outputs(tmp_path):
+    """The TRMSynthesizer call pattern Monet uses (TRMSynthesizer.m:38-136) and the three container writers."""
+    g = _g()
+    from gnuspeech_b200 import workloads as W
+    syn = g.TRMSynthesizer()
+    syn.setupSynthesisParameters(g.TRMInputParameters(22050.0))
+    for f in W.static_vowel(26, 0):
+        syn.addParameters(g.TRMParameters(*f[:7], radius=f[7:15], velum=f[15]))
+    tube = syn.synthesize()
+    ref = O.synthesize(g.TRMInputParameters(22050.0), W.static_vowel(26, 0))
+    assert tube.numberSamples == ref.numberSamples
+    assert syn.lastWAVData == O.wav_bytes(g.TRMInputParameters(22050.0), tube.resampledData, tube.maximumSampleValue)
+    pcm = tube.pcm16()
+    for fmt, magic in ((0, b".snd"), (1, b"FORM"), (2, b"RIFF")):
+        syn2 = g.TRMSynthesizer()
+        syn2.setupSynthesisParameters(g.TRMInputParameters(22050.0))
+        syn2.fileType = fmt
+        syn2.shouldSaveToSoundFile = True
+        syn2.filename = str(tmp_path / ("out%d" % fmt))
+        syn2.addParameters(W.static_vowel(26, 0))
+        syn2.synthesize()
+        raw = open(syn2.filename, "rb").read()
+        assert raw[:4] == magic
+        body = np.frombuffer(raw[-2 * pcm.size:], dtype="<i2" if fmt == 2 else ">i2")
+        assert np.array_equal(body.astype(np.int16), pcm)
