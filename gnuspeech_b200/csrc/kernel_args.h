@@ -14,7 +14,8 @@ constexpr int FRAME_CHUNK = 2;   // control frames per bulk copy (256 B)
 constexpr int WARPS_PER_CTA = 2;
 constexpr int UTT_PER_CTA = WARPS_PER_CTA * 2;
 
-constexpr int SRC_THREADS = 256;
+constexpr int SRC_THREADS = 512;
+constexpr int SRC_ILP = 4;          // outputs whose tap chains are interleaved in one lane
 constexpr int SRC_ROWS = 256;        // staged input rows per work item
 constexpr int SRC_LD = 33;           // padded leading dimension of the transposed tiles (32 utterances + 1)
 constexpr int SRC_CHUNK = 16;        // consecutive outputs a warp finishes before the transposed write-back

@@ -103,30 +103,67 @@ __global__ void __launch_bounds__(SRC_THREADS) src_kernel(SrcArgs args)
         R local_max = (R)0;
         R *yw = yT + warp * (SRC_CHUNK * SRC_LD);
         for (long long n0 = n_s + (long long)warp * SRC_CHUNK; n0 < n_e; n0 += (SRC_THREADS / 32) * SRC_CHUNK) {
-#pragma unroll 2
-            for (int j = 0; j < SRC_CHUNK; ++j) {
-                const unsigned long long T = (unsigned long long)(n0 + j) * tri;
-                const int base = (int)((long long)(T >> 16) - win_lo);
-                const unsigned F = (unsigned)(T & 0xFFFFull);
-                const R *xp = xT + base * SRC_LD + lane;
-                R acc = (R)0;
-                if (up) {
-                    R interp = (R)(F & 255u) / (R)256;
-                    unsigned fi = F >> 8;
+            if (up) {
+                // SRC_ILP outputs at a time: their 26-tap accumulation chains are independent, which is what hides
+                // the FP latency with only 8-16 warps per SM (the taps themselves stay in the reference's order)
+#pragma unroll 1
+                for (int j = 0; j < SRC_CHUNK; j += SRC_ILP) {
+                    const R *xp[SRC_ILP];
+                    unsigned F[SRC_ILP];
+                    R acc[SRC_ILP];
 #pragma unroll
-                    for (int k = 0; k < SRC_ZC; ++k) {
-                        const HD<R> c = tab[fi + 256u * k];
-                        acc += xp[-k * SRC_LD] * (c.h + c.dh * interp);
+                    for (int o = 0; o < SRC_ILP; ++o) {
+                        const unsigned long long T = (unsigned long long)(n0 + j + o) * tri;
+                        xp[o] = xT + (int)((long long)(T >> 16) - win_lo) * SRC_LD + lane;
+                        F[o] = (unsigned)(T & 0xFFFFull);
+                        acc[o] = (R)0;
                     }
-                    const unsigned G = (~F) & 0xFFFFu;
-                    interp = (R)(G & 255u) / (R)256;
-                    fi = G >> 8;
+                    {
+                        R interp[SRC_ILP];
+                        unsigned fi[SRC_ILP];
 #pragma unroll
-                    for (int k = 0; k < SRC_ZC; ++k) {
-                        const HD<R> c = tab[fi + 256u * k];
-                        acc += xp[(1 + k) * SRC_LD] * (c.h + c.dh * interp);
+                        for (int o = 0; o < SRC_ILP; ++o) { interp[o] = (R)(F[o] & 255u) / (R)256; fi[o] = F[o] >> 8; }
+#pragma unroll
+                        for (int k = 0; k < SRC_ZC; ++k) {
+#pragma unroll
+                            for (int o = 0; o < SRC_ILP; ++o) {
+                                const HD<R> c = tab[fi[o] + 256u * k];
+                                acc[o] += xp[o][-k * SRC_LD] * (c.h + c.dh * interp[o]);
+                            }
+                        }
                     }
-                } else {
+                    {
+                        R interp[SRC_ILP];
+                        unsigned fi[SRC_ILP];
+#pragma unroll
+                        for (int o = 0; o < SRC_ILP; ++o) {
+                            const unsigned G = (~F[o]) & 0xFFFFu;
+                            interp[o] = (R)(G & 255u) / (R)256;
+                            fi[o] = G >> 8;
+                        }
+#pragma unroll
+                        for (int k = 0; k < SRC_ZC; ++k) {
+#pragma unroll
+                            for (int o = 0; o < SRC_ILP; ++o) {
+                                const HD<R> c = tab[fi[o] + 256u * k];
+                                acc[o] += xp[o][(1 + k) * SRC_LD] * (c.h + c.dh * interp[o]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int o = 0; o < SRC_ILP; ++o) {
+                        yw[(j + o) * SRC_LD + lane] = acc[o];
+                        const R av = r_abs<R>(acc[o]);
+                        if (n0 + j + o < my_n_out && av > local_max) local_max = av;   // NaN never wins, like the reference
+                    }
+                }
+            } else {
+                for (int j = 0; j < SRC_CHUNK; ++j) {
+                    const unsigned long long T = (unsigned long long)(n0 + j) * tri;
+                    const int base = (int)((long long)(T >> 16) - win_lo);
+                    const unsigned F = (unsigned)(T & 0xFFFFull);
+                    const R *xp = xT + base * SRC_LD + lane;
+                    R acc = (R)0;
                     unsigned ph = (unsigned)rint((double)F * ratio), ii;
                     const R *xq = xp;
                     while ((ii = (ph >> 8)) < (unsigned)TRM_SRC_FILTER_LEN) {
@@ -145,10 +182,10 @@ __global__ void __launch_bounds__(SRC_THREADS) src_kernel(SrcArgs args)
                         xq += SRC_LD;
                         ph += phaseIncrement;
                     }
+                    yw[j * SRC_LD + lane] = acc;
+                    const R av = r_abs<R>(acc);
+                    if (n0 + j < my_n_out && av > local_max) local_max = av;
                 }
-                yw[j * SRC_LD + lane] = acc;
-                const R av = r_abs<R>(acc);
-                if (n0 + j < my_n_out && av > local_max) local_max = av;     // NaN never wins, like the reference
             }
             __syncwarp();
             // transposed write-back: each half-warp stores SRC_CHUNK consecutive samples of one utterance

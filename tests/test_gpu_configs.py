@@ -194,7 +194,9 @@ def test_multi_device_call_matches_single_device():
     b2 = g.TRMBatch(ip, [nf] * n, precision=g.TRM_PRECISION_FP64)
     pcm2 = np.zeros_like(pcm)
     b2.synthesize(frames, pcm_out=pcm2, devices=list(range(nd)))
-    assert np.array_equal(pcm, pcm2)
+    ns, po = b.numberSamples, b.pcmOffsets
+    for u in range(n):                                   # (the alignment padding between utterances is undefined)
+        assert np.array_equal(pcm[po[u]:po[u] + ns[u]], pcm2[po[u]:po[u] + ns[u]]), u
     assert np.array_equal(b.maximumSampleValues, b2.maximumSampleValues)
 
 
