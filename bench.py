@@ -39,6 +39,10 @@ METRIC = "synthesized audio-sec per wall-sec"
 UNIT = "audio-s/s"
 FLOP_PER_TUBE_SAMPLE = 390.0     # algorithmic flops per tube-rate sample
 FLOP_PER_OUT_SAMPLE = 110.0      # up-sampling converter, per output sample
+# DRAM traffic per unit measured with `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum of the
+# 4096 x 1 s launch, profiles/prof_r1_final_{f64,f32}_summary.txt) -- linear in the number of samples:
+#   waveguide: bytes per tube-rate sample, resampler / PCM: bytes per output sample
+TRAFFIC_PER_UNIT = {"fp64": {"tube": 8.99, "src": 11.28, "pcm": 9.96}, "fp32": {"tube": 5.09, "src": 5.53, "pcm": 5.86}}
 
 
 def host_cores():
@@ -133,8 +137,8 @@ def run_reference_arm(args):
     ip = g.TRMInputParameters(44100.0)
     n_frames = int(args.seconds * 250) + 1
     cores = host_cores()
-    # bounded sample per step: ~2 utterances per core of the same 10 s random-walk workload
-    n_utt = max(cores * 2, 8) if args.sample_utterances <= 0 else args.sample_utterances
+    # bounded sample per step: 16 utterances per core of the same 10 s random-walk workload (~1 s wall, ~15-20 s CPU)
+    n_utt = max(cores * 16, 32) if args.sample_utterances <= 0 else args.sample_utterances
     for _ in range(args.warmup):
         oracle_throughput(ip, n_frames, min(n_utt, cores), cores, args.seed, 0)
     t_total, audio_total = 0.0, 0.0
@@ -169,7 +173,7 @@ def main():
     ap.add_argument("--utterances", type=int, default=4096, help="utterances per GPU")
     ap.add_argument("--seconds", type=float, default=10.0, help="seconds of audio per utterance")
     ap.add_argument("--seed", type=int, default=1)
-    ap.add_argument("--sample-utterances", type=int, default=0, help="CPU arm: utterances per step (0 = 2 per core)")
+    ap.add_argument("--sample-utterances", type=int, default=0, help="CPU arm: utterances per step (0 = 16 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--also-fp32", action="store_true", help="add a fast_mode object measured the same way in FP32")
@@ -312,18 +316,22 @@ def main():
         "peak_source": "FMA chain measured live on this device (trm_cuda_fp_peak); MEASURED_PEAKS.json has no CUDA-core peak",
         "flop_per_tube_sample": FLOP_PER_TUBE_SAMPLE, "ms_per_launch": tube_ms,
         "share_of_step": tube_ms / (tube_ms + src_ms + pcm_ms),
-        "hbm_achieved_gbs": tube_bytes / (tube_ms * 1e-3) / 1e9, "traffic": None,
+        "hbm_achieved_gbs": tube_bytes / (tube_ms * 1e-3) / 1e9,
+        "algorithmic_bytes": tube_bytes, "traffic": TRAFFIC_PER_UNIT[args.precision]["tube"] * float(lay.tube_samples),
+        "traffic_source": "ncu --set full dram bytes of the 4096 x 1 s launch, scaled by samples (profiles/)",
     }
     roofline_src = {
         "kernel": "src_kernel", "bound": "hbm", "achieved": src_bytes / (src_ms * 1e-3) / 1e9, "peak": hbm_peak,
         "unit": "GB/s", "frac": src_bytes / (src_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
-        "ms_per_launch": src_ms, "share_of_step": src_ms / (tube_ms + src_ms + pcm_ms), "traffic": None,
+        "ms_per_launch": src_ms, "share_of_step": src_ms / (tube_ms + src_ms + pcm_ms),
+        "algorithmic_bytes": src_bytes, "traffic": TRAFFIC_PER_UNIT[args.precision]["src"] * float(lay.out_samples),
         "flops_tf": FLOP_PER_OUT_SAMPLE * float(lay.out_samples) / (src_ms * 1e-3) / 1e12,
     }
     roofline_pcm = {
         "kernel": "pcm_kernel", "bound": "hbm", "achieved": pcm_bytes / (pcm_ms * 1e-3) / 1e9, "peak": hbm_peak,
         "unit": "GB/s", "frac": pcm_bytes / (pcm_ms * 1e-3) / 1e9 / hbm_peak, "ms_per_launch": pcm_ms,
-        "share_of_step": pcm_ms / (tube_ms + src_ms + pcm_ms), "traffic": None,
+        "share_of_step": pcm_ms / (tube_ms + src_ms + pcm_ms),
+        "algorithmic_bytes": pcm_bytes, "traffic": TRAFFIC_PER_UNIT[args.precision]["pcm"] * float(lay.out_samples),
     }
 
     fast = None
@@ -337,7 +345,7 @@ def main():
     if not args.no_cpu_baseline and rank == 0 and world == 1:
         from gnuspeech_b200 import build as B
         B.build_oracle()
-        n_s = max(2 * cores, 8)
+        n_s = min(n_utt, max(16 * cores, 32))           # ~15-20 s of CPU work
         v, dt = oracle_throughput(ip, n_frames, n_s, cores, args.seed, 0)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "seconds": dt,
                "sample": "%d of the %d utterances x %g s, one utterance per thread, reference-faithful per-sample "
