@@ -68,6 +68,7 @@ struct KernelInfo {
     int src_ctas_per_sm;
     int tube_ctas_per_sm;
     int tube_regs, src_regs, pcm_regs;
+    int wide_smem_bytes, wide_threads, wide_max_utt, wide_regs;   // batch-throughput waveguide mapping (tube_wide.cuh)
 };
 
 }  // namespace trm

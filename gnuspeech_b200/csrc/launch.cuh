@@ -3,8 +3,11 @@
 // contraction) and exports them with C linkage for trm_cuda.cu.
 #pragma once
 
+#include <stdlib.h>
+
 #include "src_kernel.cuh"
 #include "tube_kernel.cuh"
+#include "tube_wide.cuh"
 
 namespace trm {
 
@@ -26,7 +29,15 @@ template <typename R> static int configure_kernels(KernelInfo *info)
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(src_kernel<R>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
+    const int wide_smem = (int)sizeof(WideSmem<R>);
+    e = cudaFuncSetAttribute(tube_wide_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, wide_smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(tube_wide_kernel<R>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return (int)e;
     if (info) {
+        info->wide_smem_bytes = wide_smem;
+        info->wide_threads = Wide<R>::THREADS;
+        info->wide_max_utt = 2 * Wide<R>::MAX_PAIRS;
         info->tube_smem_bytes = tube_smem;
         info->tube_threads = WARPS_PER_CTA * 32;
         info->tube_utt_per_cta = UTT_PER_CTA;
@@ -38,6 +49,7 @@ template <typename R> static int configure_kernels(KernelInfo *info)
         if (e != cudaSuccess) return (int)e;
         cudaFuncAttributes fa;
         if (cudaFuncGetAttributes(&fa, tube_kernel<R>) == cudaSuccess) info->tube_regs = fa.numRegs;
+        if (cudaFuncGetAttributes(&fa, tube_wide_kernel<R>) == cudaSuccess) info->wide_regs = fa.numRegs;
         if (cudaFuncGetAttributes(&fa, src_kernel<R>) == cudaSuccess) info->src_regs = fa.numRegs;
         if (cudaFuncGetAttributes(&fa, pcm_kernel<R>) == cudaSuccess) info->pcm_regs = fa.numRegs;
     }
@@ -62,6 +74,17 @@ template <typename R> static int launch_tube(const TubeArgs &a, cudaStream_t s)
     if (a.n_utt <= 0) return 0;
     const int grid = (a.n_utt + UTT_PER_CTA - 1) / UTT_PER_CTA;
     tube_kernel<R><<<grid, WARPS_PER_CTA * 32, UTT_PER_CTA * sizeof(UttSmem<R>), s>>>(a);
+    return (int)cudaGetLastError();
+}
+
+// batch-throughput mapping: one CTA per group of <= 2*MAX_PAIRS utterances (tube_wide.cuh)
+template <typename R> static int launch_tube_wide(const TubeArgs &a, int n_groups, cudaStream_t s)
+{
+    if (a.n_utt <= 0 || n_groups <= 0) return 0;
+    if ((a.n_utt + n_groups - 1) / n_groups > 2 * Wide<R>::MAX_PAIRS) return (int)cudaErrorInvalidConfiguration;
+    const char *dbg = getenv("TRM_WIDE_DEBUG");
+    WideArgs w{a, n_groups, dbg ? atoi(dbg) : 0};
+    tube_wide_kernel<R><<<n_groups, Wide<R>::THREADS, sizeof(WideSmem<R>), s>>>(w);
     return (int)cudaGetLastError();
 }
 
@@ -92,6 +115,10 @@ template <typename R> static int launch_pcm(const PcmArgs &a, long long max_n_ou
         return trm::upload_constants(fir, taps, np);                                                              \
     }                                                                                                             \
     extern "C" int trm_k_tube_##SUF(const trm::TubeArgs *a, cudaStream_t s) { return trm::launch_tube<R>(*a, s); } \
+    extern "C" int trm_k_tube_wide_##SUF(const trm::TubeArgs *a, int n_groups, cudaStream_t s)                    \
+    {                                                                                                             \
+        return trm::launch_tube_wide<R>(*a, n_groups, s);                                                         \
+    }                                                                                                             \
     extern "C" int trm_k_src_##SUF(const trm::SrcArgs *a, int grid, cudaStream_t s)                               \
     {                                                                                                             \
         return trm::launch_src<R>(*a, grid, s);                                                                   \

@@ -21,6 +21,8 @@ int trm_k_upload_f64(const double *, int, const unsigned long long *);
 int trm_k_upload_f32(const double *, int, const unsigned long long *);
 int trm_k_tube_f64(const trm::TubeArgs *, cudaStream_t);
 int trm_k_tube_f32(const trm::TubeArgs *, cudaStream_t);
+int trm_k_tube_wide_f64(const trm::TubeArgs *, int, cudaStream_t);
+int trm_k_tube_wide_f32(const trm::TubeArgs *, int, cudaStream_t);
 int trm_k_src_f64(const trm::SrcArgs *, int, cudaStream_t);
 int trm_k_src_f32(const trm::SrcArgs *, int, cudaStream_t);
 int trm_k_pcm_f64(const trm::PcmArgs *, long long, cudaStream_t);
@@ -190,6 +192,7 @@ struct trm_cuda_ctx {
     Arena arenas[MAX_SLOTS];
     HostStage stages[MAX_SLOTS];
     int n_slots = 8;              // chunks in flight: their kernels co-reside, copies overlap other chunks' kernels
+    int wide_min_utt = 0;         // batches at least this large use the batch-throughput waveguide mapping
 };
 
 struct trm_cuda_resident {
@@ -347,6 +350,21 @@ int upload_frames(const ChunkPlan &p, const DeviceChunk &dc, const trm_cuda_utte
     return 0;
 }
 
+// Which waveguide mapping runs a chunk of n utterances: 0 = lane-per-section (tube_kernel.cuh), otherwise the
+// number of CTAs of the batch-throughput mapping (tube_wide.cuh), one per SM and wave.  Small batches finish sooner
+// with their sections spread over lanes; TRM_TUBE_MAPPING=sections|utterances overrides the choice.
+int wide_groups(const trm_cuda_ctx *ctx, const trm::KernelInfo &ki, int n)
+{
+    const char *env = getenv("TRM_TUBE_MAPPING");
+    const bool force_sections = env && env[0] == 's', force_wide = env && env[0] == 'u';
+    if (n <= 0 || force_sections) return 0;
+    if (!force_wide && n < ctx->wide_min_utt) return 0;
+    const int sm = ctx->sm_count, gmax = ki.wide_max_utt;
+    if ((long long)n <= (long long)sm * gmax) return std::max(1, std::min(sm, (n + 1) / 2));
+    const int waves = (int)(((long long)n + (long long)sm * gmax - 1) / ((long long)sm * gmax));
+    return waves * sm;
+}
+
 int launch_stage(trm_cuda_ctx *ctx, int precision, int stage, const DeviceChunk &dc, cudaStream_t s)
 {
     const bool f64 = precision == 0;
@@ -355,7 +373,10 @@ int launch_stage(trm_cuda_ctx *ctx, int precision, int stage, const DeviceChunk 
         trm::TubeArgs a{};
         a.desc = dc.desc; a.order = dc.order; a.n_utt = dc.n; a.frames = dc.frames; a.tube = dc.tube;
         a.wavetables = ctx->d_wavetables; a.noise_k0 = ctx->noise_k0;
-        rc = f64 ? trm_k_tube_f64(&a, s) : trm_k_tube_f32(&a, s);
+        const trm::KernelInfo &ki = f64 ? ctx->info64 : ctx->info32;
+        const int groups = wide_groups(ctx, ki, dc.n);
+        if (groups > 0) rc = f64 ? trm_k_tube_wide_f64(&a, groups, s) : trm_k_tube_wide_f32(&a, groups, s);
+        else rc = f64 ? trm_k_tube_f64(&a, s) : trm_k_tube_f32(&a, s);
     } else if (stage == TRM_STAGE_SRC) {
         CK(cudaMemsetAsync(dc.maxbits, 0, (size_t)dc.n * sizeof(unsigned long long), s));
         trm::SrcArgs a{};
@@ -476,6 +497,7 @@ int trm_cuda_ctx_create(int device, const trm_cuda_tables *t, trm_cuda_ctx **out
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     c->noise_k0 = t->noise_k0;
+    c->wide_min_utt = 4 * prop.multiProcessorCount;
     int rc;
     if ((rc = trm_k_upload_f64(t->fir_coef, t->fir_taps, (const unsigned long long *)t->noise_pow)) != 0 ||
         (rc = trm_k_upload_f32(t->fir_coef, t->fir_taps, (const unsigned long long *)t->noise_pow)) != 0) {

@@ -1,0 +1,772 @@
+// tube_wide.cuh -- the TRM waveguide kernel for sm_100a, batch-throughput mapping.
+//
+// Same path as tube_kernel.cuh (TRMTubeModel.m:292-354 and everything it calls) with the work split by
+// KIND instead of by utterance:
+//
+//   feed-forward warps (one per utterance pair, lane = sample t of a 16-sample block, exactly the
+//       time-parallel phases S0/A1/S1/A2 of tube_kernel.cuh): parameter interpolation, conversions, junction /
+//       tap / band-pass coefficients, jump-ahead noise, oscillator position, glottal table look-ups, 49-tap FIR,
+//       source mixing.  Nothing here depends on the tube state.  Results go to a shared-memory ring of
+//       per-sample coefficient records.
+//   ONE recurrence warp per CTA (lane = utterance): the strictly sequential part only -- Kelly-Lochbaum ladder,
+//       velum 3-way junction, nasal branch, mouth / nose reflection + radiation filters, frication band-pass
+//       and throat low-pass recursions (TRMTubeModel.m:778-853, TRMFilters.m:19-29,47-77).  All 32 waves and
+//       9 filter memories of an utterance live in that lane's registers; the 16 junctions of one sample are
+//       independent of each other (they read the previous time slice only), so the lane has 16-wide ILP and
+//       there is NO cross-lane traffic: no shuffles, no role blends.  ~6 warp instructions per utterance-sample
+//       in FP64 and ~3.5 in FP32, against ~35 / ~18 for the lane-per-section ladder.
+//
+// One CTA per SM, up to 28 (FP64) / 30 (FP32) utterances per CTA; the ring is double-buffered so the
+// feed-forward warps work on block b+1 while the recurrence warp consumes block b (mbarrier full / empty
+// pairs).  Control frames are staged by TMA bulk copies as in tube_kernel.cuh.  Tube-rate output is transposed
+// through shared memory and stored with 128-bit coalesced stores.
+//
+// The lane-per-section kernel (tube_kernel.cuh) stays the mapping for small batches: a lone utterance
+// finishes soonest when its 16 sections are spread over lanes.  launch_stage() picks by batch size
+// (TRM_TUBE_MAPPING=sections|utterances overrides).  Both are checked against the same oracle.
+#pragma once
+
+#include "tube_kernel.cuh"
+
+namespace trm {
+
+template <typename R> struct Wide;
+template <> struct Wide<float> {
+    using Unit = float4;
+    static constexpr int MAX_PAIRS = 15;
+    static constexpr int NF = 11;                    // 16-byte units per utterance-sample
+    static constexpr int UP = 2 * MAX_PAIRS + 1;     // padded utterance dimension: odd -> conflict-free writers
+    static constexpr int THREADS = 32 * (1 + MAX_PAIRS);
+    static constexpr int OUT_LD = 20;                // 16-byte aligned rows of the output transpose tile
+};
+template <> struct Wide<double> {
+    using Unit = double2;
+    static constexpr int MAX_PAIRS = 14;
+    static constexpr int NF = 12;
+    static constexpr int UP = 2 * MAX_PAIRS + 1;
+    static constexpr int THREADS = 32 * (1 + MAX_PAIRS);
+    static constexpr int OUT_LD = 18;
+};
+constexpr int WIDE_SLOTS = 2;
+
+// feed-forward state of one utterance that must be in shared memory
+template <typename R>
+struct alignas(16) FFHalf {
+    double FR[2][FRAME_CHUNK][16];           // TMA destination, double-buffered
+    unsigned long long mbar[2];
+    double INC[TB];                          // oscillator increments of the block (conformance mode: every lane walks them)
+    R HE[FIR_HIST + TB], HO[FIR_HIST + TB];  // oscillator history, even / odd 2x-rate samples
+};
+
+template <typename R>
+struct WideSmem {
+    typename Wide<R>::Unit ring[WIDE_SLOTS][Wide<R>::NF][TB][Wide<R>::UP];
+    FFHalf<R> ff[2 * Wide<R>::MAX_PAIRS];
+    alignas(16) R outb[32][Wide<R>::OUT_LD];
+    unsigned long long full[WIDE_SLOTS], empty[WIDE_SLOTS];
+    double kc[sizeof(R) == 8 ? 18 : 1][32];   // conformance mode: per-utterance constants of the recurrence warp
+    long long n_tube[32];
+    R *out_ptr[32];
+    long long n_cta;
+};
+
+// try_wait with a suspend-time hint: the waiting warp sleeps in hardware until the phase completes instead of
+// spinning through issue slots the working warps need
+__device__ __forceinline__ void mbar_wait_sleep(void *bar, uint32_t parity)
+{
+    uint32_t ok = 0;
+    for (uint32_t spin = 0; !ok; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+            : "memory");
+        if (spin > (1u << 20)) __trap();
+    }
+}
+
+__device__ __forceinline__ void mbar_arrive(void *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct WideArgs {
+    TubeArgs t;
+    int n_groups;      // CTAs; group g holds utterances order[start(g) .. start(g+1))
+    int debug;         // profiling aid (TRM_WIDE_DEBUG): 1 = feed-forward warps skip their work, 2 = recurrence warp skips its work
+};
+
+__device__ __forceinline__ void wide_group(int n, int n_groups, int g, int &start, int &count)
+{
+    const int base = n / n_groups, rem = n % n_groups;
+    start = g * base + (g < rem ? g : rem);
+    count = base + (g < rem ? 1 : 0);
+}
+
+template <typename R>
+__global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs wargs)
+{
+    constexpr bool FAST = sizeof(R) == 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WideSmem<R> &W = *reinterpret_cast<WideSmem<R> *>(smem_raw);
+    const TubeArgs &args = wargs.t;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int g_start, g_count;
+    wide_group(args.n_utt, wargs.n_groups, blockIdx.x, g_start, g_count);
+    const int n_pairs = (g_count + 1) >> 1;
+
+    // ---- CTA init: zero the ring and histories, barriers, per-utterance pointers ---------------------------
+    {
+        uint32_t *w = reinterpret_cast<uint32_t *>(&W.ring[0][0][0][0]);
+        constexpr int NW = (int)(sizeof(W.ring) / 4);
+        for (int i = threadIdx.x; i < NW; i += blockDim.x) w[i] = 0u;
+        for (int h = warp; h < 2 * Wide<R>::MAX_PAIRS; h += blockDim.x >> 5) {
+            for (int i = lane; i < FIR_HIST + TB; i += 32) { W.ff[h].HE[i] = (R)0; W.ff[h].HO[i] = (R)0; }
+            if (lane < TB) W.ff[h].INC[lane] = 0.0;
+        }
+        if (threadIdx.x == 0) {
+            W.n_cta = 0;
+            for (int s = 0; s < WIDE_SLOTS; ++s) { mbar_init(&W.full[s], (uint32_t)n_pairs); mbar_init(&W.empty[s], 1); }
+            mbar_fence_init();
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const bool has = lane < g_count;
+        const int u = args.order ? args.order[g_start + (has ? lane : 0)] : g_start + (has ? lane : 0);
+        const trm_cuda_utterance *D = args.desc + u;
+        W.n_tube[lane] = has ? D->n_tube : 0;
+        W.out_ptr[lane] = reinterpret_cast<R *>(args.tube) + D->tube_offset;
+        if (has) atomicMax((unsigned long long *)&W.n_cta, (unsigned long long)D->n_tube);
+    }
+    __syncthreads();
+    const int64_t n_cta = W.n_cta;
+    if (n_cta <= 0 || warp > n_pairs) return;
+    const int n_blocks = (int)((n_cta + TB - 1) / TB);
+
+    if (warp == 0) {
+        // =====================================================================================================
+        // recurrence warp
+        // =====================================================================================================
+        const bool has = lane < g_count;
+        const int u = args.order ? args.order[g_start + (has ? lane : 0)] : g_start + (has ? lane : 0);
+        const trm_cuda_utterance *__restrict__ D = args.desc + u;
+        const R d = (R)D->dampingFactor;
+        R *const orow = &W.outb[lane][0];
+
+        if constexpr (FAST) {
+            const float tb1 = (float)D->tb1, gain = (float)D->throatGain;
+            const float m_b11 = (float)D->mouth[1], m_a20 = (float)D->mouth[2], m_a21 = (float)D->mouth[3], m_b21 = (float)D->mouth[4];
+            const float n_b11 = (float)D->nose[1], n_a20 = (float)D->nose[2], n_a21 = (float)D->nose[3], n_b21 = (float)D->nose[4];
+            // constant junctions: nasal N2|N3 .. N5|N6 and the nose termination, folded like the variable ones
+            float nA[4], nB[4], nC[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double k = D->nasal_coeff[q];
+                nA[q] = (float)(D->dampingFactor * (1.0 + k));
+                nB[q] = (float)(D->dampingFactor * k);
+                nC[q] = (float)(D->dampingFactor * (1.0 - k));
+            }
+            const float nose_rk = (float)(D->dampingFactor * D->nose[0] * D->nasal_coeff[4]);    // d a10 k
+            const float nose_1k = (float)(1.0 + D->nasal_coeff[4]);
+            const float m_nb11 = -m_b11, n_nb11 = -n_b11;
+            // waves: t[j] / bt[j] = top / bottom of oropharynx section Sj+1, nt / nb nasal
+            float t[10], bt[10], nt[6], nb[6];
+#pragma unroll
+            for (int q = 0; q < 10; ++q) { t[q] = 0.0f; bt[q] = 0.0f; }
+#pragma unroll
+            for (int q = 0; q < 6; ++q) { nt[q] = 0.0f; nb[q] = 0.0f; }
+            float m_ry = 0.0f, m_rx = 0.0f, m_rY = 0.0f, n_ry = 0.0f, n_rx = 0.0f, n_rY = 0.0f;
+            float y1 = 0.0f, y2 = 0.0f, thy = 0.0f;
+
+            for (int blk = 0; blk < n_blocks; ++blk) {
+                const int slot = blk & 1;
+                mbar_wait_sleep(&W.full[slot], (uint32_t)((blk >> 1) & 1));
+#pragma unroll 1
+                for (int s0 = 0; s0 < ((wargs.debug & 2) ? 0 : TB); s0 += 4) {
+                  float yo[4];
+#pragma unroll
+                  for (int si = 0; si < 4; ++si) {
+                    const int s = s0 + si;
+                    const float4 j0 = W.ring[slot][0][s][lane], j1 = W.ring[slot][1][s][lane], j2 = W.ring[slot][2][s][lane];
+                    const float4 w3 = W.ring[slot][3][s][lane], j4 = W.ring[slot][4][s][lane], j6 = W.ring[slot][5][s][lane];
+                    const float4 j7 = W.ring[slot][6][s][lane], j8 = W.ring[slot][7][s][lane], mo = W.ring[slot][8][s][lane];
+                    const float4 j10 = W.ring[slot][9][s][lane], sc = W.ring[slot][10][s][lane];
+                    // frication band-pass (TRMFilters.m:19-29; factor 2 folded into the coefficients) and throat low-pass
+                    const float fr = (sc.y + (mo.w * y1)) - (j10.w * y2);
+                    y2 = y1; y1 = fr;
+                    const float th = sc.z + (tb1 * thy);
+                    thy = th;
+                    // glottis end (m:792) and S1|S2 (m:796-798)
+                    const float t0n = (bt[0] * d) + sc.x;
+                    const float t1n = (j0.x * t[0]) - (j0.y * bt[1]);
+                    const float b0n = (j0.y * t[0]) + (j0.z * bt[1]);
+                    // S2|S3, S3|S4 (m:803-807)
+                    const float t2n = ((j1.x * t[1]) - (j1.y * bt[2])) + (j1.w * fr);
+                    const float b1n = (j1.y * t[1]) + (j1.z * bt[2]);
+                    const float t3n = ((j2.x * t[2]) - (j2.y * bt[3])) + (j2.w * fr);
+                    const float b2n = (j2.y * t[2]) + (j2.z * bt[3]);
+                    // velum 3-way junction (m:810-813): {d aL, d(aL-1), d aU, d(aU-1)}
+                    const float uc = w3.z * nb[0];
+                    const float b3n = ((w3.y * t[3]) + (w3.x * bt[4])) + uc;
+                    const float t4n = (((w3.x * t[3]) + (w3.y * bt[4])) + uc) + (mo.z * fr);
+                    const float nt0n = ((w3.x * t[3]) + (w3.x * bt[4])) + (w3.w * nb[0]);
+                    // S5|S6 (m:816-818), S6|S7 pure delay (m:821-822)
+                    const float t5n = ((j4.x * t[4]) - (j4.y * bt[5])) + (j4.w * fr);
+                    const float b4n = (j4.y * t[4]) + (j4.z * bt[5]);
+                    const float t6n = (t[5] * d) + (j0.w * fr);
+                    const float b5n = bt[6] * d;
+                    // S7|S8 .. S9|S10 (m:825-829)
+                    const float t7n = ((j6.x * t[6]) - (j6.y * bt[7])) + (j6.w * fr);
+                    const float b6n = (j6.y * t[6]) + (j6.z * bt[7]);
+                    const float t8n = ((j7.x * t[7]) - (j7.y * bt[8])) + (j7.w * fr);
+                    const float b7n = (j7.y * t[7]) + (j7.z * bt[8]);
+                    const float t9n = ((j8.x * t[8]) - (j8.y * bt[9])) + (j8.w * fr);
+                    const float b8n = (j8.y * t[8]) + (j8.z * bt[9]);
+                    // mouth (m:832-835): bottom = d a10 k8 top - b11 bottom_prev ; radiation of (1+k8) top
+                    const float b9n = (mo.x * t[9]) + (m_nb11 * m_ry);
+                    m_ry = b9n;
+                    const float xm = mo.y * t[9];
+                    const float radm = ((m_a20 * xm) + (m_a21 * m_rx)) - (m_b21 * m_rY);
+                    m_rx = xm; m_rY = radm;
+                    // nasal branch (m:839-843): N1|N2 varies with the velum, the rest is constant
+                    const float nt1n = (j10.x * nt[0]) - (j10.y * nb[1]);
+                    const float nb0n = (j10.y * nt[0]) + (j10.z * nb[1]);
+                    float ntn[6], nbn[6];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        ntn[q + 2] = (nA[q] * nt[q + 1]) - (nB[q] * nb[q + 2]);
+                        nbn[q + 1] = (nB[q] * nt[q + 1]) + (nC[q] * nb[q + 2]);
+                    }
+                    // nose (m:846-849)
+                    const float nb5n = (nose_rk * nt[5]) + (n_nb11 * n_ry);
+                    n_ry = nb5n;
+                    const float xn = nose_1k * nt[5];
+                    const float radn = ((n_a20 * xn) + (n_a21 * n_rx)) - (n_b21 * n_rY);
+                    n_rx = xn; n_rY = radn;
+
+                    t[0] = t0n; t[1] = t1n; t[2] = t2n; t[3] = t3n; t[4] = t4n; t[5] = t5n; t[6] = t6n; t[7] = t7n; t[8] = t8n; t[9] = t9n;
+                    bt[0] = b0n; bt[1] = b1n; bt[2] = b2n; bt[3] = b3n; bt[4] = b4n; bt[5] = b5n; bt[6] = b6n; bt[7] = b7n; bt[8] = b8n;
+                    bt[9] = b9n;
+                    nt[0] = nt0n; nt[1] = nt1n; nb[0] = nb0n;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { nt[q + 2] = ntn[q + 2]; nb[q + 1] = nbn[q + 1]; }
+                    nb[5] = nb5n;
+                    yo[si] = (radm + radn) + (th * gain);
+                  }
+                  *reinterpret_cast<float4 *>(&orow[s0]) = make_float4(yo[0], yo[1], yo[2], yo[3]);
+                }
+                __syncwarp(FULL);
+                if (lane == 0) mbar_arrive(&W.empty[slot]);
+                // transposed write-back: 4 lanes store the 16 samples of one utterance as 128-bit vectors
+                {
+                    const int64_t n0 = (int64_t)blk * TB;
+#pragma unroll 1
+                    for (int v0 = 0; v0 < g_count; v0 += 8) {
+                        const int v = v0 + (lane >> 2), part = lane & 3;
+                        if (v < g_count) {
+                            const int64_t left = W.n_tube[v] - n0;
+                            R *dst = W.out_ptr[v] + n0;
+                            if (left >= TB) {
+                                reinterpret_cast<float4 *>(dst)[part] = *reinterpret_cast<const float4 *>(&W.outb[v][4 * part]);
+                            } else {
+                                for (int i = 4 * part; i < 4 * part + 4; ++i)
+                                    if (i < left) dst[i] = W.outb[v][i];
+                            }
+                        }
+                    }
+                }
+                __syncwarp(FULL);
+            }
+        } else {
+            // ---- conformance mode: the reference's operations in the reference's order ---------------------------
+            // The 16 junctions of one sample are independent; the code is written stage by stage ACROSS the junctions
+            // (all differences, then all k-products, ...) so that consecutive instructions are independent and the
+            // FP64 pipe never waits on its own result.  Per-utterance constants other than the damping factor are read
+            // from shared memory when needed: registers are for the 41 state values and the interleaving.
+            enum { K_TB1, K_GAIN, K_MA10, K_MB11, K_MA20, K_MA21, K_MB21, K_NA10, K_NB11, K_NA20, K_NA21, K_NB21,
+                   K_NK0, K_NK1, K_NK2, K_NK3, K_NK4 };
+            {
+                double (*kc)[32] = W.kc;
+                kc[K_TB1][lane] = D->tb1; kc[K_GAIN][lane] = D->throatGain;
+                kc[K_MA10][lane] = D->mouth[0]; kc[K_MB11][lane] = D->mouth[1]; kc[K_MA20][lane] = D->mouth[2];
+                kc[K_MA21][lane] = D->mouth[3]; kc[K_MB21][lane] = D->mouth[4];
+                kc[K_NA10][lane] = D->nose[0]; kc[K_NB11][lane] = D->nose[1]; kc[K_NA20][lane] = D->nose[2];
+                kc[K_NA21][lane] = D->nose[3]; kc[K_NB21][lane] = D->nose[4];
+#pragma unroll
+                for (int q = 0; q < 5; ++q) kc[K_NK0 + q][lane] = D->nasal_coeff[q];
+            }
+            __syncwarp(FULL);
+#define KC(i) (W.kc[i][lane])
+            double t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0, t6 = 0, t7 = 0, t8 = 0, t9 = 0;
+            double b0 = 0, b1 = 0, b2 = 0, b3 = 0, b4 = 0, b5 = 0, b6 = 0, b7 = 0, b8 = 0, b9 = 0;
+            double nt0 = 0, nt1 = 0, nt2 = 0, nt3 = 0, nt4 = 0, nt5 = 0, nb0 = 0, nb1 = 0, nb2 = 0, nb3 = 0, nb4 = 0, nb5 = 0;
+            double m_ry = 0.0, m_rx = 0.0, m_rY = 0.0, n_ry = 0.0, n_rx = 0.0, n_rY = 0.0;
+            double y1 = 0.0, y2 = 0.0, thy = 0.0;
+
+            for (int blk = 0; blk < n_blocks; ++blk) {
+                const int slot = blk & 1;
+                mbar_wait_sleep(&W.full[slot], (uint32_t)((blk >> 1) & 1));
+#pragma unroll 1
+                for (int s0 = 0; s0 < ((wargs.debug & 2) ? 0 : TB); s0 += 2) {
+                    double yo[2];
+#pragma unroll
+                    for (int si = 0; si < 2; ++si) {
+                        const int s = s0 + si;
+                        // record: {k0,k1} {k2,aL} {k4,k6} {k7,k8} {k9,k10} {aU,FC1} {FC2,FC3} {FC4,FC5} {FC6,FC7} {FC8,2g} {2b,in} {ff,thr}
+                        const double2 q9 = W.ring[slot][9][s][lane], q10 = W.ring[slot][10][s][lane], q11 = W.ring[slot][11][s][lane];
+                        const double2 q0 = W.ring[slot][0][s][lane], q1 = W.ring[slot][1][s][lane], q5 = W.ring[slot][5][s][lane];
+                        const double2 q2 = W.ring[slot][2][s][lane], q3 = W.ring[slot][3][s][lane], q4 = W.ring[slot][4][s][lane];
+                        // frication band-pass (TRMFilters.m:19-29, factor 2 folded in) and throat low-pass (TRMFilters.m:72-77)
+                        const double fr = (q11.x + (q9.y * y1)) - (q10.x * y2);
+                        y2 = y1; y1 = fr;
+                        const double th = q11.y + (KC(K_TB1) * thy);
+                        thy = th;
+                        // ---- stage 1: differences / first products of every junction (m:792-849) ----
+                        const double e0 = t0 - b1, e1 = t1 - b2, e2 = t2 - b3, e4 = t4 - b5, e6 = t6 - b7, e7 = t7 - b8, e8 = t8 - b9;
+                        const double en0 = nt0 - nb1, en1 = nt1 - nb2, en2 = nt2 - nb3, en3 = nt3 - nb4, en4 = nt4 - nb5;
+                        const double pa = q1.y * t3, pb = q1.y * b4, pc = q5.x * nb0;
+                        const double g0 = b0 * d, g5 = t5 * d, h5 = b6 * d;
+                        const double mk = q4.x * t9, mx1 = (1.0 + q4.x) * t9;
+                        const double nkk = KC(K_NK4) * nt5, nx1 = (1.0 + KC(K_NK4)) * nt5;
+                        // ---- stage 2: deltas ----
+                        const double d0 = q0.x * e0, d1 = q0.y * e1, d2 = q1.x * e2, d4 = q2.x * e4, d6 = q2.y * e6, d7 = q3.x * e7, d8 = q3.y * e8;
+                        const double dn0 = q4.y * en0, dn1 = KC(K_NK0) * en1, dn2 = KC(K_NK1) * en2, dn3 = KC(K_NK2) * en3, dn4 = KC(K_NK3) * en4;
+                        const double jp = (pa + pb) + pc;
+                        const double mr1 = KC(K_MA10) * mk, mr2 = KC(K_MB11) * m_ry;
+                        const double nr1 = KC(K_NA10) * nkk, nr2 = KC(K_NB11) * n_ry;
+                        const double ma = KC(K_MA20) * mx1, mb = KC(K_MA21) * m_rx, mc = KC(K_MB21) * m_rY;
+                        const double na = KC(K_NA20) * nx1, nbb = KC(K_NA21) * n_rx, nc = KC(K_NB21) * n_rY;
+                        // ---- stage 3: sums ----
+                        const double u1 = t0 + d0, v0 = b1 + d0, u2 = t1 + d1, v1 = b2 + d1, u3 = t2 + d2, v2 = b3 + d2;
+                        const double u5 = t4 + d4, v4 = b5 + d4, u7 = t6 + d6, v6 = b7 + d6, u8 = t7 + d7, v7 = b8 + d7, u9 = t8 + d8, v8 = b9 + d8;
+                        const double w3 = jp - t3, w4 = jp - b4, wn = jp - nb0;
+                        const double un1 = nt0 + dn0, vn0 = nb1 + dn0, un2 = nt1 + dn1, vn1 = nb2 + dn1, un3 = nt2 + dn2, vn2 = nb3 + dn2;
+                        const double un4 = nt3 + dn3, vn3 = nb4 + dn3, un5 = nt4 + dn4, vn4 = nb5 + dn4;
+                        const double refl = mr1 - mr2, refn = nr1 - nr2;
+                        const double radm = (ma + mb) - mc, radn = (na + nbb) - nc;
+                        const double f1 = q5.y * fr;
+                        // the remaining taps are loaded late: their registers are free again by now
+                        const double2 q6 = W.ring[slot][6][s][lane], q7 = W.ring[slot][7][s][lane], q8 = W.ring[slot][8][s][lane];
+                        const double f2 = q6.x * fr, f3 = q6.y * fr, f4 = q7.x * fr, f5 = q7.y * fr, f6 = q8.x * fr, f7 = q8.y * fr, f8 = q9.x * fr;
+                        // ---- stage 4: damping, stage 5: frication injection ----
+                        m_ry = refl; m_rx = mx1; m_rY = radm;
+                        n_ry = refn; n_rx = nx1; n_rY = radn;
+                        const double nt0n = wn * d;
+                        t0 = g0 + q10.y;
+                        t1 = u1 * d;             b0 = v0 * d;
+                        t2 = (u2 * d) + f1;      b1 = v1 * d;
+                        t3 = (u3 * d) + f2;      b2 = v2 * d;
+                        b3 = w3 * d;
+                        const double t4n = (w4 * d) + f3;
+                        t5 = (u5 * d) + f4;      b4 = v4 * d;
+                        t6 = g5 + f5;            b5 = h5;
+                        t7 = (u7 * d) + f6;      b6 = v6 * d;
+                        t8 = (u8 * d) + f7;      b7 = v7 * d;
+                        t9 = (u9 * d) + f8;      b8 = v8 * d;
+                        b9 = d * refl;
+                        t4 = t4n;
+                        nt1 = un1 * d;           nb0 = vn0 * d;
+                        nt2 = un2 * d;           nb1 = vn1 * d;
+                        nt3 = un3 * d;           nb2 = vn2 * d;
+                        nt4 = un4 * d;           nb3 = vn3 * d;
+                        nt5 = un5 * d;           nb4 = vn4 * d;
+                        nb5 = d * refn;
+                        nt0 = nt0n;
+                        yo[si] = (radm + radn) + (th * KC(K_GAIN));
+                    }
+                    *reinterpret_cast<double2 *>(&orow[s0]) = make_double2(yo[0], yo[1]);
+                }
+#undef KC
+                __syncwarp(FULL);
+                if (lane == 0) mbar_arrive(&W.empty[slot]);
+                {
+                    const int64_t n0 = (int64_t)blk * TB;
+#pragma unroll 1
+                    for (int v0 = 0; v0 < g_count; v0 += 4) {
+                        const int v = v0 + (lane >> 3), part = lane & 7;
+                        if (v < g_count) {
+                            const int64_t left = W.n_tube[v] - n0;
+                            R *dst = W.out_ptr[v] + n0;
+                            if (left >= TB) {
+                                reinterpret_cast<float4 *>(dst)[part] = *reinterpret_cast<const float4 *>(&W.outb[v][2 * part]);
+                            } else {
+                                for (int i = 2 * part; i < 2 * part + 2; ++i)
+                                    if (i < left) dst[i] = W.outb[v][i];
+                            }
+                        }
+                    }
+                }
+                __syncwarp(FULL);
+            }
+        }
+        return;
+    }
+
+    // =========================================================================================================
+    // feed-forward warp: utterances 2*pair and 2*pair+1 of the group, lane = sample of a 16-sample block
+    // (phases S0 / A1 / S1 / A2 of tube_kernel.cuh; the results go to the ring instead of the ladder's tables)
+    // =========================================================================================================
+    const int pair = warp - 1;
+    const int half = lane >> 4, hl = lane & 15;
+    const int ucol = 2 * pair + half;                     // column of this half's utterance in the ring
+    FFHalf<R> &S = W.ff[ucol];
+    const bool has_utt = ucol < g_count;
+    const int u = args.order ? args.order[g_start + (has_utt ? ucol : 0)] : g_start + (has_utt ? ucol : 0);
+    const trm_cuda_utterance *__restrict__ D = args.desc + u;
+    const int64_t n_tube = has_utt ? D->n_tube : 0;
+    const int n_frames = D->n_frames;
+    const int cp = D->controlPeriod;
+    const double *__restrict__ F = args.frames + D->frame_offset * 16;
+    const double *__restrict__ wt_base = args.wavetables + (size_t)D->voice * TRM_TABLE_LENGTH;
+    const bool pulse_wave = D->waveform == 0;
+    const bool modulation = D->usesModulation != 0;
+    const int div1 = D->div1, div2 = D->div2;
+
+    const bool feeds = n_tube > 0;
+    const int n_chunks = (n_frames + FRAME_CHUNK - 1) / FRAME_CHUNK;
+    if (hl == 0 && feeds) {
+        mbar_init(&S.mbar[0], 1);
+        mbar_init(&S.mbar[1], 1);
+        mbar_fence_init();
+    }
+    __syncwarp(FULL);
+    if (hl == 0 && feeds) {
+        for (int c = 0; c < 2 && c < n_chunks; ++c) {
+            int cnt = min(FRAME_CHUNK, n_frames - c * FRAME_CHUNK);
+            mbar_expect_tx(&S.mbar[c], (uint32_t)cnt * 128u);
+            tma_bulk_g2s(&S.FR[c][0][0], F + (size_t)c * FRAME_CHUNK * 16, (uint32_t)cnt * 128u, &S.mbar[c]);
+        }
+    }
+    if (feeds) mbar_wait(&S.mbar[0], 0);
+
+    double p_cur = 0.0, p_delta = 0.0, p_next = feeds ? S.FR[0][0][hl] : 0.0;
+    int f_idx = 0, jc = 0;
+    double pos = 0.0;
+    unsigned long long pos_fx = 0ull;
+    unsigned long long kb = args.noise_k0;
+    const unsigned long long MASK44 = (1ull << 44) - 1ull;
+    const unsigned long long pw0 = c_noise_pow[hl], pw1 = c_noise_pow[hl + 1], pwB = c_noise_pow[TB];
+    R xm1 = 0, xm2 = 0;
+    const int pf = hl >> 1, pc = hl & 1;                   // parameter lane -> (unit, component) of the staged value
+
+    for (int blk = 0; blk < n_blocks; ++blk) {
+        const int slot = blk & 1;
+        const int64_t n0 = (int64_t)blk * TB;
+        const int64_t left = n_tube - n0;
+        const int nb = left >= TB ? TB : (left > 0 ? (int)left : 0);
+        const bool active = hl < nb;
+        if (blk >= WIDE_SLOTS) mbar_wait_sleep(&W.empty[slot], (uint32_t)(((blk >> 1) - 1) & 1));
+        if (wargs.debug & 1) {
+            __syncwarp(FULL);
+            if (lane == 0) mbar_arrive(&W.full[slot]);
+            continue;
+        }
+
+        // ---- S0: parameter interpolation, lane = parameter (m:611-688).  The 16 x 16 interpolated values are
+        //      staged INSIDE this utterance's part of the ring slot (fields 0..7, sample position rotated by the
+        //      field so that the stores of the 16 parameter lanes fall into different banks); phase A1 reads
+        //      them back into registers before it writes any record.
+        int refill = -1;
+        for (int s = 0; s < TB;) {
+            if (jc == 0 && f_idx + 1 < n_frames && feeds) {
+                const int fn = f_idx + 1;
+                const int ch = fn / FRAME_CHUNK;
+                if ((fn % FRAME_CHUNK) == 0) {
+                    refill = ch + 1;
+                    mbar_wait(&S.mbar[ch & 1], (uint32_t)((ch >> 1) & 1));
+                }
+                const double nxt = S.FR[ch & 1][fn % FRAME_CHUNK][hl];
+                p_cur = p_next;
+                p_delta = (nxt - p_cur) / (double)cp;
+                p_next = nxt;
+            }
+            const int run = min(TB - s, cp - jc);
+            for (int i = 0; i < run; ++i) {
+                reinterpret_cast<double *>(&W.ring[slot][pf][(s + i + pf) & (TB - 1)][ucol])[pc] = p_cur;
+                p_cur += p_delta;
+            }
+            s += run;
+            jc += run;
+            if (jc == cp) { jc = 0; ++f_idx; }
+        }
+        __syncwarp(FULL);
+        if (hl == 0 && refill >= 0 && refill < n_chunks) {
+            const int cnt = min(FRAME_CHUNK, n_frames - refill * FRAME_CHUNK);
+            mbar_expect_tx(&S.mbar[refill & 1], (uint32_t)cnt * 128u);
+            tma_bulk_g2s(&S.FR[refill & 1][0][0], F + (size_t)refill * FRAME_CHUNK * 16, (uint32_t)cnt * 128u, &S.mbar[refill & 1]);
+        }
+
+        // ---- A1: lane = sample: conversions and coefficients (m:294-300, 712-773; TRMFilters.m:9-17) ---------
+        double prm[16];
+#pragma unroll
+        for (int f = 0; f < 8; ++f) {
+            const double2 v = *reinterpret_cast<const double2 *>(&W.ring[slot][f][(hl + f) & (TB - 1)][ucol]);
+            prm[2 * f] = v.x; prm[2 * f + 1] = v.y;
+        }
+        __syncwarp(FULL);                                   // every staged value is in registers: records may be written
+        double inc_d;
+        {
+            const double f0 = 220.0 * exp2((prm[0] + 3.0) / 12.0);
+            inc_d = (f0 / 2.0) * D->basicIncrement;
+            if constexpr (!FAST) S.INC[hl] = inc_d;
+        }
+        double ax_d;
+        R ax, ah1;
+        R bp_alpha2;
+        if constexpr (FAST) {
+            const float axf = amplitude_f((float)prm[1]);
+            ax_d = (double)axf;
+            {
+                const float tq = axf * (float)D->tnDelta;
+                const float fr = tq - floorf(tq);
+                if (fabsf(fr - 0.5f) < 2e-3f) ax_d = amplitude_db(prm[1]);
+            }
+            ax = axf;
+            ah1 = amplitude_f((float)prm[2]);
+            const float fa = amplitude_f((float)prm[3]);
+            const float dd = (float)D->dampingFactor;
+            float r2[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { const float r = (float)prm[7 + q]; r2[q] = r * r; }
+            float tap[8];
+            {
+                const double fpos = prm[4];
+                const int ipos = (int)fpos;
+                const float comp = (float)(fpos - (double)ipos);
+                const float t0 = (1.0f - comp) * fa, t1 = comp * fa;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) tap[q] = (q == ipos) ? t0 : ((ipos >= 0 && q == ipos + 1) ? t1 : 0.0f);
+            }
+            auto two_port = [&](float ra2, float rb2, float w) {
+                const float inv = __fdividef(dd, ra2 + rb2);
+                return make_float4(2.0f * ra2 * inv, (ra2 - rb2) * inv, 2.0f * rb2 * inv, w);
+            };
+            float beta2, gamma2;
+            {
+                const float sr = (float)D->sampleRate;
+                const float pi = 3.14159265358979323846f;
+                const float inv_sr = 1.0f / sr;
+                float su, cu;
+                __sincosf((pi * (float)prm[6]) * inv_sr, &su, &cu);
+                const float cosv = __cosf(((2.0f * pi) * (float)prm[5]) * inv_sr);
+                beta2 = __fdividef(cu - su, cu + su);
+                gamma2 = (1.0f + beta2) * cosv;
+                bp_alpha2 = 0.5f - 0.5f * beta2;
+            }
+            W.ring[slot][0][hl][ucol] = two_port(r2[0], r2[1], tap[4]);      // S1|S2; .w = FC5 (pure-delay junction S6|S7)
+            W.ring[slot][1][hl][ucol] = two_port(r2[1], r2[2], tap[0]);
+            W.ring[slot][2][hl][ucol] = two_port(r2[2], r2[3], tap[1]);
+            W.ring[slot][4][hl][ucol] = two_port(r2[3], r2[4], tap[3]);
+            W.ring[slot][5][hl][ucol] = two_port(r2[4], r2[5], tap[5]);
+            W.ring[slot][6][hl][ucol] = two_port(r2[5], r2[6], tap[6]);
+            W.ring[slot][7][hl][ucol] = two_port(r2[6], r2[7], tap[7]);
+            {
+                const float vel = (float)prm[15], v2 = vel * vel;
+                const float inv = __fdividef(dd, (r2[3] + r2[3]) + v2);
+                W.ring[slot][3][hl][ucol] = make_float4(2.0f * r2[3] * inv, -v2 * inv, 2.0f * v2 * inv, (v2 - (r2[3] + r2[3])) * inv);
+                W.ring[slot][9][hl][ucol] = two_port(v2, (float)D->nr1sq, beta2);
+            }
+            {
+                const float ap2 = (float)D->apScale2;
+                const float inv = __fdividef(1.0f, r2[7] + ap2);
+                W.ring[slot][8][hl][ucol] = make_float4(dd * (float)D->mouth[0] * ((r2[7] - ap2) * inv), 2.0f * r2[7] * inv, tap[2], gamma2);
+            }
+        } else {
+            ax_d = amplitude_db(prm[1]);
+            ax = (R)ax_d;
+            ah1 = (R)amplitude_db(prm[2]);
+            double r2[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { const double r = prm[7 + q]; r2[q] = r * r; }
+            const double k0 = (r2[0] - r2[1]) / (r2[0] + r2[1]);
+            const double k1 = (r2[1] - r2[2]) / (r2[1] + r2[2]);
+            const double k2 = (r2[2] - r2[3]) / (r2[2] + r2[3]);
+            const double k4 = (r2[3] - r2[4]) / (r2[3] + r2[4]);
+            const double k6 = (r2[4] - r2[5]) / (r2[4] + r2[5]);
+            const double k7 = (r2[5] - r2[6]) / (r2[5] + r2[6]);
+            const double k8 = (r2[6] - r2[7]) / (r2[6] + r2[7]);
+            const double ap2 = D->apScale2;
+            const double k9 = (r2[7] - ap2) / (r2[7] + ap2);
+            const double vel = prm[15];
+            const double v2 = vel * vel;
+            const double sum = 2.0 / ((r2[3] + r2[3]) + v2);
+            const double aL = sum * r2[3], aU = sum * v2;
+            const double n2 = D->nr1sq;
+            const double k10 = (v2 - n2) / (v2 + n2);
+            double tap[8];
+            {
+                const double fa = amplitude_db(prm[3]);
+                const double fpos = prm[4];
+                const int ipos = (int)fpos;
+                const double comp = fpos - (double)ipos;
+                const double rem = 1.0 - comp;
+                const double t0 = rem * fa, t1 = comp * fa;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) tap[q] = (q == ipos) ? t0 : ((ipos >= 0 && q == ipos + 1) ? t1 : 0.0);
+            }
+            double beta2, gamma2;
+            {
+                const double sr = D->sampleRate;
+                const double pi = 3.14159265358979323846;
+                const double tanv = tan((pi * prm[6]) / sr);
+                const double cosv = cos(((2.0 * pi) * prm[5]) / sr);
+                const double beta = (1.0 - tanv) / (2.0 * (1.0 + tanv));
+                beta2 = 2.0 * beta;
+                gamma2 = 2.0 * ((0.5 + beta) * cosv);
+                bp_alpha2 = (R)(2.0 * ((0.5 - beta) / 2.0));
+            }
+            W.ring[slot][0][hl][ucol] = make_double2(k0, k1);
+            W.ring[slot][1][hl][ucol] = make_double2(k2, aL);
+            W.ring[slot][2][hl][ucol] = make_double2(k4, k6);
+            W.ring[slot][3][hl][ucol] = make_double2(k7, k8);
+            W.ring[slot][4][hl][ucol] = make_double2(k9, k10);
+            W.ring[slot][5][hl][ucol] = make_double2(aU, tap[0]);
+            W.ring[slot][6][hl][ucol] = make_double2(tap[1], tap[2]);
+            W.ring[slot][7][hl][ucol] = make_double2(tap[3], tap[4]);
+            W.ring[slot][8][hl][ucol] = make_double2(tap[5], tap[6]);
+            W.ring[slot][9][hl][ucol] = make_double2(tap[7], gamma2);
+            reinterpret_cast<double *>(&W.ring[slot][10][hl][ucol])[0] = beta2;
+        }
+        // noise (TRMUtility.m:71-85 as the MCG mod 2^44) + one-zero low-pass (TRMFilters.m:81-86)
+        R lp_noise;
+        {
+            const unsigned long long kt = (kb * pw1) & MASK44, kp = (kb * pw0) & MASK44;
+            const double nz = (double)(long long)kt * TWO_M44 - 0.5;
+            const double nzp = (n0 + hl == 0) ? 0.0 : ((double)(long long)kp * TWO_M44 - 0.5);
+            lp_noise = (R)(nz + nzp);
+            kb = (kb * pwB) & MASK44;
+        }
+
+        // ---- S1: oscillator position (TRMWavetable.m:165-168, 28-34) -------------------------------------------
+        double p0, p1;
+        if constexpr (FAST) {
+            const unsigned long long inc_fx = __double2ull_rn(inc_d * 36028797018963968.0);
+            unsigned long long incl = inc_fx + inc_fx;
+#pragma unroll
+            for (int o = 1; o < TB; o <<= 1) {
+                const unsigned long long up = __shfl_up_sync(FULL, incl, o, 16);
+                if (hl >= o) incl += up;
+            }
+            const unsigned long long ub = pos_fx + incl, ua = ub - inc_fx;
+            pos_fx += __shfl_sync(FULL, incl, (lane & 16) | (TB - 1));
+            const unsigned long long top = 511ull << 55;
+            p0 = (ua > top) ? -((double)(0ull - ua) * 2.77555756156289135e-17) : (double)ua * 2.77555756156289135e-17;
+            p1 = (ub > top) ? -((double)(0ull - ub) * 2.77555756156289135e-17) : (double)ub * 2.77555756156289135e-17;
+        } else {
+            __syncwarp(FULL);                               // INC of the whole block is visible
+            p0 = 0.0; p1 = 0.0;
+#pragma unroll
+            for (int s = 0; s < TB; ++s) {
+                const double di = S.INC[s];
+                pos = pos + di;
+                pos = pos - ((pos > 511.0) ? 512.0 : 0.0);     // mod0: wraps only above 511 (TRMWavetable.m:28-34)
+                const double pa = pos;
+                pos = pos + di;
+                pos = pos - ((pos > 511.0) ? 512.0 : 0.0);
+                if (hl == s) { p0 = pa; p1 = pos; }
+            }
+        }
+
+        // ---- A2: table look-ups, FIR, source mixing (TRMWavetable.m:174-195, m:305-337) --------------------------
+        {
+            if (!active) { p0 = 0.0; p1 = 0.0; }
+            const double newDiv2 = (double)div2 - rint(ax_d * D->tnDelta);
+            const double Ld = newDiv2 - (double)div1;
+            int lo0 = ((int)p0) & (TRM_TABLE_LENGTH - 1), lo1 = ((int)p1) & (TRM_TABLE_LENGTH - 1);
+            int hi0 = lo0 + 1, hi1 = lo1 + 1;
+            if (hi0 > 511) hi0 -= 512;
+            if (hi1 > 511) hi1 -= 512;
+            if constexpr (FAST) {
+                const float Lf = (float)Ld;
+                const float scale = __fdividef(1.0f, Lf * Lf);
+                const float inv_div1 = 1.0f / (float)div1;
+                const float w00 = table_value_fast(wt_base, lo0, div1, inv_div1, newDiv2, scale, pulse_wave);
+                const float w01 = table_value_fast(wt_base, hi0, div1, inv_div1, newDiv2, scale, pulse_wave);
+                const float w10 = table_value_fast(wt_base, lo1, div1, inv_div1, newDiv2, scale, pulse_wave);
+                const float w11 = table_value_fast(wt_base, hi1, div1, inv_div1, newDiv2, scale, pulse_wave);
+                S.HE[FIR_HIST + hl] = w00 + ((float)(p0 - (double)lo0) * (w01 - w00));
+                S.HO[FIR_HIST + hl] = w10 + ((float)(p1 - (double)lo1) * (w11 - w10));
+            } else {
+                const R scale = (R)(1.0 / (Ld * Ld));
+                R w0 = table_value<R>(wt_base, lo0, div1, div2, newDiv2, scale, pulse_wave);
+                R w1 = table_value<R>(wt_base, hi0, div1, div2, newDiv2, scale, pulse_wave);
+                S.HE[FIR_HIST + hl] = w0 + ((R)(p0 - (double)lo0) * (w1 - w0));
+                w0 = table_value<R>(wt_base, lo1, div1, div2, newDiv2, scale, pulse_wave);
+                w1 = table_value<R>(wt_base, hi1, div1, div2, newDiv2, scale, pulse_wave);
+                S.HO[FIR_HIST + hl] = w0 + ((R)(p1 - (double)lo1) * (w1 - w0));
+            }
+        }
+        __syncwarp(FULL);
+        R sig;
+        {
+            const R *ho = &S.HO[FIR_HIST + hl], *he = &S.HE[FIR_HIST + hl];
+            R pulse0;
+            if constexpr (FAST) {
+                float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll
+                for (int q = 0; q < FIR_HIST; q += 2) {
+                    s0 += ho[-q] * FirCoef<R>::at(2 * q);
+                    s1 += he[-q] * FirCoef<R>::at(2 * q + 1);
+                    s2 += ho[-q - 1] * FirCoef<R>::at(2 * q + 2);
+                    s3 += he[-q - 1] * FirCoef<R>::at(2 * q + 3);
+                }
+                s0 += ho[-FIR_HIST] * FirCoef<R>::at(2 * FIR_HIST);
+                pulse0 = (s0 + s1) + (s2 + s3);
+            } else {
+                R acc = (R)0;
+#pragma unroll
+                for (int q = 0; q < FIR_HIST; ++q) {
+                    acc += ho[-q] * FirCoef<R>::at(2 * q);
+                    acc += he[-q] * FirCoef<R>::at(2 * q + 1);
+                }
+                acc += ho[-FIR_HIST] * FirCoef<R>::at(2 * FIR_HIST);
+                pulse0 = acc;
+            }
+            const R bf = (R)D->breathinessFactor, one_minus_bf = (R)(1.0 - D->breathinessFactor);
+            const R pulsed_noise = lp_noise * pulse0;
+            const R pulse = ax * ((pulse0 * one_minus_bf) + (pulsed_noise * bf));
+            if (modulation) {
+                R crossmix = ax * (R)D->crossmixFactor;
+                crossmix = (crossmix < (R)1) ? crossmix : (R)1;
+                sig = (pulsed_noise * crossmix) + (lp_noise * ((R)1 - crossmix));
+            } else
+                sig = lp_noise;
+            const R tube_in = (pulse + (ah1 * sig)) * (R)0.125;
+            const R thr_in = (R)D->ta0 * (pulse * (R)0.125);
+            // band-pass feed-forward part alpha*(x[n]-x[n-2]); x[n-2] comes from two lanes down or the carry
+            R x2 = __shfl_sync(FULL, sig, (lane & 16) | ((hl - 2) & 15));
+            if (hl == 0) x2 = xm2;
+            if (hl == 1) x2 = xm1;
+            const R bp_ff = bp_alpha2 * (sig - x2);
+            const int last = nb > 0 ? nb - 1 : 0;
+            const R l1 = __shfl_sync(FULL, sig, (lane & 16) | last);
+            const R l2 = __shfl_sync(FULL, sig, (lane & 16) | (last > 0 ? last - 1 : 0));
+            xm2 = (last > 0) ? l2 : xm1;
+            xm1 = l1;
+            if constexpr (FAST) {
+                W.ring[slot][10][hl][ucol] = make_float4(tube_in, bp_ff, thr_in, 0.0f);
+            } else {
+                reinterpret_cast<double *>(&W.ring[slot][10][hl][ucol])[1] = tube_in;
+                W.ring[slot][11][hl][ucol] = make_double2(bp_ff, thr_in);
+            }
+        }
+        __syncwarp(FULL);
+        if (lane == 0) mbar_arrive(&W.full[slot]);
+        {
+            // slide the oscillator history down by one block (rows TB.. -> 0..)
+            const R e0 = S.HE[TB + hl], o0 = S.HO[TB + hl];
+            const R e1 = (hl < FIR_HIST - TB) ? S.HE[2 * TB + hl] : (R)0;
+            const R o1 = (hl < FIR_HIST - TB) ? S.HO[2 * TB + hl] : (R)0;
+            __syncwarp(FULL);
+            S.HE[hl] = e0; S.HO[hl] = o0;
+            if (hl < FIR_HIST - TB) { S.HE[TB + hl] = e1; S.HO[TB + hl] = o1; }
+        }
+        __syncwarp(FULL);
+    }
+}
+
+}  // namespace trm

@@ -9,6 +9,14 @@ import oracle_lib as O
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(params=["sections", "utterances"], autouse=True)
+def tube_mapping(request, monkeypatch):
+    """Every test runs with both waveguide mappings: lane-per-section (tube_kernel.cuh, what small batches get by
+    default) and the batch-throughput mapping (tube_wide.cuh, what large batches get)."""
+    monkeypatch.setenv("TRM_TUBE_MAPPING", request.param)
+    return request.param
+
 FP64_TOL = 1e-9
 FP32_SNR_DB = 80.0
 
@@ -225,3 +233,35 @@ def test_synthesizer_adapter_and_file_outputs(tmp_path):
         assert raw[:4] == magic
         body = np.frombuffer(raw[-2 * pcm.size:], dtype="<i2" if fmt == 2 else ">i2")
         assert np.array_equal(body.astype(np.int16), pcm)
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_mappings_agree_bit_for_bit(precision, monkeypatch):
+    """The two waveguide mappings (lane-per-section / lane-per-utterance + feed-forward warps) perform the same
+    operations in the same order on every sample: their tube-rate signals, output samples, maxima and PCM are
+    identical bits, so a result never depends on which mapping the batch size selected.  Ragged lengths (including
+    utterances that end inside a 16-sample block and an odd utterance count), mixed voices and rates."""
+    g = _g()
+    from gnuspeech_b200 import workloads as W
+    rng = np.random.default_rng(11)
+    n_frames = [int(x) for x in rng.integers(2, 260, 75)] + [1, 2, 301]
+    frames = W.random_walk_ragged(n_frames, seed=77)
+    voices = [dict(), dict(length=15.0), dict(length=10.0, temperature=32.0), dict(waveform=1), dict(usesModulation=0, lossFactor=1.5)]
+    ips = [g.TRMInputParameters(44100.0 if u % 3 else 22050.0, **voices[u % len(voices)]) for u in range(len(n_frames))]
+    out = {}
+    for mapping in ("sections", "utterances"):
+        monkeypatch.setenv("TRM_TUBE_MAPPING", mapping)
+        b, pcm, smp, tube = _run(ips, frames, n_frames, precision, want_tube=True)
+        to, nt = b.tubeOffsets, None
+        out[mapping] = (b.numberSamples.copy(), b.maximumSampleValues.copy(), pcm, smp, tube, to.copy())
+    a, c = out["sections"], out["utterances"]
+    assert np.array_equal(a[0], c[0])
+    assert np.array_equal(a[1], c[1]), "per-utterance maxima differ between the mappings"
+    assert np.array_equal(a[2], c[2]), "PCM differs between the mappings"
+    ns, oo = a[0], None
+    b2 = g.TRMBatch(ips, n_frames, precision=precision)
+    oo, to = b2.outOffsets, b2.tubeOffsets
+    for u in range(len(n_frames)):
+        assert np.array_equal(a[3][oo[u]:oo[u] + ns[u]], c[3][oo[u]:oo[u] + ns[u]]), "output samples of utterance %d" % u
+        nt = (n_frames[u] - 1) * g.derive(ips[u], n_frames[u]).controlPeriod
+        assert np.array_equal(a[4][to[u]:to[u] + nt], c[4][to[u]:to[u] + nt]), "tube-rate signal of utterance %d" % u

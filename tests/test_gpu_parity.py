@@ -12,6 +12,14 @@ import oracle_lib as O
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(params=["sections", "utterances"], autouse=True)
+def tube_mapping(request, monkeypatch):
+    """Every test runs with both waveguide mappings: lane-per-section (tube_kernel.cuh, what small batches get by
+    default) and the batch-throughput mapping (tube_wide.cuh, what large batches get)."""
+    monkeypatch.setenv("TRM_TUBE_MAPPING", request.param)
+    return request.param
+
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 FP64_TOL = 1e-9
 FP32_SNR_DB = 80.0

@@ -40,6 +40,13 @@ def main():
     lm = line_map(tag, kernel)
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], stdout=subprocess.PIPE, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
+    # a report may hold several kernels: keep the section whose "Kernel Name" row matches the demangled hint
+    hint = os.environ.get("NCU_KERNEL", "tube_kernel")
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
+    for a, b in zip(starts[:-1], starts[1:]):
+        if hint in rows[a][1]:
+            rows = rows[a:b]
+            break
     h, data = rows[1], rows[2:]
     ix = {n: i for i, n in enumerate(h)}
     base = int(data[0][ix["Address"]], 16)
