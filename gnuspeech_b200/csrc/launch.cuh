@@ -13,7 +13,7 @@ namespace trm {
 
 template <typename R> constexpr int src_smem_bytes()
 {
-    return TRM_SRC_FILTER_LEN * (int)sizeof(HD<R>) + (SRC_ROWS + (SRC_THREADS / 32) * SRC_CHUNK) * SRC_LD * (int)sizeof(R);
+    return (32 * SRC_XLD + SRC_NT_MAX * SRC_CLD + (SRC_THREADS / 32) * 32 * (SRC_CHUNK + 1)) * (int)sizeof(R);
 }
 
 template <typename R> static int configure_kernels(KernelInfo *info)

