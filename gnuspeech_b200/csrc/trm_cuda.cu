@@ -191,7 +191,8 @@ struct trm_cuda_ctx {
     cudaStream_t streams[MAX_SLOTS]{};
     Arena arenas[MAX_SLOTS];
     HostStage stages[MAX_SLOTS];
-    int n_slots = 8;              // chunks in flight: their kernels co-reside, copies overlap other chunks' kernels
+    int n_slots = 3;              // chunks in flight: one uploading, one computing, one downloading
+    cudaEvent_t ev_in[MAX_SLOTS]{}, ev_run[MAX_SLOTS]{}, ev_out[MAX_SLOTS]{};
     int wide_min_utt = 0;         // batches at least this large use the batch-throughput waveguide mapping
 };
 
@@ -401,9 +402,12 @@ int launch_stage(trm_cuda_ctx *ctx, int precision, int stage, const DeviceChunk 
     return 0;
 }
 
-int chunk_utterances(int n, const trm_cuda_utterance *desc, size_t esz)
+int chunk_utterances(const trm_cuda_ctx *ctx, int precision, int n, const trm_cuda_utterance *desc, size_t esz)
 {
-    // Chunk size: enough utterances to fill the GPU (2 per warp), bounded by scratch memory.
+    // Chunk size: the kernels of one chunk run alone on the device, so a chunk must be large enough to fill it --
+    // for the batch-throughput waveguide mapping that is >= ~14 utterances per SM (below that its recurrence warp,
+    // not the feed-forward work, sets the time) -- and small enough that there are at least two chunks, so that the
+    // PCM of one chunk leaves for the host while the next one is computed.  Bounded by scratch memory.
     const char *env = getenv("TRM_CHUNK_UTTERANCES");
     if (env && atoi(env) > 0) return atoi(env);
     size_t per_utt = 0;
@@ -412,10 +416,11 @@ int chunk_utterances(int n, const trm_cuda_utterance *desc, size_t esz)
         per_utt += (size_t)desc[i].n_frames * 128 + ((size_t)desc[i].n_tube + (size_t)desc[i].n_out) * esz +
                    (size_t)desc[i].n_out * 2 * desc[i].channels;
     per_utt = per_utt / std::max(probe, 1) + 1;
-    const size_t budget = (size_t)16 << 30;                     // per in-flight chunk
-    long long by_mem = (long long)(budget / per_utt);
-    long long want = 512;                                       // 8 chunks of configs[1] in flight
-    if (n <= 768) want = n;
+    const size_t budget = (size_t)24 << 30;                     // per in-flight chunk
+    const long long by_mem = std::max<long long>(1, (long long)(budget / per_utt));
+    const trm::KernelInfo &ki = precision == 0 ? ctx->info64 : ctx->info32;
+    const long long lo = (long long)ctx->sm_count * (ki.wide_max_utt / 2), hi = (long long)ctx->sm_count * ki.wide_max_utt;
+    long long want = std::min<long long>(hi, std::max<long long>(lo, (n + 1) / 2));
     long long c = std::max<long long>(1, std::min<long long>(std::min<long long>(want, by_mem), n));
     const long long n_chunks = (n + c - 1) / c;                 // balance the chunks
     return (int)((n + n_chunks - 1) / n_chunks);
@@ -526,8 +531,7 @@ int trm_cuda_ctx_create(int device, const trm_cuda_tables *t, trm_cuda_ctx **out
         CK(cudaMemcpy(c->d_tab_f32, tf.data(), tf.size() * sizeof(tf[0]), cudaMemcpyHostToDevice));
     }
     {
-        // earlier chunks get the higher stream priority so their resampler / PCM kernels are placed first and
-        // their PCM leaves for the host while later chunks are still in the waveguide kernel
+        // streams[0..2] = copy-in, compute, copy-out of the chunk pipeline (trm_cuda_synthesize_host)
         int lo = 0, hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));          // lo = least (numerically largest)
         const char *env = getenv("TRM_SLOTS");
@@ -535,6 +539,9 @@ int trm_cuda_ctx_create(int device, const trm_cuda_tables *t, trm_cuda_ctx **out
         for (int i = 0; i < MAX_SLOTS; ++i) {
             const int prio = std::min(lo, hi + i);
             CK(cudaStreamCreateWithPriority(&c->streams[i], cudaStreamNonBlocking, prio));
+            CK(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&c->ev_run[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
         }
     }
     *out = c;
@@ -563,6 +570,11 @@ void trm_cuda_ctx_destroy(trm_cuda_ctx *c)
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (auto &s : c->streams) if (s) cudaStreamDestroy(s);
+    for (int i = 0; i < MAX_SLOTS; ++i) {
+        if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+        if (c->ev_run[i]) cudaEventDestroy(c->ev_run[i]);
+        if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
+    }
     for (auto &a : c->arenas) a.release();
     for (auto &h : c->stages) h.release();
     if (c->d_wavetables) cudaFree(c->d_wavetables);
@@ -580,10 +592,14 @@ int trm_cuda_synthesize_host(trm_cuda_ctx *ctx, int precision, int n, const trm_
     CK(cudaSetDevice(ctx->device));
     const size_t esz = precision == 0 ? sizeof(double) : sizeof(float);
     const bool want_pcm = pcm_host != nullptr;
-    const int per_chunk = chunk_utterances(n, desc, esz);
+    const int per_chunk = chunk_utterances(ctx, precision, n, desc, esz);
     const int n_chunks = (n + per_chunk - 1) / per_chunk;
-    const int N_SLOTS = ctx->n_slots;
-    // TRM_TRACE=1: per-chunk timeline of the pipeline stages (CUDA events on each chunk's stream), printed to stderr
+    const int N_SLOTS = std::min(ctx->n_slots, std::max(n_chunks, 1));
+    // Three-stage pipeline over chunks: frames go up on the copy-in stream, the three kernels of a chunk run on the
+    // compute stream (one chunk at a time: a waveguide launch fills every SM), PCM / samples come back on the copy-out
+    // stream.  H2D of chunk k+1 and D2H of chunk k-1 overlap the kernels of chunk k (full-duplex PCIe).
+    cudaStream_t s_in = ctx->streams[0], s_run = ctx->streams[1], s_out = ctx->streams[2];
+    // TRM_TRACE=1: per-chunk timeline of the pipeline stages (CUDA events), printed to stderr
     const bool trace = getenv("TRM_TRACE") != nullptr;
     std::vector<cudaEvent_t> tev;
     cudaEvent_t t_origin = nullptr;
@@ -594,14 +610,14 @@ int trm_cuda_synthesize_host(trm_cuda_ctx *ctx, int precision, int n, const trm_
         cudaEventRecord(e, st);
         tev.push_back(e);
     };
-    if (trace) { cudaEventCreate(&t_origin); cudaEventRecord(t_origin, ctx->streams[0]); }
-    std::vector<ChunkPlan> plans(std::min(n_chunks, N_SLOTS));
+    if (trace) { cudaEventCreate(&t_origin); cudaEventRecord(t_origin, s_in); cudaStreamWaitEvent(s_run, t_origin, 0); cudaStreamWaitEvent(s_out, t_origin, 0); }
+    std::vector<ChunkPlan> plans(N_SLOTS);
     std::vector<int> slot_chunk(N_SLOTS, -1);
     int64_t n_launch = 0;
 
     auto finish_slot = [&](int slot) -> int {
-        // wait for the slot's stream, then hand the per-utterance maxima to the caller
-        CK(cudaStreamSynchronize(ctx->streams[slot]));
+        // wait for the slot's copy-out, then hand the per-utterance maxima to the caller
+        CK(cudaEventSynchronize(ctx->ev_out[slot]));
         const int ci = slot_chunk[slot];
         if (ci >= 0 && max_host) {
             const ChunkPlan &p = plans[slot];
@@ -628,37 +644,44 @@ int trm_cuda_synthesize_host(trm_cuda_ctx *ctx, int precision, int n, const trm_
         if ((rc = ctx->stages[slot].reserve(p.stage_bytes())) != 0) return rc;
         DeviceChunk dc;
         carve(ctx->arenas[slot], p, esz, want_pcm, dc);
-        cudaStream_t s = ctx->streams[slot];
-        mark(s);
-        if ((rc = upload_plan(p, dc, ctx->stages[slot].base, s)) != 0) return rc;
-        if ((rc = upload_frames(p, dc, desc, frames_host, s)) != 0) return rc;
-        mark(s);
+        // ---- copy-in -----------------------------------------------------------------------------------------
+        mark(s_in);
+        if ((rc = upload_plan(p, dc, ctx->stages[slot].base, s_in)) != 0) return rc;
+        if ((rc = upload_frames(p, dc, desc, frames_host, s_in)) != 0) return rc;
+        CK(cudaEventRecord(ctx->ev_in[slot], s_in));
+        mark(s_in);
+        // ---- kernels -----------------------------------------------------------------------------------------
+        CK(cudaStreamWaitEvent(s_run, ctx->ev_in[slot], 0));
         for (int st = 0; st < TRM_STAGE_COUNT; ++st) {
-            if (st == TRM_STAGE_PCM && !want_pcm) { mark(s); continue; }
-            if ((rc = launch_stage(ctx, precision, st, dc, s)) != 0) return rc;
-            mark(s);
+            if (st == TRM_STAGE_PCM && !want_pcm) { mark(s_run); continue; }
+            if ((rc = launch_stage(ctx, precision, st, dc, s_run)) != 0) return rc;
+            mark(s_run);
             ++n_launch;
         }
+        CK(cudaEventRecord(ctx->ev_run[slot], s_run));
+        // ---- copy-out ----------------------------------------------------------------------------------------
+        CK(cudaStreamWaitEvent(s_out, ctx->ev_run[slot], 0));
         if (want_pcm && p.pcm_elems) {
             long long c_hi = 0;
             for (const auto &d : p.desc) c_hi = std::max<long long>(c_hi, d.pcm_offset + d.n_out * d.channels);
-            CK(cudaMemcpyAsync(pcm_host + p.pcm_lo, dc.pcm, (size_t)c_hi * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(pcm_host + p.pcm_lo, dc.pcm, (size_t)c_hi * sizeof(int16_t), cudaMemcpyDeviceToHost, s_out));
         }
         if (samples_host && p.out_elems) {
             long long o_hi = 0;
             for (const auto &d : p.desc) o_hi = std::max<long long>(o_hi, d.out_offset + d.n_out);
-            CK(cudaMemcpyAsync((unsigned char *)samples_host + (size_t)p.out_lo * esz, dc.out, (size_t)o_hi * esz, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync((unsigned char *)samples_host + (size_t)p.out_lo * esz, dc.out, (size_t)o_hi * esz, cudaMemcpyDeviceToHost, s_out));
         }
         if (tube_host && p.tube_elems) {
             long long t_hi = 0;
             for (const auto &d : p.desc) t_hi = std::max<long long>(t_hi, d.tube_offset + d.n_tube);
-            CK(cudaMemcpyAsync((unsigned char *)tube_host + (size_t)p.tube_lo * esz, dc.tube, (size_t)t_hi * esz, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync((unsigned char *)tube_host + (size_t)p.tube_lo * esz, dc.tube, (size_t)t_hi * esz, cudaMemcpyDeviceToHost, s_out));
         }
         if (max_host) {
             unsigned char *mb = ctx->stages[slot].base + p.stage_bytes() - align_up(p.desc.size() * sizeof(unsigned long long), 256);
-            CK(cudaMemcpyAsync(mb, dc.maxbits, p.desc.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(mb, dc.maxbits, p.desc.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s_out));
         }
-        mark(s);
+        CK(cudaEventRecord(ctx->ev_out[slot], s_out));
+        mark(s_out);
         slot_chunk[slot] = ci;
     }
     for (int slot = 0; slot < N_SLOTS; ++slot) {
