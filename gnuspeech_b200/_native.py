@@ -100,6 +100,8 @@ def lib():
     sig("TRMBatchKernelLaunches", i64, vp)
     sig("TRMBatchSynthesize", C.c_int, vp, vp, vp, vp, vp, C.c_int)
     sig("TRMBatchSynthesizeDebug", C.c_int, vp, vp, vp, vp, vp, C.c_int)
+    sig("TRMBatchSynthesizeAsync", vp, vp, vp, vp, vp, vp, C.c_int, vp)
+    sig("TRMBatchWait", C.c_int, vp)
     sig("TRMBatchMakeResident", vp, vp, vp, C.c_int, P(C.c_int))
     sig("TRMResidentRunStage", C.c_int, vp, C.c_int, vp)
     sig("TRMResidentRun", C.c_int, vp, vp)

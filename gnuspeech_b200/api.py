@@ -364,12 +364,48 @@ class TRMBatch(object):
         check(N.lib().TRMBatchSynthesize(self._h, _ptr(frames), _ptr(pcm_out), _ptr(samples_out), _ptr(devs), nd),
               "TRMBatchSynthesize")
 
+    def synthesize_async(self, frames, pcm_out=None, samples_out=None, devices=None):
+        """Non-blocking form (TRMBatchSynthesizeAsync): returns a ticket; ticket.wait() blocks until the outputs are in
+        the host buffers.  Two tickets per device overlap (copy-out of one call behind the kernels of the next); use one
+        TRMBatch object per ticket in flight."""
+        devs = None
+        nd = 1
+        if devices is not None:
+            devs = np.ascontiguousarray(devices, dtype=np.int32)
+            nd = int(devs.shape[0])
+        err = C.c_int(0)
+        h = N.lib().TRMBatchSynthesizeAsync(self._h, _ptr(frames), _ptr(pcm_out), _ptr(samples_out), _ptr(devs), nd, C.byref(err))
+        if not h:
+            check(err.value or N.TRM_ERR_CUDA, "TRMBatchSynthesizeAsync")
+        return TRMBatchTicket(h, (frames, pcm_out, samples_out, devs, self))
+
     def synthesize_debug(self, frames, pcm_out=None, samples_out=None, tube_out=None, device=0):
         check(N.lib().TRMBatchSynthesizeDebug(self._h, _ptr(frames), _ptr(pcm_out), _ptr(samples_out), _ptr(tube_out),
                                               device), "TRMBatchSynthesizeDebug")
 
     def make_resident(self, frames, device=0):
         return TRMResident(self, frames, device)
+
+
+class TRMBatchTicket(object):
+    """Handle of an asynchronous TRMBatch call; keeps the call's buffers alive until wait() returns."""
+
+    def __init__(self, handle, keep):
+        self._h = handle
+        self._keep = keep
+
+    def wait(self):
+        if self._h:
+            h, self._h = self._h, None
+            rc = N.lib().TRMBatchWait(h)
+            self._keep = None
+            check(rc, "TRMBatchWait")
+
+    def __del__(self):
+        try:
+            self.wait()
+        except Exception:
+            pass
 
 
 class TRMResident(object):

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <tuple>
@@ -180,11 +181,23 @@ struct ChunkPlan {
 
 }  // namespace
 
+// One compute queue per device, shared by every context (lane) on it: the kernels of concurrent calls run in
+// submission order -- waveguide, resampler, PCM of call k, then those of call k+1 -- instead of fighting for the SMs
+// (a waveguide launch of call k+1 that slips in front of call k's resampler would delay k's copy-out by a whole
+// waveguide kernel).  Copies stay on per-context streams.  The mutex covers the enqueue of one chunk's three kernels.
+static cudaStream_t g_run_stream[64];
+static std::mutex g_run_mu[64];
+// Likewise one copy-in queue per device: the frames of concurrent calls go up one call after the other at full PCIe
+// rate (the first call's kernels start after ITS upload, not after everybody's).
+static cudaStream_t g_in_stream[64];
+static std::mutex g_in_mu[64];
+
 struct trm_cuda_ctx {
     int device = 0;
     int sm_count = 0;
     double *d_wavetables = nullptr;
     int wt_capacity = 0;
+    std::vector<double> wt_host;      // what d_wavetables holds
     void *d_tab_f64 = nullptr, *d_tab_f32 = nullptr;
     uint64_t noise_k0 = 0;
     trm::KernelInfo info64{}, info32{};
@@ -416,11 +429,14 @@ int chunk_utterances(const trm_cuda_ctx *ctx, int precision, int n, const trm_cu
         per_utt += (size_t)desc[i].n_frames * 128 + ((size_t)desc[i].n_tube + (size_t)desc[i].n_out) * esz +
                    (size_t)desc[i].n_out * 2 * desc[i].channels;
     per_utt = per_utt / std::max(probe, 1) + 1;
-    const size_t budget = (size_t)24 << 30;                     // per in-flight chunk
+    const size_t budget = (size_t)32 << 30;                     // per in-flight chunk (three lanes per device)
     const long long by_mem = std::max<long long>(1, (long long)(budget / per_utt));
     const trm::KernelInfo &ki = precision == 0 ? ctx->info64 : ctx->info32;
     const long long lo = (long long)ctx->sm_count * (ki.wide_max_utt / 2), hi = (long long)ctx->sm_count * ki.wide_max_utt;
-    long long want = std::min<long long>(hi, std::max<long long>(lo, (n + 1) / 2));
+    // FP64: a launch below ~28 utterances per SM is bound by the latency of its feed-forward warps, so halving a batch
+    // costs more kernel time than the overlapped copy-out saves -> one chunk up to the device's capacity.  FP32: the
+    // kernels are short next to the PCIe time of their PCM -> two chunks, the first one's PCM hides behind the second.
+    long long want = precision == 0 ? hi : std::min<long long>(hi, std::max<long long>(lo, (n + 1) / 2));
     long long c = std::max<long long>(1, std::min<long long>(std::min<long long>(want, by_mem), n));
     const long long n_chunks = (n + c - 1) / c;                 // balance the chunks
     return (int)((n + n_chunks - 1) / n_chunks);
@@ -531,7 +547,13 @@ int trm_cuda_ctx_create(int device, const trm_cuda_tables *t, trm_cuda_ctx **out
         CK(cudaMemcpy(c->d_tab_f32, tf.data(), tf.size() * sizeof(tf[0]), cudaMemcpyHostToDevice));
     }
     {
-        // streams[0..2] = copy-in, compute, copy-out of the chunk pipeline (trm_cuda_synthesize_host)
+        // streams[2] = copy-out of the chunk pipeline (trm_cuda_synthesize_host); frames and kernels go to the device's
+        // shared copy-in and compute queues
+        {
+            std::lock_guard<std::mutex> lk(g_run_mu[device]);
+            if (!g_run_stream[device]) CK(cudaStreamCreateWithFlags(&g_run_stream[device], cudaStreamNonBlocking));
+            if (!g_in_stream[device]) CK(cudaStreamCreateWithFlags(&g_in_stream[device], cudaStreamNonBlocking));
+        }
         int lo = 0, hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));          // lo = least (numerically largest)
         const char *env = getenv("TRM_SLOTS");
@@ -551,16 +573,21 @@ int trm_cuda_ctx_create(int device, const trm_cuda_tables *t, trm_cuda_ctx **out
 int trm_cuda_set_wavetables(trm_cuda_ctx *c, const double *tables, int n_voices)
 {
     if (n_voices <= 0) return fail_msg("trm_cuda_set_wavetables: no voices");
+    const size_t n = (size_t)n_voices * TRM_TABLE_LENGTH;
+    // unchanged since the last call (the usual case: one voice set per application): nothing to do, and in particular
+    // no synchronisation that would serialise this call behind another lane's work on the same device
+    if (c->wt_host.size() == n && memcmp(c->wt_host.data(), tables, n * sizeof(double)) == 0) return 0;
     CK(cudaSetDevice(c->device));
-    CK(cudaDeviceSynchronize());
+    for (int i = 0; i < 3; ++i) CK(cudaStreamSynchronize(c->streams[i]));   // this context's own work only
     if (n_voices > c->wt_capacity) {
         if (c->d_wavetables) cudaFree(c->d_wavetables);
         c->d_wavetables = nullptr;
         c->wt_capacity = 0;
-        CK(cudaMalloc((void **)&c->d_wavetables, (size_t)n_voices * TRM_TABLE_LENGTH * sizeof(double)));
+        CK(cudaMalloc((void **)&c->d_wavetables, n * sizeof(double)));
         c->wt_capacity = n_voices;
     }
-    CK(cudaMemcpy(c->d_wavetables, tables, (size_t)n_voices * TRM_TABLE_LENGTH * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_wavetables, tables, n * sizeof(double), cudaMemcpyHostToDevice));
+    c->wt_host.assign(tables, tables + n);
     return 0;
 }
 
@@ -598,7 +625,7 @@ int trm_cuda_synthesize_host(trm_cuda_ctx *ctx, int precision, int n, const trm_
     // Three-stage pipeline over chunks: frames go up on the copy-in stream, the three kernels of a chunk run on the
     // compute stream (one chunk at a time: a waveguide launch fills every SM), PCM / samples come back on the copy-out
     // stream.  H2D of chunk k+1 and D2H of chunk k-1 overlap the kernels of chunk k (full-duplex PCIe).
-    cudaStream_t s_in = ctx->streams[0], s_run = ctx->streams[1], s_out = ctx->streams[2];
+    cudaStream_t s_in = g_in_stream[ctx->device], s_run = g_run_stream[ctx->device], s_out = ctx->streams[2];
     // TRM_TRACE=1: per-chunk timeline of the pipeline stages (CUDA events), printed to stderr
     const bool trace = getenv("TRM_TRACE") != nullptr;
     std::vector<cudaEvent_t> tev;
@@ -610,7 +637,7 @@ int trm_cuda_synthesize_host(trm_cuda_ctx *ctx, int precision, int n, const trm_
         cudaEventRecord(e, st);
         tev.push_back(e);
     };
-    if (trace) { cudaEventCreate(&t_origin); cudaEventRecord(t_origin, s_in); cudaStreamWaitEvent(s_run, t_origin, 0); cudaStreamWaitEvent(s_out, t_origin, 0); }
+    if (trace) { cudaEventCreate(&t_origin); cudaEventRecord(t_origin, s_out); }
     std::vector<ChunkPlan> plans(N_SLOTS);
     std::vector<int> slot_chunk(N_SLOTS, -1);
     int64_t n_launch = 0;
@@ -645,20 +672,26 @@ int trm_cuda_synthesize_host(trm_cuda_ctx *ctx, int precision, int n, const trm_
         DeviceChunk dc;
         carve(ctx->arenas[slot], p, esz, want_pcm, dc);
         // ---- copy-in -----------------------------------------------------------------------------------------
-        mark(s_in);
-        if ((rc = upload_plan(p, dc, ctx->stages[slot].base, s_in)) != 0) return rc;
-        if ((rc = upload_frames(p, dc, desc, frames_host, s_in)) != 0) return rc;
-        CK(cudaEventRecord(ctx->ev_in[slot], s_in));
-        mark(s_in);
-        // ---- kernels -----------------------------------------------------------------------------------------
-        CK(cudaStreamWaitEvent(s_run, ctx->ev_in[slot], 0));
-        for (int st = 0; st < TRM_STAGE_COUNT; ++st) {
-            if (st == TRM_STAGE_PCM && !want_pcm) { mark(s_run); continue; }
-            if ((rc = launch_stage(ctx, precision, st, dc, s_run)) != 0) return rc;
-            mark(s_run);
-            ++n_launch;
+        {
+            std::lock_guard<std::mutex> lk(g_in_mu[ctx->device]);
+            mark(s_in);
+            if ((rc = upload_plan(p, dc, ctx->stages[slot].base, s_in)) != 0) return rc;
+            if ((rc = upload_frames(p, dc, desc, frames_host, s_in)) != 0) return rc;
+            CK(cudaEventRecord(ctx->ev_in[slot], s_in));
+            mark(s_in);
         }
-        CK(cudaEventRecord(ctx->ev_run[slot], s_run));
+        // ---- kernels -----------------------------------------------------------------------------------------
+        {
+            std::lock_guard<std::mutex> lk(g_run_mu[ctx->device]);
+            CK(cudaStreamWaitEvent(s_run, ctx->ev_in[slot], 0));
+            for (int st = 0; st < TRM_STAGE_COUNT; ++st) {
+                if (st == TRM_STAGE_PCM && !want_pcm) { mark(s_run); continue; }
+                if ((rc = launch_stage(ctx, precision, st, dc, s_run)) != 0) return rc;
+                mark(s_run);
+                ++n_launch;
+            }
+            CK(cudaEventRecord(ctx->ev_run[slot], s_run));
+        }
         // ---- copy-out ----------------------------------------------------------------------------------------
         CK(cudaStreamWaitEvent(s_out, ctx->ev_run[slot], 0));
         if (want_pcm && p.pcm_elems) {

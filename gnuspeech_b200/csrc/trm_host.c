@@ -426,12 +426,15 @@ static int describe(const TRMInputParameters *ip, int32_t n_frames, voice_set *v
  * CUDA contexts: one per device, created on first use
  * ---------------------------------------------------------------------------------------------- */
 #define MAX_DEVICES 64
-static trm_cuda_ctx *g_ctx[MAX_DEVICES];
-static pthread_mutex_t g_ctx_mu[MAX_DEVICES];
+/* Three context lanes per device (one call uploading, one computing, one downloading): each lane owns its streams, device arenas and pinned staging, so several calls can be
+ * in flight on one GPU (TRMBatchSynthesizeAsync): the PCM of call k leaves for the host while call k+1 computes. */
+#define CTX_LANES 3
+static trm_cuda_ctx *g_ctx[MAX_DEVICES][CTX_LANES];
+static pthread_mutex_t g_ctx_mu[MAX_DEVICES][CTX_LANES];
 static pthread_mutex_t g_ctx_table_mu = PTHREAD_MUTEX_INITIALIZER;
 static int g_ctx_mu_init;
 
-static int acquire_ctx(int device, trm_cuda_ctx **out)
+static int acquire_ctx(int device, trm_cuda_ctx **out, int *lane_out)
 {
     int rc;
     const trm_cuda_tables *t = tables(&rc);
@@ -439,21 +442,30 @@ static int acquire_ctx(int device, trm_cuda_ctx **out)
     if (device < 0 || device >= MAX_DEVICES) return set_err(TRM_ERR_CUDA, "bad device ordinal%s", "");
     pthread_mutex_lock(&g_ctx_table_mu);
     if (!g_ctx_mu_init) {
-        for (int i = 0; i < MAX_DEVICES; i++) pthread_mutex_init(&g_ctx_mu[i], NULL);
+        for (int i = 0; i < MAX_DEVICES; i++)
+            for (int l = 0; l < CTX_LANES; l++) pthread_mutex_init(&g_ctx_mu[i][l], NULL);
         g_ctx_mu_init = 1;
     }
-    if (!g_ctx[device]) {
-        if (trm_cuda_ctx_create(device, t, &g_ctx[device]) != 0) {
-            pthread_mutex_unlock(&g_ctx_table_mu);
+    pthread_mutex_unlock(&g_ctx_table_mu);
+    /* a context serves one call at a time: take the first free lane, else queue on lane 0 */
+    int lane = -1;
+    for (int l = 0; l < CTX_LANES && lane < 0; l++)
+        if (pthread_mutex_trylock(&g_ctx_mu[device][l]) == 0) lane = l;
+    if (lane < 0) { lane = 0; pthread_mutex_lock(&g_ctx_mu[device][0]); }
+    if (!g_ctx[device][lane]) {
+        pthread_mutex_lock(&g_ctx_table_mu);
+        const int failed = trm_cuda_ctx_create(device, t, &g_ctx[device][lane]) != 0;
+        pthread_mutex_unlock(&g_ctx_table_mu);
+        if (failed) {
+            pthread_mutex_unlock(&g_ctx_mu[device][lane]);
             return cuda_err();
         }
     }
-    pthread_mutex_unlock(&g_ctx_table_mu);
-    pthread_mutex_lock(&g_ctx_mu[device]);       /* a context serves one call at a time */
-    *out = g_ctx[device];
+    *out = g_ctx[device][lane];
+    *lane_out = lane;
     return TRM_OK;
 }
-static void release_ctx(int device) { pthread_mutex_unlock(&g_ctx_mu[device]); }
+static void release_ctx(int device, int lane) { pthread_mutex_unlock(&g_ctx_mu[device][lane]); }
 
 void *TRMHostAlloc(size_t bytes)
 {
@@ -720,13 +732,14 @@ static void *shard_main(void *arg)
 {
     shard_job *j = arg;
     trm_cuda_ctx *ctx;
-    j->rc = acquire_ctx(j->device, &ctx);
+    int lane = 0;
+    j->rc = acquire_ctx(j->device, &ctx, &lane);
     if (j->rc == TRM_OK) {
         if (trm_cuda_set_wavetables(ctx, j->b->voices.tables, j->b->voices.n) != 0 ||
             trm_cuda_synthesize_host(ctx, j->b->precision, j->u1 - j->u0, j->b->desc + j->u0, (const double *)j->frames,
                                      j->pcm, j->samples, j->b->maxima + j->u0, j->tube, &j->launches) != 0)
             j->rc = cuda_err();
-        release_ctx(j->device);
+        release_ctx(j->device, lane);
     }
     if (j->rc) snprintf(j->msg, sizeof j->msg, "%s", g_errmsg);
     return NULL;
@@ -781,6 +794,56 @@ int TRMBatchSynthesize(TRMBatch *b, const TRMParameters *frames, int16_t *pcm_ou
     return batch_run(b, frames, pcm_out, samples_out, NULL, devices, n_devices);
 }
 
+/* ---- asynchronous calls: one host thread per ticket; two tickets per device overlap (context lanes) ---- */
+struct TRMBatchTicket {
+    pthread_t th;
+    TRMBatch *b;
+    const TRMParameters *frames;
+    int16_t *pcm;
+    void *samples;
+    int devices[MAX_DEVICES], n_devices, has_devices;
+    int rc;
+    char msg[512];
+};
+
+static void *ticket_main(void *arg)
+{
+    TRMBatchTicket *t = arg;
+    t->rc = batch_run(t->b, t->frames, t->pcm, t->samples, NULL, t->has_devices ? t->devices : NULL, t->n_devices);
+    if (t->rc) snprintf(t->msg, sizeof t->msg, "%s", g_errmsg);
+    return NULL;
+}
+
+TRMBatchTicket *TRMBatchSynthesizeAsync(TRMBatch *b, const TRMParameters *frames, int16_t *pcm_out, void *samples_out,
+                                        const int *devices, int n_devices, int *err)
+{
+    int dummy;
+    if (!err) err = &dummy;
+    TRMBatchTicket *t = calloc(1, sizeof *t);
+    if (!t) { *err = set_err(TRM_ERR_NOMEM, "out of memory%s", ""); return NULL; }
+    t->b = b; t->frames = frames; t->pcm = pcm_out; t->samples = samples_out;
+    t->n_devices = n_devices > MAX_DEVICES ? MAX_DEVICES : n_devices;
+    t->has_devices = devices != NULL;
+    for (int k = 0; devices && k < t->n_devices; k++) t->devices[k] = devices[k];
+    if (pthread_create(&t->th, NULL, ticket_main, t) != 0) {
+        free(t);
+        *err = set_err(TRM_ERR_NOMEM, "cannot start a host thread%s", "");
+        return NULL;
+    }
+    *err = TRM_OK;
+    return t;
+}
+
+int TRMBatchWait(TRMBatchTicket *t)
+{
+    if (!t) return set_err(TRM_ERR_PARAM, "null ticket%s", "");
+    pthread_join(t->th, NULL);
+    const int rc = t->rc;
+    if (rc) snprintf(g_errmsg, sizeof g_errmsg, "%s", t->msg);
+    free(t);
+    return rc;
+}
+
 /* like TRMBatchSynthesize, additionally returning the tube-rate signal (TRMBatchTubeElements() elements) */
 int TRMBatchSynthesizeDebug(TRMBatch *b, const TRMParameters *frames, int16_t *pcm_out, void *samples_out,
                             void *tube_out, int device)
@@ -799,9 +862,10 @@ TRMResident *TRMBatchMakeResident(TRMBatch *b, const TRMParameters *frames, int 
     int dummy;
     if (!err) err = &dummy;
     trm_cuda_ctx *ctx;
-    if ((*err = acquire_ctx(device, &ctx)) != TRM_OK) return NULL;
+    int lane = 0;
+    if ((*err = acquire_ctx(device, &ctx, &lane)) != TRM_OK) return NULL;
     TRMResident *r = calloc(1, sizeof *r);
-    if (!r) { release_ctx(device); *err = set_err(TRM_ERR_NOMEM, "out of memory%s", ""); return NULL; }
+    if (!r) { release_ctx(device, lane); *err = set_err(TRM_ERR_NOMEM, "out of memory%s", ""); return NULL; }
     r->device = device;
     if (trm_cuda_set_wavetables(ctx, b->voices.tables, b->voices.n) != 0 ||
         trm_cuda_resident_create(ctx, b->precision, b->n, b->desc, (const double *)frames, &r->res) != 0) {
@@ -810,7 +874,7 @@ TRMResident *TRMBatchMakeResident(TRMBatch *b, const TRMParameters *frames, int 
         r = NULL;
     } else
         *err = TRM_OK;
-    release_ctx(device);
+    release_ctx(device, lane);
     return r;
 }
 int TRMResidentRunStage(TRMResident *r, int stage, void *cuda_stream)

@@ -197,6 +197,16 @@ const double  *TRMBatchMaximumSampleValues(const TRMBatch *batch); /* [n]       
 int TRMBatchSynthesize(TRMBatch *batch, const TRMParameters *frames, int16_t *pcm_out, void *samples_out,
                        const int *devices, int n_devices);
 
+/* Asynchronous form for callers with a stream of batches: returns at once with a ticket; TRMBatchWait blocks until the
+ * outputs are in the host buffers, frees the ticket and returns the call's status.  Every device keeps up to three calls in
+ * flight (three context lanes, each with its own streams and scratch), so the PCM of call k is copied out while call
+ * k+1 computes and call k+2 uploads its frames.  One ticket per TRMBatch object at a time (the batch holds the call's maxima); inputs and outputs
+ * must stay valid until TRMBatchWait returns.  (The reference has no counterpart: -synthesize is synchronous.) */
+typedef struct TRMBatchTicket TRMBatchTicket;
+TRMBatchTicket *TRMBatchSynthesizeAsync(TRMBatch *batch, const TRMParameters *frames, int16_t *pcm_out, void *samples_out,
+                                        const int *devices, int n_devices, int *err);
+int TRMBatchWait(TRMBatchTicket *ticket);
+
 /* Debug / conformance variant on one device: additionally returns the tube-rate signal (what -synthesize
  * hands to dataFill:, TRMTubeModel.m:346) in the batch's arithmetic type; TRMBatchTubeElements() elements,
  * utterance u at TRMBatchTubeOffsets()[u]. */

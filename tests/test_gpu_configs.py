@@ -273,3 +273,30 @@ def test_mappings_agree(precision, monkeypatch):
             ch = 2 if ips[u].channels == 2 else 1
             d = np.abs(a[2][po[u]:po[u] + ns[u] * ch].astype(np.int32) - c[2][po[u]:po[u] + ns[u] * ch].astype(np.int32))
             assert d.max() <= 1, "utterance %d: PCM differs by %d LSB between the mappings" % (u, int(d.max()))
+
+
+def test_async_calls_overlap_and_match_blocking():
+    """TRMBatchSynthesizeAsync / TRMBatchWait: two calls in flight on one device (two context lanes) return the same
+    bytes as the blocking call, in any completion order; a ticket reports errors like the blocking call does."""
+    g = _g()
+    from gnuspeech_b200 import workloads as W
+    n, nf = 96, 126
+    ip = g.TRMInputParameters(44100.0)
+    frames_a = W.random_walk(n, nf, seed=41)
+    frames_b = W.random_walk(n, nf, seed=42)
+    ref = []
+    for fr in (frames_a, frames_b):
+        b, pcm, _, _ = _run(ip, fr, [nf] * n, g.TRM_PRECISION_FP64)
+        ref.append((pcm.copy(), b.maximumSampleValues.copy()))
+    ns, po = b.numberSamples, b.pcmOffsets
+    batches = [g.TRMBatch(ip, [nf] * n, precision=g.TRM_PRECISION_FP64) for _ in range(2)]
+    pcms = [np.zeros(batches[0].layout.total_pcm_samples, np.int16) for _ in range(2)]
+    for rounds in range(3):
+        tickets = [batches[k].synthesize_async((frames_a, frames_b)[k], pcm_out=pcms[k], devices=[0]) for k in range(2)]
+        for k in (1, 0):
+            tickets[k].wait()
+        for k in range(2):
+            assert np.array_equal(batches[k].maximumSampleValues, ref[k][1])
+            for u in range(n):                               # (the alignment padding between utterances is undefined)
+                assert np.array_equal(pcms[k][po[u]:po[u] + ns[u]], ref[k][0][po[u]:po[u] + ns[u]]), (rounds, k, u)
+            pcms[k][:] = 0
