@@ -40,9 +40,9 @@ UNIT = "audio-s/s"
 FLOP_PER_TUBE_SAMPLE = 390.0     # algorithmic flops per tube-rate sample
 FLOP_PER_OUT_SAMPLE = 110.0      # up-sampling converter, per output sample
 # DRAM traffic per unit measured with `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum of the
-# 4096 x 1 s launch, profiles/prof_r1_final_{f64,f32}_summary.txt) -- linear in the number of samples:
+# 4096 x 1 s launch, profiles/prof_r1b_{fp64,fp32}_summary.txt) -- linear in the number of samples:
 #   waveguide: bytes per tube-rate sample, resampler / PCM: bytes per output sample
-TRAFFIC_PER_UNIT = {"fp64": {"tube": 8.99, "src": 11.28, "pcm": 9.96}, "fp32": {"tube": 5.09, "src": 5.53, "pcm": 5.86}}
+TRAFFIC_PER_UNIT = {"fp64": {"tube": 8.95, "src": 11.34, "pcm": 9.97}, "fp32": {"tube": 5.07, "src": 5.55, "pcm": 5.86}}
 
 
 def host_cores():
@@ -340,7 +340,7 @@ def main():
     src_bytes = float(lay.tube_samples) * esz + float(lay.out_samples) * esz
     pcm_bytes = float(lay.out_samples) * (esz + 2)
     roofline = {
-        "kernel": "tube_kernel<%s>" % ("double" if args.precision == "fp64" else "float"),
+        "kernel": "tube_wide_kernel<%s>" % ("double" if args.precision == "fp64" else "float"),
         "bound": "fp64-pipe" if args.precision == "fp64" else "fp32-pipe",
         "achieved": tube_tf, "peak": peak_tf.value, "unit": "TFLOP/s", "frac": tube_tf / peak_tf.value if peak_tf.value else None,
         "peak_source": "FMA chain measured live on this device (trm_cuda_fp_peak); MEASURED_PEAKS.json has no CUDA-core peak",
