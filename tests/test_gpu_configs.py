@@ -300,3 +300,92 @@ def test_async_calls_overlap_and_match_blocking():
             for u in range(n):                               # (the alignment padding between utterances is undefined)
                 assert np.array_equal(pcms[k][po[u]:po[u] + ns[u]], ref[k][0][po[u]:po[u] + ns[u]]), (rounds, k, u)
             pcms[k][:] = 0
+
+
+def _spot_check(b, pcm, ips, frames, n_frames, precision, picks):
+    """oracle comparison of a few utterances of a big batch: PCM within 1 LSB, numberSamples, maxima"""
+    g = _g()
+    ns, po, mx = b.numberSamples, b.pcmOffsets, b.maximumSampleValues
+    off = np.concatenate(([0], np.cumsum(n_frames)))
+    for u in picks:
+        ip = ips[u] if isinstance(ips, (list, tuple)) else ips
+        ref = O.synthesize(ip, frames[off[u]:off[u + 1]], want_tube=False)
+        assert ns[u] == ref.numberSamples, u
+        tol = 1e-9 if precision == g.TRM_PRECISION_FP64 else 2e-5
+        assert abs(mx[u] - ref.maximumSampleValue) <= tol * ref.maximumSampleValue, u
+        pcm_ref = O.pcm16(ip, ref.samples, ref.maximumSampleValue).astype(np.int32)
+        d = np.abs(pcm[po[u]:po[u] + ns[u]].astype(np.int32) - pcm_ref)
+        assert d.max() <= 1, "utterance %d: PCM off by %d LSB" % (u, int(d.max()))
+
+
+def test_config2_full_size_fp32():
+    """configs[1] at BASELINE size: 4096 random-walk utterances x 10 s, FP32 fast mode, through TRMBatchSynthesize with
+    host buffers.  Properties that do not need the oracle at this size: every utterance has the sample count of the
+    closed form and is normalised to full scale (its loudest PCM code is +-32767 at 60 dB volume); a spread of
+    utterances is compared with the oracle (+-1 LSB)."""
+    g = _g()
+    from gnuspeech_b200 import workloads as W
+    n, nf = 4096, 2501
+    frames = g.PinnedArray((n * nf, 16), np.float64)
+    W.random_walk(n, nf, seed=1, out=frames.array)
+    ip = g.TRMInputParameters(44100.0)
+    b = g.TRMBatch(ip, [nf] * n, precision=g.TRM_PRECISION_FP32)
+    pcm = g.PinnedArray(int(b.layout.total_pcm_samples), np.int16)
+    b.synthesize(frames, pcm_out=pcm, devices=[0])
+    ns, po = b.numberSamples, b.pcmOffsets
+    assert (ns == 441059).all()
+    peaks = np.array([np.abs(pcm.array[po[u]:po[u] + ns[u]]).max() for u in range(0, n, 16)])
+    assert (peaks == 32767).all()
+    assert np.isfinite(b.maximumSampleValues).all() and (b.maximumSampleValues > 0).all()
+    _spot_check(b, pcm.array, ip, frames.array, [nf] * n, g.TRM_PRECISION_FP32, [0, 1337, 4095])
+    pcm.free()
+    frames.free()
+
+
+def test_config3_full_grid_fp32():
+    """configs[2] at BASELINE size: the full 65,536-point static grid x 0.5 s (TRAcT-style sweep), FP32 fast mode.
+    Static vowels: the two pitches of the grid give identical spectra up to the source, the closed-form sample count
+    holds for every utterance, every utterance is normalised to full scale; grid corners are compared with the oracle."""
+    g = _g()
+    from gnuspeech_b200 import workloads as W
+    n, nf = 65536, 126
+    frames = W.grid(range(n), nf)
+    ip = g.TRMInputParameters(44100.0)
+    b = g.TRMBatch(ip, [nf] * n, precision=g.TRM_PRECISION_FP32)
+    pcm = np.zeros(int(b.layout.total_pcm_samples), np.int16)
+    b.synthesize(frames, pcm_out=pcm, devices=[0])
+    ns, po = b.numberSamples, b.pcmOffsets
+    assert (ns == 22109).all()
+    peaks = np.array([np.abs(pcm[po[u]:po[u] + ns[u]]).max() for u in range(0, n, 97)])
+    assert (peaks == 32767).all()
+    # same tract, same pitch, different batch position -> same bytes (grid index bit 14 = velum, bit 15 = pitch)
+    b1 = g.TRMBatch(ip, [nf], precision=g.TRM_PRECISION_FP32)
+    for u in (0, 12345, 65535):
+        one = np.zeros(int(b1.layout.total_pcm_samples), np.int16)
+        b1.synthesize(frames[u * nf:(u + 1) * nf], pcm_out=one, devices=[0])
+        d = np.abs(one[:ns[u]].astype(np.int32) - pcm[po[u]:po[u] + ns[u]].astype(np.int32))
+        assert d.max() <= 1, u                            # +-1 LSB: the lone utterance runs the other lane mapping
+    _spot_check(b, pcm, ip, frames, [nf] * n, g.TRM_PRECISION_FP32, [0, 21845, 43690, 65535])
+
+
+def test_config4_full_size_mixed_lengths():
+    """configs[3] at BASELINE size: 256 utterances of 5-60 s, alternating 44.1 / 22.05 kHz (load balancing: longest
+    first inside the kernels, ragged everywhere), FP32 fast mode; the shortest, the longest and two others are compared
+    with the oracle, all are checked for sample count and normalisation."""
+    g = _g()
+    from gnuspeech_b200 import workloads as W
+    rng = np.random.default_rng(4)
+    n = 256
+    n_frames = [int(x) for x in rng.integers(5 * 250, 60 * 250 + 1, n)]
+    n_frames[7], n_frames[200] = 5 * 250 + 1, 60 * 250 + 1
+    frames = W.random_walk_ragged(n_frames, seed=9)
+    ips = [g.TRMInputParameters(44100.0 if u % 2 == 0 else 22050.0) for u in range(n)]
+    b = g.TRMBatch(ips, n_frames, precision=g.TRM_PRECISION_FP32)
+    pcm = np.zeros(int(b.layout.total_pcm_samples), np.int16)
+    b.synthesize(frames, pcm_out=pcm, devices=[0])
+    ns, po = b.numberSamples, b.pcmOffsets
+    for u in range(n):
+        want = g.derive(ips[u], n_frames[u]).numberSamples
+        assert ns[u] == want, u
+        assert np.abs(pcm[po[u]:po[u] + ns[u]]).max() == 32767, u
+    _spot_check(b, pcm, ips, frames, n_frames, g.TRM_PRECISION_FP32, [7, 200, 64, 129])
