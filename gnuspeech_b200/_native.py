@@ -28,6 +28,16 @@ class TRMInputParametersStruct(C.Structure):
     ]
 
 
+class TRMSynthesisParametersStruct(C.Structure):
+    """TRMSynthesisParameters (include/trm.h; reference MMSynthesisParameters.h:22-52)."""
+    _fields_ = [(n, C.c_double) for n in (
+        "masterVolume", "vocalTractLength", "temperature", "balance", "breathiness", "lossFactor", "pitch",
+        "throatCutoff", "throatVolume", "apertureScaling", "mouthCoef", "noseCoef", "mixOffset",
+        "n1", "n2", "n3", "n4", "n5", "tp", "tnMin", "tnMax")] + [
+        ("glottalPulseShape", C.c_int32), ("shouldUseNoiseModulation", C.c_int32), ("samplingRate", C.c_int32),
+        ("outputChannels", C.c_int32)]
+
+
 class TRMDerivedValuesStruct(C.Structure):
     _fields_ = [("controlPeriod", C.c_int32), ("sampleRate", C.c_int32), ("actualTubeLength", C.c_double),
                 ("padSize", C.c_int32), ("timeRegisterIncrement", C.c_uint32), ("tubeSamples", C.c_int64),
@@ -88,6 +98,10 @@ def lib():
     sig("TRMTubeModelGenerateWAVData", vp, vp, P(sz), P(C.c_int))
     sig("TRMTubeModelSaveOutputToFile", C.c_int, vp, C.c_char_p)
     sig("TRMFree", None, vp)
+    sig("TRMSynthesisParametersRestoreDefaults", None, vp)
+    sig("TRMSynthesisParametersForVoice", C.c_int, C.c_char_p, vp)
+    sig("TRMInputParametersFromSynthesisParameters", None, vp, C.c_int32, vp)
+    sig("TRMSynthesisParametersString", vp, vp)
     sig("TRMBatchCreate", vp, C.c_int, vp, C.c_int, vp, vp, C.c_int, P(C.c_int))
     sig("TRMBatchFree", None, vp)
     sig("TRMBatchGetLayout", None, vp, P(TRMBatchLayoutStruct))

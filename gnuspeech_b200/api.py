@@ -40,6 +40,39 @@ class TRMInputParameters(N.TRMInputParametersStruct):
         return o
 
 
+class MMSynthesisParameters(N.TRMSynthesisParametersStruct):
+    """Utterance-rate voice parameters as Monet keeps them (MMSynthesisParameters.m:160-310): the registered defaults
+    (male voice), the named voices of Other/voices.config, the TRM header they map to and its text form."""
+
+    def __init__(self, voice=None):
+        super().__init__()
+        if voice is None:
+            N.lib().TRMSynthesisParametersRestoreDefaults(C.byref(self))
+        else:
+            check(N.lib().TRMSynthesisParametersForVoice(voice.encode(), C.byref(self)), "TRMSynthesisParametersForVoice")
+
+    def restoreDefaultValues(self):
+        N.lib().TRMSynthesisParametersRestoreDefaults(C.byref(self))
+
+    @property
+    def sampleRate(self):
+        return 22050.0 if self.samplingRate == 0 else 44100.0
+
+    def inputParameters(self, fileFormat=0):
+        """What -[TRMSynthesizer setupSynthesisParameters:] writes into the TRM header (TRMSynthesizer.m:38-65)."""
+        ip = TRMInputParameters()
+        N.lib().TRMInputParametersFromSynthesisParameters(C.byref(self), fileFormat, C.byref(ip))
+        return ip
+
+    @property
+    def parameterString(self):
+        p = N.lib().TRMSynthesisParametersString(C.byref(self))
+        try:
+            return C.string_at(p).decode()
+        finally:
+            N.lib().TRMFree(p)
+
+
 class TRMParameters(object):
     """One control frame (TRMParameters.h:9-17)."""
 

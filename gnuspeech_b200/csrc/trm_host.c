@@ -18,6 +18,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <strings.h>
 
 /* ------------------------------------------------------------------------------------------------
  * errors
@@ -604,6 +605,107 @@ int TRMDataListWriteToFile(const TRMDataList *l, const char *path)
     }
     if (fclose(fp) != 0) return set_err(TRM_ERR_IO, "write error on \"%s\"", path);
     return TRM_OK;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Voice parameters (MMSynthesisParameters.m:160-310, Other/voices.config:15-48, TRMSynthesizer.m:38-65)
+ * ---------------------------------------------------------------------------------------------- */
+void TRMSynthesisParametersRestoreDefaults(TRMSynthesisParameters *sp)
+{
+    memset(sp, 0, sizeof *sp);
+    sp->masterVolume = 60;      sp->vocalTractLength = 17.5; sp->temperature = 25;  sp->balance = 0;
+    sp->breathiness = 1;        sp->lossFactor = 0.5;        sp->pitch = -12;
+    sp->throatCutoff = 1500;    sp->throatVolume = 6;        sp->apertureScaling = 3.05;
+    sp->mouthCoef = 5000;       sp->noseCoef = 5000;         sp->mixOffset = 54;
+    sp->n1 = 1.35; sp->n2 = 1.96; sp->n3 = 1.91; sp->n4 = 1.3; sp->n5 = 0.73;
+    sp->tp = 40; sp->tnMin = 16; sp->tnMax = 32;
+    sp->glottalPulseShape = 0;  sp->shouldUseNoiseModulation = 1;
+    sp->samplingRate = 1;       /* 44100 */
+    sp->outputChannels = 1;     /* stereo */
+}
+
+int TRMSynthesisParametersForVoice(const char *name, TRMSynthesisParameters *sp)
+{
+    static const struct { const char *name; double length, tp, tnMin, tnMax, pitch; } voices[] = {
+        {"Male", 17.5, 0.40, 0.24, 0.24, -12.0}, {"Female", 15.0, 0.40, 0.32, 0.32, 0.0}, {"LgChild", 12.5, 0.40, 0.24, 0.24, 2.5},
+        {"SmChild", 10.0, 0.40, 0.24, 0.24, 5.0}, {"Baby", 7.5, 0.40, 0.24, 0.24, 7.5},
+    };
+    if (!name || !sp) return set_err(TRM_ERR_PARAM, "null argument%s", "");
+    for (size_t i = 0; i < sizeof voices / sizeof voices[0]; i++) {
+        if (strcasecmp(name, voices[i].name) == 0) {
+            TRMSynthesisParametersRestoreDefaults(sp);
+            sp->vocalTractLength = voices[i].length;
+            sp->tp = voices[i].tp * 100.0;
+            sp->tnMin = voices[i].tnMin * 100.0;
+            sp->tnMax = voices[i].tnMax * 100.0;
+            sp->pitch = voices[i].pitch;
+            return TRM_OK;
+        }
+    }
+    return set_err(TRM_ERR_PARAM, "unknown voice \"%s\"", name);
+}
+
+void TRMInputParametersFromSynthesisParameters(const TRMSynthesisParameters *sp, int32_t fileFormat, TRMInputParameters *ip)
+{
+    memset(ip, 0, sizeof *ip);
+    ip->outputFileFormat = fileFormat;
+    ip->outputRate = sp->samplingRate == 0 ? 22050.0f : 44100.0f;
+    ip->controlRate = 250;
+    ip->volume = sp->masterVolume;
+    ip->channels = sp->outputChannels + 1;
+    ip->balance = sp->balance;
+    ip->waveform = sp->glottalPulseShape;
+    ip->tp = sp->tp; ip->tnMin = sp->tnMin; ip->tnMax = sp->tnMax;
+    ip->breathiness = sp->breathiness;
+    ip->length = sp->vocalTractLength;
+    ip->temperature = sp->temperature;
+    ip->lossFactor = sp->lossFactor;
+    ip->apScale = sp->apertureScaling;
+    ip->mouthCoef = sp->mouthCoef;
+    ip->noseCoef = sp->noseCoef;
+    ip->noseRadius[0] = 0;
+    ip->noseRadius[1] = sp->n1; ip->noseRadius[2] = sp->n2; ip->noseRadius[3] = sp->n3;
+    ip->noseRadius[4] = sp->n4; ip->noseRadius[5] = sp->n5;
+    ip->throatCutoff = sp->throatCutoff;
+    ip->throatVol = sp->throatVolume;
+    ip->usesModulation = sp->shouldUseNoiseModulation;
+    ip->mixOffset = sp->mixOffset;
+}
+
+char *TRMSynthesisParametersString(const TRMSynthesisParameters *sp)
+{
+    char *buf = malloc(4096);
+    if (!buf) { set_err(TRM_ERR_NOMEM, "out of memory%s", ""); return NULL; }
+    int n = 0;
+#define LINE(fmt, v, text) n += snprintf(buf + n, 4096 - (size_t)n, fmt, v, text)
+    LINE("%u\t\t; %s\n", 0u, "output file format (0 = AU, 1 = AIFF, 2 = WAVE)");
+    LINE("%g\t\t; %s\n", sp->samplingRate == 0 ? 22050.0 : 44100.0, "output sample rate (22050.0, 44100.0)");
+    LINE("%u\t\t; %s\n", 250u, "input control rate (1 - 1000 Hz)");
+    LINE("%f\t; %s\n", sp->masterVolume, "master volume (0 - 60 dB)");
+    LINE("%lu\t\t; %s\n", (unsigned long)(sp->outputChannels + 1), "number of sound output channels (1 or 2)");
+    LINE("%f\t; %s\n", sp->balance, "stereo balance (-1 to +1)");
+    LINE("%lu\t\t; %s\n", (unsigned long)sp->glottalPulseShape, "glottal source waveform type (0 = pulse, 1 = sine)");
+    LINE("%f\t; %s\n", sp->tp, "glottal pulse rise time (5 - 50 % of GP period)");
+    LINE("%f\t; %s\n", sp->tnMin, "glottal pulse fall time minimum (5 - 50 % of GP period)");
+    LINE("%f\t; %s\n", sp->tnMax, "glottal pulse fall time maximum (5 - 50 % of GP period)");
+    LINE("%f\t; %s\n", sp->breathiness, "glottal source breathiness (0 - 10 % of GS amplitude)");
+    LINE("%f\t; %s\n", sp->vocalTractLength, "nominal tube length (10 - 20 cm)");
+    LINE("%f\t; %s\n", sp->temperature, "tube temperature (25 - 40 degrees celsius)");
+    LINE("%f\t; %s\n", sp->lossFactor, "junction loss factor (0 - 5 % of unity gain)");
+    LINE("%f\t; %s\n", sp->apertureScaling, "aperture scaling radius (3.05 - 12 cm)");
+    LINE("%f\t; %s\n", sp->mouthCoef, "mouth aperture coefficient (0 - 0.99)");
+    LINE("%f\t; %s\n", sp->noseCoef, "nose aperture coefficient (0 - 0.99)");
+    LINE("%f\t; %s\n", sp->n1, "radius of nose section 1 (0 - 3 cm)");
+    LINE("%f\t; %s\n", sp->n2, "radius of nose section 2 (0 - 3 cm)");
+    LINE("%f\t; %s\n", sp->n3, "radius of nose section 3 (0 - 3 cm)");
+    LINE("%f\t; %s\n", sp->n4, "radius of nose section 4 (0 - 3 cm)");
+    LINE("%f\t; %s\n", sp->n5, "radius of nose section 5 (0 - 3 cm)");
+    LINE("%f\t; %s\n", sp->throatCutoff, "throat lowpass frequency cutoff (50 - nyquist Hz)");
+    LINE("%f\t; %s\n", sp->throatVolume, "throat volume (0 - 48 dB)");
+    LINE("%d\t\t; %s\n", (int)sp->shouldUseNoiseModulation, "pulse modulation of noise (0 = off, 1 = on)");
+    LINE("%f\t; %s", sp->mixOffset, "noise crossmix offset (30 - 60 db)");
+#undef LINE
+    return buf;
 }
 
 /* ------------------------------------------------------------------------------------------------

@@ -130,6 +130,42 @@ const TRMParameters *TRMDataListValues(const TRMDataList *list);
 int          TRMDataListWriteToFile(const TRMDataList *list, const char *path);
 
 /* ---------------------------------------------------------------------------------------------
+ * Utterance-rate ("voice") parameters as Monet keeps them: MMSynthesisParameters
+ * (Frameworks/GnuSpeech/MonetModel/MMSynthesisParameters.h:22-52).  Field for field the reference's properties;
+ * the defaults are the registered NSUserDefaults of MMSynthesisParameters.m:160-190.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct TRMSynthesisParameters {
+    double  masterVolume;        /* dB, 0..60   */
+    double  vocalTractLength;    /* cm          */
+    double  temperature;         /* deg C       */
+    double  balance;             /* -1..+1      */
+    double  breathiness;         /* % of GS amplitude */
+    double  lossFactor;          /* % of unity gain   */
+    double  pitch;               /* semitones, added to every frame's glottal pitch by the frame generator
+                                    (EventList.m:985); NOT part of the TRM header */
+    double  throatCutoff, throatVolume, apertureScaling, mouthCoef, noseCoef, mixOffset;
+    double  n1, n2, n3, n4, n5;
+    double  tp, tnMin, tnMax;
+    int32_t glottalPulseShape;        /* 0 pulse, 1 sine  (MMGlottalPulseShape)                 */
+    int32_t shouldUseNoiseModulation;
+    int32_t samplingRate;             /* 0 = 22050 Hz, 1 = 44100 Hz  (MMSamplingRate)          */
+    int32_t outputChannels;           /* 0 = mono, 1 = stereo        (MMChannels)              */
+} TRMSynthesisParameters;
+
+/* +initialize / -restoreDefaultValues (MMSynthesisParameters.m:160-225): the male voice. */
+void TRMSynthesisParametersRestoreDefaults(TRMSynthesisParameters *sp);
+/* The five voice types of the TextToSpeech kit (Other/voices.config:15-48): "Male", "Female", "LgChild", "SmChild",
+ * "Baby" (case-insensitive): defaults with that voice's tract length, glottal pulse rise / fall times (the file gives
+ * them as fractions of the period, the header wants per cent) and base pitch.  TRM_ERR_PARAM for an unknown name. */
+int  TRMSynthesisParametersForVoice(const char *name, TRMSynthesisParameters *sp);
+/* -[TRMSynthesizer setupSynthesisParameters:] (TRMSynthesizer.m:38-65): the TRM header of an utterance.
+ * controlRate = 250, channels = outputChannels + 1, noseRadius[0] = 0, outputFileFormat keeps `fileFormat`. */
+void TRMInputParametersFromSynthesisParameters(const TRMSynthesisParameters *sp, int32_t fileFormat, TRMInputParameters *ip);
+/* -parameterString (MMSynthesisParameters.m:278-310): the 26 header lines of a TRM input file, byte for byte the
+ * reference's printf formats.  Returns a malloc'ed string (TRMFree). */
+char *TRMSynthesisParametersString(const TRMSynthesisParameters *sp);
+
+/* ---------------------------------------------------------------------------------------------
  * TRMTubeModel  (TRMTubeModel.h:29-40).  Single-use like the reference (TRMSynthesizer.m:120).
  * ------------------------------------------------------------------------------------------- */
 typedef struct TRMTubeModel TRMTubeModel;

@@ -189,3 +189,44 @@ def test_no_cpu_fallback():
     with pytest.raises(g.TRMError) as e:
         b.synthesize(W.static_vowel(3, 0), pcm_out=np.zeros(b.layout.total_pcm_samples, np.int16))
     assert e.value.code == -5
+
+
+def test_voice_parameters_defaults_header_and_named_voices(tmp_path):
+    """MMSynthesisParameters layer: the registered defaults are the male voice; -parameterString
+    reproduces the 26 header lines of the reference's own sample input (Applications/Monet/samples/gnuspeech.input,
+    committed as tests/golden/gnuspeech.input) byte for byte; the header round-trips through the TRM file parser into
+    the TRMInputParameters that -setupSynthesisParameters: builds; the named voices of Other/voices.config give the
+    tube rates of SURVEY 8 (control period / sample rate follow from the tract length)."""
+    g = _g()
+    sp = g.MMSynthesisParameters()
+    assert (sp.masterVolume, sp.vocalTractLength, sp.temperature, sp.pitch) == (60.0, 17.5, 25.0, -12.0)
+    assert (sp.tp, sp.tnMin, sp.tnMax, sp.glottalPulseShape, sp.shouldUseNoiseModulation) == (40.0, 16.0, 32.0, 0, 1)
+    assert (sp.samplingRate, sp.outputChannels) == (1, 1)               # 44.1 kHz stereo are Monet's defaults
+    # the reference's sample file was written with 22.05 kHz mono
+    sp.samplingRate, sp.outputChannels = 0, 0
+    want = open(os.path.join(GOLDEN, "gnuspeech.input")).read().split("\n")[:26]
+    got = sp.parameterString.split("\n")
+    # line 2: the sample file predates the "%g" the current -parameterString uses for the rate (MMSynthesisParameters.m:283)
+    assert got[1] == "22050\t\t; output sample rate (22050.0, 44100.0)" and want[1].startswith("22050.000000")
+    assert got[:1] + got[2:] == want[:1] + want[2:]
+    # round trip: header text -> TRM file parser == -setupSynthesisParameters:
+    path = tmp_path / "voice.input"
+    path.write_text(sp.parameterString + "\n" + " ".join(["0.0"] * 16) + "\n")
+    dl = g.TRMDataList.initWithContentsOfFile(str(path))
+    a, b = dl.inputParameters, sp.inputParameters()
+    for name, _ in a._fields_:
+        va, vb = getattr(a, name), getattr(b, name)
+        if name == "noseRadius":
+            assert list(va)[1:] == list(vb)[1:]
+        else:
+            assert va == vb, name
+    assert b.channels == 1 and b.controlRate == 250.0 and b.noseRadius[0] == 0.0
+    # named voices
+    want_rates = {"Male": (79, 19750), "Female": (92, 23000), "LgChild": (111, 27750), "SmChild": (139, 34750), "Baby": (185, 46250)}
+    for name, (cp, sr) in want_rates.items():
+        v = g.MMSynthesisParameters(name.lower())
+        d = g.derive(v.inputParameters(), 251)
+        assert (d.controlPeriod, d.sampleRate) == (cp, sr), name
+    assert g.MMSynthesisParameters("Female").tnMin == 32.0 and g.MMSynthesisParameters("Baby").pitch == 7.5
+    with pytest.raises(g.TRMError):
+        g.MMSynthesisParameters("tenor")
