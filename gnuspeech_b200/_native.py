@@ -38,6 +38,13 @@ class TRMSynthesisParametersStruct(C.Structure):
         ("outputChannels", C.c_int32)]
 
 
+class TRMFrameGenerationStruct(C.Structure):
+    """TRMFrameGeneration (include/trm.h; MMIntonation.m:74-80, EventList.m:983)."""
+    _fields_ = [("useMacroIntonation", C.c_int32), ("useMicroIntonation", C.c_int32), ("useSmoothIntonation", C.c_int32),
+                ("useDrift", C.c_int32), ("driftDeviation", C.c_double), ("driftCutoff", C.c_double), ("pitch", C.c_double),
+                ("driftSeed", C.c_float), ("reserved", C.c_int32)]
+
+
 class TRMDerivedValuesStruct(C.Structure):
     _fields_ = [("controlPeriod", C.c_int32), ("sampleRate", C.c_int32), ("actualTubeLength", C.c_double),
                 ("padSize", C.c_int32), ("timeRegisterIncrement", C.c_uint32), ("tubeSamples", C.c_int64),
@@ -114,6 +121,10 @@ def lib():
     sig("TRMBatchKernelLaunches", i64, vp)
     sig("TRMBatchSynthesize", C.c_int, vp, vp, vp, vp, vp, C.c_int)
     sig("TRMBatchSynthesizeDebug", C.c_int, vp, vp, vp, vp, vp, C.c_int)
+    sig("TRMFrameGenerationSetDefaults", None, vp)
+    sig("TRMEventListFrameCount", i64, vp, i64)
+    sig("TRMBatchGenerateFrames", C.c_int, vp, vp, vp, vp, vp, C.c_int, vp, vp, C.c_int)
+    sig("TRMBatchSynthesizeEvents", C.c_int, vp, vp, vp, vp, vp, C.c_int, vp, vp, C.c_int)
     sig("TRMBatchSynthesizeAsync", vp, vp, vp, vp, vp, vp, C.c_int, vp)
     sig("TRMBatchWait", C.c_int, vp)
     sig("TRMBatchMakeResident", vp, vp, vp, C.c_int, P(C.c_int))

@@ -73,6 +73,33 @@ class MMSynthesisParameters(N.TRMSynthesisParametersStruct):
             N.lib().TRMFree(p)
 
 
+EVENT_DTYPE = np.dtype([("time", np.int64), ("value", np.float64, (36,))])   # TRMEvent (include/trm.h; Event.h)
+
+
+class TRMFrameGeneration(N.TRMFrameGenerationStruct):
+    """Intonation switches, drift and base pitch of the control-frame generator (MMIntonation.m:74-80)."""
+
+    def __init__(self, **kw):
+        super().__init__()
+        N.lib().TRMFrameGenerationSetDefaults(C.byref(self))
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+
+def make_events(times, values):
+    """Structured TRMEvent array from times (ms) and an (n, 36) value array (NaN = no value at that event)."""
+    ev = np.zeros(len(times), EVENT_DTYPE)
+    ev["time"] = times
+    ev["value"] = values
+    return ev
+
+
+def event_list_frame_count(events):
+    """Number of frames -generateOutputInTimeRange: emits for an event list (TRMEventListFrameCount)."""
+    events = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
+    return int(N.lib().TRMEventListFrameCount(events.ctypes.data_as(C.c_void_p), len(events)))
+
+
 class TRMParameters(object):
     """One control frame (TRMParameters.h:9-17)."""
 
@@ -411,6 +438,32 @@ class TRMBatch(object):
         if not h:
             check(err.value or N.TRM_ERR_CUDA, "TRMBatchSynthesizeAsync")
         return TRMBatchTicket(h, (frames, pcm_out, samples_out, devs, self))
+
+    def _event_args(self, events, n_events, fg):
+        events = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
+        cnt = np.ascontiguousarray(n_events, dtype=np.int32)
+        off = np.concatenate(([0], np.cumsum(cnt)[:-1])).astype(np.int64)
+        if isinstance(fg, (list, tuple)):
+            arr = (N.TRMFrameGenerationStruct * len(fg))(*fg)
+            return events, off, cnt, arr, 0
+        return events, off, cnt, fg, 1
+
+    def generate_frames(self, events, n_events, fg, device=0):
+        """Control frames of every utterance from its event list, generated on the GPU (TRMBatchGenerateFrames).
+        events: the utterances' TRMEvent lists back to back; n_events: events per utterance; fg: one TRMFrameGeneration
+        for all, or a list with one per utterance.  Returns (frames (total_frames, 16), drift seeds at exit)."""
+        events, off, cnt, fga, shared = self._event_args(events, n_events, fg)
+        frames = np.zeros((max(1, int(self.layout.total_frames)), 16), np.float64)
+        seeds = np.zeros(max(1, len(cnt)), np.float32)
+        check(N.lib().TRMBatchGenerateFrames(self._h, _ptr(events), _ptr(off), _ptr(cnt), C.cast(C.byref(fga) if shared else fga, C.c_void_p),
+                                             shared, _ptr(frames), _ptr(seeds), device), "TRMBatchGenerateFrames")
+        return frames[:int(self.layout.total_frames)], seeds[:len(cnt)]
+
+    def synthesize_events(self, events, n_events, fg, pcm_out=None, samples_out=None, device=0):
+        """Event lists in, PCM out (TRMBatchSynthesizeEvents): the frames never exist on the host."""
+        events, off, cnt, fga, shared = self._event_args(events, n_events, fg)
+        check(N.lib().TRMBatchSynthesizeEvents(self._h, _ptr(events), _ptr(off), _ptr(cnt), C.cast(C.byref(fga) if shared else fga, C.c_void_p),
+                                               shared, _ptr(pcm_out), _ptr(samples_out), device), "TRMBatchSynthesizeEvents")
 
     def synthesize_debug(self, frames, pcm_out=None, samples_out=None, tube_out=None, device=0):
         check(N.lib().TRMBatchSynthesizeDebug(self._h, _ptr(frames), _ptr(pcm_out), _ptr(samples_out), _ptr(tube_out),

@@ -43,9 +43,10 @@ def _run(cmd, verbose):
 def build(verbose=False, force=False):
     os.makedirs(LIB, exist_ok=True)
     os.makedirs(OBJ, exist_ok=True)
-    headers = [os.path.join(CSRC, h) for h in ("tube_kernel.cuh", "src_kernel.cuh", "launch.cuh", "kernel_args.h")]
+    headers = [os.path.join(CSRC, h) for h in ("tube_kernel.cuh", "tube_wide.cuh", "src_kernel.cuh", "framegen_kernel.cuh",
+                                               "launch.cuh", "kernel_args.h")]
     headers += [os.path.join(INC, h) for h in ("trm.h", "trm_cuda.h", "trm_workload.h")]
-    cu = [("kernels_f64", ["-fmad=false"]), ("kernels_f32", []), ("trm_cuda", [])]
+    cu = [("kernels_f64", ["-fmad=false"]), ("kernels_f32", []), ("kernels_aux", ["-fmad=false"]), ("trm_cuda", [])]
     objs = []
     for name, extra in cu:
         src = os.path.join(CSRC, name + ".cu")

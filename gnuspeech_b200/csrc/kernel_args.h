@@ -61,6 +61,19 @@ struct PcmArgs {
     int16_t *pcm;
 };
 
+// control-frame generator (framegen_kernel.cuh)
+struct FrameGenArgs {
+    const trm_cuda_utterance *desc;       // frame_offset / n_frames of every utterance
+    int n_utt;
+    const trm_cuda_event *events;         // all utterances back to back
+    const long long *ev_offset;           // [n_utt] first event of utterance u
+    const int *ev_count;                  // [n_utt]
+    const trm_cuda_framegen *fg;          // [n_utt] or [1] if shared
+    int shared_fg;
+    double *frames;                       // [frame][16]
+    float *seed_out;                      // [n_utt] drift seed at exit, may be null
+};
+
 struct KernelInfo {
     int tube_smem_bytes;
     int tube_threads;

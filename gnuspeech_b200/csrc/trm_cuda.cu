@@ -28,6 +28,7 @@ int trm_k_src_f64(const trm::SrcArgs *, int, cudaStream_t);
 int trm_k_src_f32(const trm::SrcArgs *, int, cudaStream_t);
 int trm_k_pcm_f64(const trm::PcmArgs *, long long, cudaStream_t);
 int trm_k_pcm_f32(const trm::PcmArgs *, long long, cudaStream_t);
+int trm_k_framegen(const trm::FrameGenArgs *, cudaStream_t);
 }
 
 // FMA-chain kernels used to MEASURE the FP32 / FP64 CUDA-core peak of the device the bench runs on
@@ -198,6 +199,7 @@ struct trm_cuda_ctx {
     double *d_wavetables = nullptr;
     int wt_capacity = 0;
     std::vector<double> wt_host;      // what d_wavetables holds
+    Arena gen;                        // frame generator: events, descriptors, generated frames
     void *d_tab_f64 = nullptr, *d_tab_f32 = nullptr;
     uint64_t noise_k0 = 0;
     trm::KernelInfo info64{}, info32{};
@@ -357,12 +359,12 @@ int upload_frames(const ChunkPlan &p, const DeviceChunk &dc, const trm_cuda_utte
 {
     if (p.frame_rows == 0) return 0;
     if (p.frames_dense) {
-        CK(cudaMemcpyAsync(dc.frames, frames_host + (size_t)p.frames_lo * 16, p.frame_rows * 128, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(dc.frames, frames_host + (size_t)p.frames_lo * 16, p.frame_rows * 128, cudaMemcpyDefault, s));
     } else {
         for (size_t i = 0; i < p.desc.size(); ++i) {
             const auto &g = desc_global[p.u0 + i];
             CK(cudaMemcpyAsync(dc.frames + (size_t)p.desc[i].frame_offset * 16, frames_host + (size_t)g.frame_offset * 16,
-                               (size_t)g.n_frames * 128, cudaMemcpyHostToDevice, s));
+                               (size_t)g.n_frames * 128, cudaMemcpyDefault, s));
         }
     }
     return 0;
@@ -603,6 +605,7 @@ void trm_cuda_ctx_destroy(trm_cuda_ctx *c)
         if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
     }
     for (auto &a : c->arenas) a.release();
+    c->gen.release();
     for (auto &h : c->stages) h.release();
     if (c->d_wavetables) cudaFree(c->d_wavetables);
     if (c->d_tab_f64) cudaFree(c->d_tab_f64);
@@ -732,6 +735,51 @@ int trm_cuda_synthesize_host(trm_cuda_ctx *ctx, int precision, int n, const trm_
         cudaEventDestroy(t_origin);
     }
     if (launches) *launches = n_launch;
+    return 0;
+}
+
+int trm_cuda_generate_frames(trm_cuda_ctx *ctx, int n, const trm_cuda_utterance *desc, const trm_cuda_event *events,
+                             const int64_t *ev_offset, const int32_t *ev_count, const trm_cuda_framegen *fg, int shared_fg,
+                             const double **frames_dev, double *frames_host, float *seed_host)
+{
+    if (frames_dev) *frames_dev = nullptr;
+    if (n <= 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    long long n_events = 0, frames_hi = 0;
+    for (int u = 0; u < n; ++u) {
+        n_events = std::max<long long>(n_events, ev_offset[u] + ev_count[u]);
+        frames_hi = std::max<long long>(frames_hi, desc[u].frame_offset + desc[u].n_frames);
+    }
+    const size_t n_fg = shared_fg ? 1 : (size_t)n;
+    std::vector<long long> off(ev_offset, ev_offset + n);
+    size_t bytes = 0;
+    auto add = [&](size_t x) { bytes = align_up(bytes, 256) + x; };
+    add((size_t)n * sizeof(trm_cuda_utterance)); add((size_t)n_events * sizeof(trm_cuda_event)); add((size_t)n * sizeof(long long));
+    add((size_t)n * sizeof(int)); add(n_fg * sizeof(trm_cuda_framegen)); add((size_t)n * sizeof(float)); add((size_t)frames_hi * 128);
+    int rc;
+    if ((rc = ctx->gen.reserve(bytes + 256)) != 0) return rc;
+    ctx->gen.reset();
+    trm::FrameGenArgs a{};
+    auto *d_desc = (trm_cuda_utterance *)ctx->gen.take((size_t)n * sizeof(trm_cuda_utterance));
+    auto *d_ev = (trm_cuda_event *)ctx->gen.take((size_t)n_events * sizeof(trm_cuda_event));
+    auto *d_off = (long long *)ctx->gen.take((size_t)n * sizeof(long long));
+    auto *d_cnt = (int *)ctx->gen.take((size_t)n * sizeof(int));
+    auto *d_fg = (trm_cuda_framegen *)ctx->gen.take(n_fg * sizeof(trm_cuda_framegen));
+    auto *d_seed = (float *)ctx->gen.take((size_t)n * sizeof(float));
+    auto *d_frames = (double *)ctx->gen.take((size_t)frames_hi * 128);
+    cudaStream_t s = ctx->streams[2];
+    CK(cudaMemcpyAsync(d_desc, desc, (size_t)n * sizeof(trm_cuda_utterance), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_ev, events, (size_t)n_events * sizeof(trm_cuda_event), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_off, off.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_cnt, ev_count, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_fg, fg, n_fg * sizeof(trm_cuda_framegen), cudaMemcpyHostToDevice, s));
+    a.desc = d_desc; a.n_utt = n; a.events = d_ev; a.ev_offset = d_off; a.ev_count = d_cnt; a.fg = d_fg; a.shared_fg = shared_fg;
+    a.frames = d_frames; a.seed_out = d_seed;
+    if ((rc = trm_k_framegen(&a, s)) != 0) return fail("frame generator launch", (cudaError_t)rc);
+    if (frames_host) CK(cudaMemcpyAsync(frames_host, d_frames, (size_t)frames_hi * 128, cudaMemcpyDeviceToHost, s));
+    if (seed_host) CK(cudaMemcpyAsync(seed_host, d_seed, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (frames_dev) *frames_dev = d_frames;
     return 0;
 }
 

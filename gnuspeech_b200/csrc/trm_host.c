@@ -896,6 +896,86 @@ int TRMBatchSynthesize(TRMBatch *b, const TRMParameters *frames, int16_t *pcm_ou
     return batch_run(b, frames, pcm_out, samples_out, NULL, devices, n_devices);
 }
 
+/* ---- control frames from event lists (EventList.m:883-1061) ---- */
+void TRMFrameGenerationSetDefaults(TRMFrameGeneration *fg)
+{
+    memset(fg, 0, sizeof *fg);
+    fg->useMacroIntonation = fg->useMicroIntonation = fg->useSmoothIntonation = fg->useDrift = 1;   /* MMIntonation.m:74-80 */
+    fg->driftDeviation = 1.0;
+    fg->driftCutoff = 4;
+    fg->pitch = -12;                 /* MMSynthesisParameters default */
+    fg->driftSeed = 0.7892347f;      /* MMDriftGenerator.m:6 */
+}
+
+/* The time loop of -generateOutputInTimeRange: without the values (planning: how many frames will there be?):
+ * one frame per 4 ms step while events remain; the event index advances by at most one per step (m:973-1030). */
+int64_t TRMEventListFrameCount(const TRMEvent *ev, int64_t count)
+{
+    if (!ev || count < 2) return 0;
+    int64_t i = 1, emitted = 0;
+    uint64_t now = 0, next = (uint64_t)ev[1].time;
+    while (i < count) {
+        emitted++;
+        now = (uint64_t)((double)now + 4.0);
+        if (now >= next) {
+            i++;
+            if (i == count) break;
+            next = (uint64_t)ev[i].time;
+        }
+    }
+    return emitted;
+}
+
+static int check_event_lists(const TRMBatch *b, const TRMEvent *events, const int64_t *event_offset, const int32_t *n_events)
+{
+    if (!events || !event_offset || !n_events) return set_err(TRM_ERR_PARAM, "null event arguments%s", "");
+    for (int u = 0; u < b->n; u++) {
+        const int64_t want = n_events[u] >= 0 ? TRMEventListFrameCount(events + event_offset[u], n_events[u]) : -1;
+        if (want != b->desc[u].n_frames)
+            return set_err(TRM_ERR_PARAM, "utterance frame count differs from TRMEventListFrameCount of its event list%s", "");
+    }
+    return TRM_OK;
+}
+
+int TRMBatchGenerateFrames(TRMBatch *b, const TRMEvent *events, const int64_t *event_offset, const int32_t *n_events,
+                           const TRMFrameGeneration *fg, int shared_fg, TRMParameters *frames_out, float *drift_seed_out,
+                           int device)
+{
+    int rc = check_event_lists(b, events, event_offset, n_events);
+    if (rc) return rc;
+    if (b->n == 0) return TRM_OK;
+    trm_cuda_ctx *ctx;
+    int lane = 0;
+    if ((rc = acquire_ctx(device, &ctx, &lane)) != TRM_OK) return rc;
+    if (trm_cuda_generate_frames(ctx, b->n, b->desc, (const trm_cuda_event *)events, event_offset, n_events,
+                                 (const trm_cuda_framegen *)fg, shared_fg, NULL, (double *)frames_out, drift_seed_out) != 0)
+        rc = cuda_err();
+    release_ctx(device, lane);
+    return rc;
+}
+
+int TRMBatchSynthesizeEvents(TRMBatch *b, const TRMEvent *events, const int64_t *event_offset, const int32_t *n_events,
+                             const TRMFrameGeneration *fg, int shared_fg, int16_t *pcm_out, void *samples_out, int device)
+{
+    int rc = check_event_lists(b, events, event_offset, n_events);
+    if (rc) return rc;
+    if (b->n == 0) return TRM_OK;
+    trm_cuda_ctx *ctx;
+    int lane = 0;
+    if ((rc = acquire_ctx(device, &ctx, &lane)) != TRM_OK) return rc;
+    const double *frames_dev = NULL;
+    if (trm_cuda_set_wavetables(ctx, b->voices.tables, b->voices.n) != 0 ||
+        trm_cuda_generate_frames(ctx, b->n, b->desc, (const trm_cuda_event *)events, event_offset, n_events,
+                                 (const trm_cuda_framegen *)fg, shared_fg, &frames_dev, NULL, NULL) != 0 ||
+        trm_cuda_synthesize_host(ctx, b->precision, b->n, b->desc, frames_dev, pcm_out, samples_out, b->maxima, NULL,
+                                 &b->launches) != 0)
+        rc = cuda_err();
+    else
+        b->launches += 1;
+    release_ctx(device, lane);
+    return rc;
+}
+
 /* ---- asynchronous calls: one host thread per ticket; two tickets per device overlap (context lanes) ---- */
 struct TRMBatchTicket {
     pthread_t th;

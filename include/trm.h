@@ -243,6 +243,38 @@ TRMBatchTicket *TRMBatchSynthesizeAsync(TRMBatch *batch, const TRMParameters *fr
                                         const int *devices, int n_devices, int *err);
 int TRMBatchWait(TRMBatchTicket *ticket);
 
+/* ---------------------------------------------------------------------------------------------
+ * Control frames from event lists: the step before the tube model in Monet,
+ * -[EventList generateOutputInTimeRange:forSynthesizer:parameterLogger:] (Frameworks/GnuSpeech/MonetModel/
+ * EventList.m:883-1061, full time range) with MMDriftGenerator (MMDriftGenerator.m:41-78), run on the GPU so that a
+ * batch needs only its sparse event lists uploaded.
+ * ------------------------------------------------------------------------------------------- */
+#define TRM_EVENT_VALUES 36
+/* Event (MonetModel/Event.h): time in ms; value[0..15] the 16 TRM parameters, [16..31] the "special" offsets added to
+ * them, [32] macro intonation (semitones), [33..35] smooth-intonation slopes; NaN = no value at this event. */
+typedef struct TRMEvent { int64_t time; double value[TRM_EVENT_VALUES]; } TRMEvent;
+/* What the generator takes from MMIntonation (MMIntonation.m:74-80) and the model (EventList.m:983). */
+typedef struct TRMFrameGeneration {
+    int32_t useMacroIntonation, useMicroIntonation, useSmoothIntonation, useDrift;   /* defaults: all 1 */
+    double  driftDeviation, driftCutoff;     /* defaults 1.0, 4 */
+    double  pitch;                           /* synthesisParameters.pitch, added to every frame's glottal pitch */
+    float   driftSeed;                       /* drift generator state at entry; 0.7892347 for a fresh generator */
+    int32_t reserved;
+} TRMFrameGeneration;
+void    TRMFrameGenerationSetDefaults(TRMFrameGeneration *fg);
+/* Number of 4 ms frames the generator emits for an event list (what n_frames of TRMBatchCreate must be). */
+int64_t TRMEventListFrameCount(const TRMEvent *events, int64_t n_events);
+/* Runs the generator for every utterance of the batch on `device` and returns the frames in frames_out
+ * (TRMBatchLayout.total_frames entries, utterance u at the frame_offset given to TRMBatchCreate).  Utterance u reads
+ * events[event_offset[u] .. +n_events[u]); fg has one entry per utterance, or one for all if shared_fg != 0.
+ * drift_seed_out (n floats, may be NULL) receives each generator's seed at exit. */
+int TRMBatchGenerateFrames(TRMBatch *batch, const TRMEvent *events, const int64_t *event_offset, const int32_t *n_events,
+                           const TRMFrameGeneration *fg, int shared_fg, TRMParameters *frames_out, float *drift_seed_out,
+                           int device);
+/* Event lists in, PCM out: generator and tube model back to back on the device; the frames never exist on the host. */
+int TRMBatchSynthesizeEvents(TRMBatch *batch, const TRMEvent *events, const int64_t *event_offset, const int32_t *n_events,
+                             const TRMFrameGeneration *fg, int shared_fg, int16_t *pcm_out, void *samples_out, int device);
+
 /* Debug / conformance variant on one device: additionally returns the tube-rate signal (what -synthesize
  * hands to dataFill:, TRMTubeModel.m:346) in the batch's arithmetic type; TRMBatchTubeElements() elements,
  * utterance u at TRMBatchTubeOffsets()[u]. */

@@ -78,6 +78,16 @@ typedef struct trm_cuda_tables {
     uint64_t noise_k0;                         /* state before the first draw: k1 * 377^-1 mod 2^44     */
 } trm_cuda_tables;
 
+/* Control-frame generator inputs (EventList.m:883-1061; include/trm.h TRMEvent / TRMFrameGeneration have the same layout) */
+#define TRM_EVENT_VALUES 36
+typedef struct trm_cuda_event { int64_t time; double value[TRM_EVENT_VALUES]; } trm_cuda_event;
+typedef struct trm_cuda_framegen {
+    int32_t useMacroIntonation, useMicroIntonation, useSmoothIntonation, useDrift;
+    double  driftDeviation, driftCutoff, pitch;
+    float   driftSeed;
+    int32_t reserved;
+} trm_cuda_framegen;
+
 typedef struct trm_cuda_ctx trm_cuda_ctx;
 typedef struct trm_cuda_resident trm_cuda_resident;
 
@@ -119,6 +129,17 @@ int  trm_cuda_resident_run(trm_cuda_resident *res, void *stream);               
 int  trm_cuda_resident_fetch(trm_cuda_resident *res, int16_t *pcm_host, void *samples_host,
                              double *max_host, void *tube_host);                 /* blocking D2H          */
 int  trm_cuda_stage_launches(int stage);     /* kernel launches one stage issues */
+/*
+ * Control frames on the device (replaces -[EventList generateOutputInTimeRange:...], EventList.m:883-1061): uploads
+ * the event lists of the n utterances (utterance u: events[ev_offset[u] .. +ev_count[u]); fg: one entry per
+ * utterance, or one for all if shared_fg), runs the generator kernel and leaves the frames -- desc[u].n_frames of
+ * them at frame desc[u].frame_offset -- in a device buffer owned by the context.  *frames_dev receives that buffer
+ * (valid until the next call on this context; usable as the `frames_host` argument of trm_cuda_synthesize_host,
+ * which copies with cudaMemcpyDefault).  frames_host / seed_host, if not NULL, receive copies.  Blocking.
+ */
+int  trm_cuda_generate_frames(trm_cuda_ctx *ctx, int n, const trm_cuda_utterance *desc, const trm_cuda_event *events,
+                              const int64_t *ev_offset, const int32_t *ev_count, const trm_cuda_framegen *fg, int shared_fg,
+                              const double **frames_dev, double *frames_host, float *seed_host);
 /* Measures the device's FMA peak (TFLOP/s, 2 flops per FMA) with a register-resident FMA chain:
  * precision 0 = FP64, 1 = FP32.  The waveguide kernel's roofline denominator. */
 int  trm_cuda_fp_peak(int device, int precision, int reps, double *tflops);

@@ -1047,3 +1047,141 @@ int oracle_synthesize_batch(const oracle_input_parameters *ip, int shared_ip, co
     }
     return n_threads > 0 ? rc : -3;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Control-frame generator (EventList.m:883-1061, MMDriftGenerator.m:41-78).  Operation by operation in the
+ * reference's order and types: currentValues / currentDeltas are double, the output table and the drift generator
+ * are float.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct { float pitchDeviation, pitchOffset, a0, b1, seed, previousSample; } drift_t;
+
+/* MMDriftGenerator.m:41-58 */
+static void drift_configure(drift_t *g, float deviation, float sampleRate, float lowpassCutoff)
+{
+    g->pitchDeviation = deviation * 2.0;
+    g->pitchOffset = deviation;
+    if (lowpassCutoff < 0.0) lowpassCutoff = 0.0;
+    else if (lowpassCutoff > (sampleRate / 2.0)) lowpassCutoff = sampleRate / 2.0;
+    g->a0 = (lowpassCutoff * 2.0) / sampleRate;
+    g->b1 = 1.0 - g->a0;
+    g->previousSample = 0.0;
+}
+
+/* MMDriftGenerator.m:65-78 */
+static float drift_generate(drift_t *g)
+{
+    float temp = g->seed * 377.0f;
+    g->seed = temp - (int32_t)temp;
+    temp = (g->seed * g->pitchDeviation) - g->pitchOffset;
+    g->previousSample = (g->a0 * temp) + (g->b1 * g->previousSample);
+    return g->previousSample;
+}
+
+static int64_t generate_frames(const oracle_event *ev, int64_t count, const oracle_framegen *fg, oracle_frame *out,
+                               int64_t max_frames, float *seed_out)
+{
+    if (seed_out && fg) *seed_out = fg->driftSeed;
+    if (count == 0) return 0;                                       /* m:890-891 */
+    drift_t drift = {0, 0, 0, 0, fg ? fg->driftSeed : 0.7892347f, 0};
+    const double millisecondsPerInterval = 1000.0 / 250.0;
+    if (fg && fg->useDrift) drift_configure(&drift, (float)fg->driftDeviation, (float)(1000 / 4), (float)fg->driftCutoff);   /* m:903-907 */
+
+    double currentValues[36], currentDeltas[36], temp;
+    int64_t emitted = 0;
+    if (count < 2) return 0;     /* the reference indexes _mutableEvents[1] unconditionally: a one-event list is undefined */
+    for (int i = 0; i < 16; i++) {                                  /* m:919-926 */
+        int64_t j = 1;
+        while (isnan(temp = ev[j].value[i])) j++;
+        currentValues[i] = ev[0].value[i];
+        currentDeltas[i] = ((temp - currentValues[i]) / (double)(ev[j].time)) * millisecondsPerInterval;
+    }
+    for (int i = 16; i < 36; i++) currentValues[i] = currentDeltas[i] = 0.0;   /* m:929-930 */
+    if (fg && fg->useSmoothIntonation) {                            /* m:932-943 */
+        int64_t j = 0;
+        while (isnan(temp = ev[j].value[32])) {
+            j++;
+            if (j >= count) break;
+        }
+        currentValues[32] = j < count ? ev[j].value[32] : NAN;      /* the reference reads out of bounds here */
+        currentDeltas[32] = 0.0;
+    } else if (fg) {                                                /* m:944-961 */
+        int64_t j = 1;
+        while (isnan(temp = ev[j].value[32])) {
+            j++;
+            if (j >= count) break;
+        }
+        currentValues[32] = ev[0].value[32];
+        if (j < count) currentDeltas[32] = ((temp - currentValues[32]) / (double)(ev[j].time)) * millisecondsPerInterval;
+        else currentDeltas[32] = 0;
+        currentValues[32] = -20.0;
+    }
+
+    int64_t i = 1;
+    uint64_t currentTime_ms = 0;
+    uint64_t nextTime = (uint64_t)ev[1].time;
+    float table[16];
+    while (i < count) {                                             /* m:973 */
+        if (fg) {
+            for (int j = 0; j < 16; j++) table[j] = (float)currentValues[j] + (float)currentValues[j + 16];
+            if (!fg->useMicroIntonation) table[0] = 0.0;
+            if (fg->useDrift) table[0] += drift_generate(&drift);
+            if (fg->useMacroIntonation) table[0] += currentValues[32];
+            table[0] += fg->pitch;
+            if (out && emitted < max_frames)
+                for (int j = 0; j < 16; j++) out[emitted].v[j] = table[j];
+        }
+        emitted++;
+        if (fg) {
+            for (int j = 0; j < 32; j++)
+                if (currentDeltas[j]) currentValues[j] += currentDeltas[j];
+            if (fg->useSmoothIntonation) {
+                currentDeltas[34] += currentDeltas[35];
+                currentDeltas[33] += currentDeltas[34];
+                currentValues[32] += currentDeltas[33];
+            } else {
+                if (currentDeltas[32]) currentValues[32] += currentDeltas[32];
+            }
+        }
+        currentTime_ms += millisecondsPerInterval;
+
+        if (currentTime_ms >= nextTime) {                           /* m:1025 */
+            i++;
+            if (i == count) break;
+            nextTime = (uint64_t)ev[i].time;
+            if (!fg) continue;
+            for (int j = 0; j < 33; j++) {
+                if (!isnan(ev[i - 1].value[j])) {
+                    int64_t k = i;
+                    while (isnan(temp = ev[k].value[j])) {
+                        if (k >= count - 1) {
+                            currentDeltas[j] = 0.0;
+                            break;
+                        }
+                        k++;
+                    }
+                    if (!isnan(temp))
+                        currentDeltas[j] = (temp - currentValues[j]) / (double)((uint64_t)ev[k].time - currentTime_ms) * millisecondsPerInterval;
+                }
+            }
+            if (fg->useSmoothIntonation) {
+                if (!isnan(ev[i - 1].value[33])) {
+                    currentValues[32] = ev[i - 1].value[32];
+                    currentDeltas[32] = 0.0;
+                    currentDeltas[33] = ev[i - 1].value[33];
+                    currentDeltas[34] = ev[i - 1].value[34];
+                    currentDeltas[35] = ev[i - 1].value[35];
+                }
+            }
+        }
+    }
+    if (seed_out) *seed_out = drift.seed;
+    return emitted;
+}
+
+int64_t oracle_frame_count(const oracle_event *events, int64_t n_events) { return generate_frames(events, n_events, NULL, NULL, 0, NULL); }
+
+int64_t oracle_generate_frames(const oracle_event *events, int64_t n_events, const oracle_framegen *fg, oracle_frame *out,
+                               int64_t max_frames, float *seed_out)
+{
+    return generate_frames(events, n_events, fg, out, max_frames, seed_out);
+}

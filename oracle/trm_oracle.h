@@ -118,6 +118,25 @@ int oracle_synthesize_batch(const oracle_input_parameters *ip, int shared_ip,
                             int n_utterances, int flags, int n_threads,
                             int32_t *numberSamples, double *maximumSampleValue, double *checksum);
 
+/* ------------------------------------------------------------------------------------------------
+ * Control-frame generator: -[EventList generateOutputInTimeRange:forSynthesizer:parameterLogger:]
+ * (Frameworks/GnuSpeech/MonetModel/EventList.m:883-1061, full time range) + MMDriftGenerator
+ * (MMDriftGenerator.m:41-78).  SURVEY.md 8(f) rank 1.  Reference tests / golden vectors for it: none -> parity unpinned.
+ * ---------------------------------------------------------------------------------------------- */
+#define ORACLE_EVENT_VALUES 36
+typedef struct { int64_t time; double value[ORACLE_EVENT_VALUES]; } oracle_event;   /* Event.m: time in ms, NaN = unset */
+typedef struct {
+    int32_t useMacroIntonation, useMicroIntonation, useSmoothIntonation, useDrift;   /* MMIntonation.m:74-80 */
+    double  driftDeviation, driftCutoff;
+    double  pitch;                 /* model.synthesisParameters.pitch, added to every frame's glottal pitch (m:983) */
+    float   driftSeed;             /* MMDriftGenerator seed at entry (0.7892347 for a fresh generator) */
+} oracle_framegen;
+/* number of frames the loop emits */
+int64_t oracle_frame_count(const oracle_event *events, int64_t n_events);
+/* writes at most max_frames frames, returns the number the loop emits; *seed_out = drift seed at exit (may be NULL) */
+int64_t oracle_generate_frames(const oracle_event *events, int64_t n_events, const oracle_framegen *fg,
+                               oracle_frame *out, int64_t max_frames, float *seed_out);
+
 #ifdef __cplusplus
 }
 #endif

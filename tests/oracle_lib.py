@@ -69,6 +69,77 @@ def lib():
     return _lib
 
 
+EVENT_DTYPE = np.dtype([("time", np.int64), ("value", np.float64, (36,))])   # oracle_event
+
+
+class OracleFrameGen(C.Structure):
+    _fields_ = [("useMacroIntonation", C.c_int32), ("useMicroIntonation", C.c_int32), ("useSmoothIntonation", C.c_int32),
+                ("useDrift", C.c_int32), ("driftDeviation", C.c_double), ("driftCutoff", C.c_double), ("pitch", C.c_double),
+                ("driftSeed", C.c_float)]
+
+
+def frame_count(events):
+    events = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
+    L = lib()
+    L.oracle_frame_count.restype = C.c_int64
+    L.oracle_frame_count.argtypes = [C.c_void_p, C.c_int64]
+    return int(L.oracle_frame_count(events.ctypes.data_as(C.c_void_p), len(events)))
+
+
+def generate_frames(events, fg):
+    """Control frames of one event list by the oracle's restatement of EventList.m:883-1061.  fg: any object with the
+    TRMFrameGeneration fields.  Returns (frames (n, 16), drift seed at exit)."""
+    events = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
+    L = lib()
+    L.oracle_generate_frames.restype = C.c_int64
+    L.oracle_generate_frames.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    o = OracleFrameGen(*[getattr(fg, n) for n, _ in OracleFrameGen._fields_])
+    n = frame_count(events)
+    out = np.zeros((max(n, 1), 16), np.float64)
+    seed = C.c_float(0)
+    got = L.oracle_generate_frames(events.ctypes.data_as(C.c_void_p), len(events), C.byref(o), out.ctypes.data_as(C.c_void_p), n,
+                                   C.byref(seed))
+    assert got == n
+    return out[:n], seed.value
+
+
+def synthetic_event_list(seed, seconds, smooth=True):
+    """An event list shaped like Monet's (EventList.m applyRule / applyIntonation): posture events every 40-160 ms
+    carry all 16 parameters, transition events in between carry a few, 'special' offsets (tracks 16..31) and macro
+    intonation (32; with slopes 33..35 when smooth intonation is used) appear at some events; values are floats."""
+    rng = np.random.default_rng(seed)
+    lo = np.array([-22, 0, 0, 0, 0, 864, 500, 0.8, 0.05, 0.05, 0.05, 0.05, 0.05, 0.05, 0.05, 0.1])
+    hi = np.array([-2, 60, 10, 24, 7, 5500, 4500, 0.8, 2.61, 2.61, 2.61, 2.61, 2.61, 2.61, 2.61, 1.5])
+    times, vals = [0], []
+    t = 0
+    while t < seconds * 1000:
+        t += int(rng.integers(3, 40)) * 4 + int(rng.integers(0, 4))      # not always on the 4 ms grid
+        times.append(t)
+    n = len(times)
+    v = np.full((n, 36), np.nan)
+    posture = np.zeros(n, bool)
+    posture[0] = posture[-1] = True
+    posture[rng.random(n) < 0.45] = True
+    for i in range(n):
+        if posture[i]:
+            v[i, :16] = lo + (hi - lo) * rng.random(16)
+        else:
+            pick = rng.random(16) < 0.3
+            v[i, :16][pick] = (lo + (hi - lo) * rng.random(16))[pick]
+        if rng.random() < 0.2:
+            k = 16 + int(rng.integers(0, 16))
+            v[i, k] = (hi - lo)[k - 16] * 0.05 * (rng.random() - 0.5)
+        if rng.random() < 0.3 or i == 0:
+            v[i, 32] = 6.0 * (rng.random() - 0.5)
+            if smooth:
+                v[i, 33:36] = (rng.random(3) - 0.5) * [0.2, 0.01, 0.0005]
+    v = v.astype(np.float32).astype(np.float64)                          # Monet's values are floats
+    ev = np.zeros(n, EVENT_DTYPE)
+    ev["time"] = times
+    ev["value"] = v
+    return ev
+
+
 def as_oracle_ip(ip):
     """Reinterprets any struct with the TRMInputParameters layout (e.g. gnuspeech_b200.TRMInputParameters)."""
     o = OracleInputParameters()

@@ -200,3 +200,57 @@ def test_batch_threads_match_single():
     for u in range(5):
         r = O.synthesize(ip, frames[u * 21:(u + 1) * 21])
         assert ns[u] == r.numberSamples and mx[u] == r.maximumSampleValue
+
+
+def test_frame_generator_restatement_properties():
+    """Control-frame generator (EventList.m:883-1061 + MMDriftGenerator.m).  The reference has no
+    tests or vectors for it (parity unpinned); the restatement is checked through what the algorithm must satisfy:
+    frame count of the time loop, exact reproduction of constant tracks, linear interpolation between events with the
+    float rounding of the output table, NaN events skipped, intonation switches, and the drift generator's float MCG
+    (same x377 generator as the tube's noise source, in single precision)."""
+    import gnuspeech_b200 as g
+    fg = g.TRMFrameGeneration(useDrift=0, useMacroIntonation=0, useSmoothIntonation=0, pitch=0.0)
+    # two events 400 ms apart, every parameter ramps 1 -> 2: 100 frames, value[k] = float(1 + k/100) up to accumulated rounding
+    v = np.full((2, 36), np.nan)
+    v[0, :16], v[1, :16] = 1.0, 2.0
+    ev = g.make_events([0, 400], v)
+    assert O.frame_count(ev) == 100 == g.event_list_frame_count(ev)
+    fr, _ = O.generate_frames(ev, fg)
+    assert fr.shape == (100, 16)
+    want = np.float32(1.0 + np.arange(100) * 0.01)
+    assert np.abs(fr - want[:, None]).max() < 2e-6 and fr[0, 0] == 1.0
+    assert (fr == fr.astype(np.float32)).all()                            # the table is float
+    # an event in between that carries no value for the parameter does not bend its line; one that does, does
+    v = np.full((3, 36), np.nan)
+    v[0, :16], v[2, :16] = 1.0, 2.0
+    v[1, 3] = 5.0
+    ev = g.make_events([0, 200, 400], v)
+    fr, _ = O.generate_frames(ev, fg)
+    assert np.abs(fr[:, 0] - want).max() < 2e-6                          # track 0 unaffected
+    assert abs(fr[50, 3] - 5.0) < 1e-5 and abs(fr[25, 3] - 3.0) < 1e-5 and abs(fr[75, 3] - 3.5) < 1e-5
+    # constant tracks are reproduced exactly; base pitch and macro intonation add to the glottal pitch only
+    v = np.full((4, 36), np.nan)
+    v[:, :16] = np.float32(np.linspace(0.3, 1.8, 16))
+    v[0, 32] = v[3, 32] = 2.5
+    ev = g.make_events([0, 100, 230, 1000], v)
+    fg2 = g.TRMFrameGeneration(useDrift=0, useSmoothIntonation=0, pitch=-12.0)
+    fr, _ = O.generate_frames(ev, fg2)
+    assert len(fr) == 250 and (fr[:, 1:] == v[0, 1:16]).all()
+    assert np.allclose(fr[:, 0], np.float32(v[0, 0]) + (-20.0) - 12.0)   # non-smooth mode starts the macro track at -20 (m:961)
+    # micro intonation off zeroes the parameter-track contribution to the pitch
+    fg3 = g.TRMFrameGeneration(useDrift=0, useMacroIntonation=0, useMicroIntonation=0, useSmoothIntonation=0, pitch=-7.0)
+    fr, _ = O.generate_frames(ev, fg3)
+    assert (fr[:, 0] == -7.0).all()
+    # drift: bounded by the deviation, low-passed, deterministic in the seed, seed advances once per frame
+    fg4 = g.TRMFrameGeneration(useMacroIntonation=0, useMicroIntonation=0, useSmoothIntonation=0, pitch=0.0, driftDeviation=1.0, driftCutoff=4)
+    fr, seed = O.generate_frames(ev, fg4)
+    assert np.abs(fr[:, 0]).max() <= 1.0 and np.abs(np.diff(fr[:, 0])).max() < 0.1 and fr[:, 0].std() > 0.01
+    s = np.float32(0.7892347)
+    for _ in range(250):
+        t = np.float32(s * np.float32(377.0))
+        s = np.float32(t - np.float32(np.int32(t)))
+    assert seed == s
+    # frame count of the planner == the oracle's loop on Monet-shaped lists, including off-grid event times
+    for k in range(20):
+        ev = O.synthetic_event_list(100 + k, 1.5)
+        assert O.frame_count(ev) == g.event_list_frame_count(ev) > 0
