@@ -907,21 +907,22 @@ void TRMFrameGenerationSetDefaults(TRMFrameGeneration *fg)
     fg->driftSeed = 0.7892347f;      /* MMDriftGenerator.m:6 */
 }
 
-/* The time loop of -generateOutputInTimeRange: without the values (planning: how many frames will there be?):
- * one frame per 4 ms step while events remain; the event index advances by at most one per step (m:973-1030). */
+/* The time loop of -generateOutputInTimeRange: without the values (planning: how many frames will there be?).
+ * The reference emits one frame per 4 ms step while events remain, and after each step moves on to the next event
+ * once the clock has reached the current one's time -- at most one event per step (m:973-1030).  So event i is
+ * "current" for max(1, ceil((time_i - now) / 4)) steps, where now is the clock when it became current: O(events)
+ * instead of O(frames).  (tests/test_oracle.py checks this against the oracle's literal loop.) */
 int64_t TRMEventListFrameCount(const TRMEvent *ev, int64_t count)
 {
     if (!ev || count < 2) return 0;
-    int64_t i = 1, emitted = 0;
-    uint64_t now = 0, next = (uint64_t)ev[1].time;
-    while (i < count) {
-        emitted++;
-        now = (uint64_t)((double)now + 4.0);
-        if (now >= next) {
-            i++;
-            if (i == count) break;
-            next = (uint64_t)ev[i].time;
-        }
+    int64_t emitted = 0;
+    uint64_t now = 0;
+    for (int64_t i = 1; i < count; i++) {
+        const uint64_t next = (uint64_t)ev[i].time;
+        uint64_t steps = next > now ? (next - now + 3) / 4 : 1;
+        if (steps < 1) steps = 1;
+        emitted += (int64_t)steps;
+        now += 4 * steps;
     }
     return emitted;
 }

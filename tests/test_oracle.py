@@ -254,3 +254,10 @@ def test_frame_generator_restatement_properties():
     for k in range(20):
         ev = O.synthetic_event_list(100 + k, 1.5)
         assert O.frame_count(ev) == g.event_list_frame_count(ev) > 0
+    # ... and on adversarial ones: repeated times, gaps shorter than a frame (the loop advances one event per step)
+    rng = np.random.default_rng(0)
+    for k in range(500):
+        n = int(rng.integers(2, 12))
+        t = np.concatenate(([0], np.cumsum(rng.integers(0, 30, n - 1))))
+        ev = g.make_events(t, np.zeros((n, 36)))
+        assert O.frame_count(ev) == g.event_list_frame_count(ev), t
