@@ -371,8 +371,10 @@ int upload_frames(const ChunkPlan &p, const DeviceChunk &dc, const trm_cuda_utte
 }
 
 // Which waveguide mapping runs a chunk of n utterances: 0 = lane-per-section (tube_kernel.cuh), otherwise the
-// number of CTAs of the batch-throughput mapping (tube_wide.cuh), one per SM and wave.  Small batches finish sooner
-// with their sections spread over lanes; TRM_TUBE_MAPPING=sections|utterances overrides the choice.
+// number of CTAs of the lane-per-utterance mapping (tube_wide.cuh), one per SM and wave.  The latter is the default at
+// every batch size: even a lone utterance finishes sooner when its feed-forward and recurrence parts run as two
+// concurrent warps than when they alternate inside one (measured, profiles/README.md).  TRM_TUBE_MAPPING=sections
+// selects the lane-per-section kernel (the two agree bit for bit in FP64).
 int wide_groups(const trm_cuda_ctx *ctx, const trm::KernelInfo &ki, int n)
 {
     const char *env = getenv("TRM_TUBE_MAPPING");
@@ -524,7 +526,7 @@ int trm_cuda_ctx_create(int device, const trm_cuda_tables *t, trm_cuda_ctx **out
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     c->noise_k0 = t->noise_k0;
-    c->wide_min_utt = 4 * prop.multiProcessorCount;
+    c->wide_min_utt = 1;     // measured: the batch-throughput mapping is the faster one at every batch size (profiles/README.md)
     int rc;
     if ((rc = trm_k_upload_f64(t->fir_coef, t->fir_taps, (const unsigned long long *)t->noise_pow)) != 0 ||
         (rc = trm_k_upload_f32(t->fir_coef, t->fir_taps, (const unsigned long long *)t->noise_pow)) != 0) {

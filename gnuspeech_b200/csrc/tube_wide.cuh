@@ -417,7 +417,9 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
     const bool has_utt = ucol < g_count;
     const int u = args.order ? args.order[g_start + (has_utt ? ucol : 0)] : g_start + (has_utt ? ucol : 0);
     const trm_cuda_utterance *__restrict__ D = args.desc + u;
-    const int64_t n_tube = has_utt ? D->n_tube : 0;
+    // a half without an utterance (odd group size) recomputes the group's first utterance into a ring column nobody
+    // reads: all-zero parameters would send every division and transcendental of that half down its slow path
+    const int64_t n_tube = D->n_tube;
     const int n_frames = D->n_frames;
     const int cp = D->controlPeriod;
     const double *__restrict__ F = args.frames + D->frame_offset * 16;
