@@ -25,7 +25,18 @@ constexpr int SRC_NT_MAX = 256;      // outputs per work item (bounded by SRC_RO
 constexpr int PCM_THREADS = 256;
 constexpr int PCM_PER_THREAD = 8;
 
+// Carried state of one utterance for streaming synthesis (tube_wide.cuh): 4 eight-byte header words
+// {oscillator position (double), the same in 2^-55 table entries (fast mode), noise generator state, "no sample
+// produced yet" flag} followed by STATE_R values of the arithmetic type: oscillator history even / odd (24 + 24),
+// band-pass input x[n-1], x[n-2], then the 41 recurrence values (waves, reflection / radiation memories, band-pass
+// and throat outputs).
+constexpr int STATE_HDR = 4;
+constexpr int STATE_R = 96;
+constexpr int STATE_HE = 0, STATE_HO = 24, STATE_XM = 48, STATE_SER = 50;
+inline size_t tube_state_bytes(size_t esz) { return STATE_HDR * 8 + STATE_R * esz; }
+
 struct TubeArgs {
+    void *state;                 // streaming: [n_utt] carried states (loaded at start, stored at the end), else null
     const trm_cuda_utterance *desc;
     const int *order;            // slot -> utterance (longest first), may be null
     int n_utt;
@@ -48,6 +59,7 @@ struct SrcArgs {
     const int *tile_utt;             // [n_tiles][32] utterance index or -1
     const int *tile_nt;              // [n_tiles] outputs per work item of that tile (window fits SRC_ROWS)
     const long long *tile_max_out;   // [n_tiles] longest utterance of the tile
+    const long long *tile_first_out; // [n_tiles] first output of the tile's first work item (0 unless streaming)
     const long long *item_base;      // [n_tiles+1] prefix sum of work items
     int n_tiles;
     long long total_items;

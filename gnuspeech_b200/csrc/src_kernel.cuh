@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(SRC_THREADS, sizeof(R) == 4 ? 3 : 2) src_kerne
     R *xU = reinterpret_cast<R *>(smem_raw);                             // [32][SRC_XLD] input windows, utterance-major
     R *Cf = xU + 32 * SRC_XLD;                                           // [SRC_NT_MAX][SRC_CLD] coefficients
     R *yT = Cf + SRC_NT_MAX * SRC_CLD;                                   // [warps][32][YLD]
-    __shared__ long long s_tube_off[32], s_out_off[32], s_n_in[32], s_n_out[32];
+    __shared__ long long s_tube_off[32], s_out_off[32], s_n_in[32], s_n_out[32], s_out_start[32], s_in_start[32];
     __shared__ int s_tile;
     __shared__ unsigned long long s_bar;
 
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(SRC_THREADS, sizeof(R) == 4 ? 3 : 2) src_kerne
     int pad = 0, reach = 0, nt = 0;
     bool up = true;
     double ratio = 1.0;
-    long long tile_max = 0;
+    long long tile_max = 0, tile_out0 = 0;
     R local_max = (R)0;
     auto flush_max = [&]() {
         // per-utterance maximum: integer atomicMax on the bit pattern (order independent for non-negative doubles)
@@ -128,6 +128,8 @@ __global__ void __launch_bounds__(SRC_THREADS, sizeof(R) == 4 ? 3 : 2) src_kerne
                 s_out_off[lane] = D->out_offset;
                 s_n_in[lane] = u >= 0 ? D->n_tube : -1;
                 s_n_out[lane] = u >= 0 ? D->n_out : 0;
+                s_out_start[lane] = u >= 0 ? D->out_start : 0;      // streaming: earlier outputs exist already,
+                s_in_start[lane] = u >= 0 ? D->in_start : 0;        // earlier inputs are no longer in memory
             }
             // signature of the tile (row 0 is always a real utterance)
             const trm_cuda_utterance *__restrict__ D0 = args.desc + args.tile_utt[tile * 32];
@@ -140,9 +142,10 @@ __global__ void __launch_bounds__(SRC_THREADS, sizeof(R) == 4 ? 3 : 2) src_kerne
             tile_first = args.item_base[tile];
             tile_end = args.item_base[tile + 1];
             tile_max = args.tile_max_out[tile];
+            tile_out0 = args.tile_first_out[tile];
             __syncthreads();
         }
-        const long long n_s = (item - tile_first) * nt;
+        const long long n_s = tile_out0 + (item - tile_first) * nt;
         const int n_item = (int)((n_s + nt < tile_max) ? nt : tile_max - n_s);         // outputs of this item
         const unsigned long long T0 = (unsigned long long)n_s * tri;
         const long long P0 = (long long)(T0 >> 16);
@@ -157,7 +160,9 @@ __global__ void __launch_bounds__(SRC_THREADS, sizeof(R) == 4 ? 3 : 2) src_kerne
             // bulk copy of [lo, hi) (clipped to the utterance's 16-byte-padded extent)
             const long long n_in = s_n_in[lane];
             const long long n_al = (n_in + A - 1) / A * A;
-            const long long lo = qb > 0 ? qb : 0, hi = (qb + span < n_al) ? qb + span : n_al;
+            long long lo = qb > 0 ? qb : 0;
+            if (lo < s_in_start[lane]) lo = s_in_start[lane];            // (a multiple of A; only discarded outputs look below it)
+            const long long hi = (qb + span < n_al) ? qb + span : n_al;
             const unsigned bytes = (hi > lo) ? (unsigned)(hi - lo) * (unsigned)sizeof(R) : 0u;
             unsigned total = bytes;
 #pragma unroll
@@ -204,6 +209,7 @@ __global__ void __launch_bounds__(SRC_THREADS, sizeof(R) == 4 ? 3 : 2) src_kerne
         }
 
         const int my_out = (int)((s_n_out[lane] - n_s < (long long)n_item) ? (s_n_out[lane] - n_s > 0 ? s_n_out[lane] - n_s : 0) : n_item);
+        const int my_lo = (int)((s_out_start[lane] - n_s > 0) ? ((s_out_start[lane] - n_s < (long long)n_item) ? s_out_start[lane] - n_s : n_item) : 0);
         R *yw = yT + warp * (32 * YLD);
         const R *xl = xU + lane * SRC_XLD + off;                         // xl[i] = window element i of this lane's utterance
         if (up) {
@@ -232,16 +238,18 @@ __global__ void __launch_bounds__(SRC_THREADS, sizeof(R) == 4 ? 3 : 2) src_kerne
                 for (int i = 0; i < PIECES; ++i) {
                     const int r = (32 / PIECES) * i + lane / PIECES, part = lane % PIECES;
                     const long long left = s_n_out[r] - (n_s + c0) - A * part;        // valid samples from this piece on
-                    if (left > 0 && A * part < j) {
+                    const long long skip = s_out_start[r] - (n_s + c0) - A * part;   // leading samples that exist already
+                    if (left > 0 && A * part < j && skip < A) {
                         R *dst = reinterpret_cast<R *>(args.out) + s_out_off[r] + n_s + c0 + A * part;
                         const R *src = yw + r * YLD + A * part;
-                        if (left >= A && A * part + A <= j) {
+                        if (left >= A && A * part + A <= j && skip <= 0) {
                             Vec16<R> v;
 #pragma unroll
                             for (int e = 0; e < A; ++e) v.e[e] = src[e];
                             v.store(dst);
                         } else {
-                            for (int e = 0; e < A && e < left && A * part + e < j; ++e) dst[e] = src[e];
+                            for (int e = 0; e < A && e < left && A * part + e < j; ++e)
+                                if (e >= skip) dst[e] = src[e];
                         }
                     }
                 }
@@ -269,7 +277,7 @@ __global__ void __launch_bounds__(SRC_THREADS, sizeof(R) == 4 ? 3 : 2) src_kerne
                             }
                         }
                         yw[lane * YLD + j] = acc;
-                        const R av = (nr < my_out) ? r_abs<R>(acc) : (R)0;
+                        const R av = (nr < my_out && nr >= my_lo) ? r_abs<R>(acc) : (R)0;
                         local_max = (av > local_max) ? av : local_max;   // NaN never wins, like the reference
                         ++nr;
                         if (++j == SRC_CHUNK) write_back();
@@ -309,14 +317,14 @@ __global__ void __launch_bounds__(SRC_THREADS, sizeof(R) == 4 ? 3 : 2) src_kerne
                         ph += phaseIncrement;
                     }
                     yw[lane * YLD + j] = acc;
-                    const R av = (c0 + j < my_out) ? r_abs<R>(acc) : (R)0;
+                    const R av = (c0 + j < my_out && c0 + j >= my_lo) ? r_abs<R>(acc) : (R)0;
                     local_max = (av > local_max) ? av : local_max;
                 }
                 __syncwarp();
 #pragma unroll
                 for (int i = 0; i < SRC_CHUNK; ++i) {
                     const int r = (32 / SRC_CHUNK) * i + lane / SRC_CHUNK, cc = lane % SRC_CHUNK;
-                    if (n_s + c0 + cc < s_n_out[r])
+                    if (n_s + c0 + cc < s_n_out[r] && n_s + c0 + cc >= s_out_start[r])
                         (reinterpret_cast<R *>(args.out) + s_out_off[r])[n_s + c0 + cc] = yw[r * YLD + cc];
                 }
                 __syncwarp();

@@ -128,7 +128,7 @@ struct DeviceChunk {
     trm_cuda_utterance *desc = nullptr;
     int *order = nullptr;
     int *tile_utt = nullptr, *tile_nt = nullptr;
-    long long *tile_max_out = nullptr, *item_base = nullptr;
+    long long *tile_max_out = nullptr, *tile_first_out = nullptr, *item_base = nullptr;
     unsigned long long *maxbits = nullptr;
     double *frames = nullptr;
     void *tube = nullptr, *out = nullptr;
@@ -145,7 +145,7 @@ struct ChunkPlan {
     std::vector<int> order;
     // resampler work decomposition (src_kernel.cuh): tiles of <= 32 utterances with one converter signature
     std::vector<int> tile_utt, tile_nt;
-    std::vector<long long> tile_max_out, item_base;
+    std::vector<long long> tile_max_out, tile_first_out, item_base;
     bool frames_dense = true;
     long long frames_lo = 0;                // host frame index of the span start (dense case)
     size_t frame_rows = 0;
@@ -162,6 +162,7 @@ struct ChunkPlan {
         add(tile_utt.size() * sizeof(int));
         add(tile_nt.size() * sizeof(int));
         add(tile_max_out.size() * sizeof(long long));
+        add(tile_first_out.size() * sizeof(long long));
         add(item_base.size() * sizeof(long long));
         add(n * sizeof(unsigned long long));
         add(frame_rows * 128);
@@ -175,7 +176,8 @@ struct ChunkPlan {
         size_t n = desc.size();
         return align_up(n * sizeof(trm_cuda_utterance), 256) + align_up(n * sizeof(int), 256) +
                align_up(tile_utt.size() * sizeof(int), 256) + align_up(tile_nt.size() * sizeof(int), 256) +
-               align_up(tile_max_out.size() * sizeof(long long), 256) + align_up(item_base.size() * sizeof(long long), 256) +
+               align_up(tile_max_out.size() * sizeof(long long), 256) + align_up(tile_first_out.size() * sizeof(long long), 256) +
+               align_up(item_base.size() * sizeof(long long), 256) +
                align_up(n * sizeof(unsigned long long), 256);
     }
 };
@@ -275,7 +277,7 @@ void plan_chunk(const trm_cuda_utterance *desc, int u0, int u1, ChunkPlan &p)
             if (ka != kb) return ka < kb;
             return p.desc[a].n_out > p.desc[b].n_out;
         });
-        p.tile_utt.clear(); p.tile_nt.clear(); p.tile_max_out.clear(); p.item_base.assign(1, 0);
+        p.tile_utt.clear(); p.tile_nt.clear(); p.tile_max_out.clear(); p.tile_first_out.clear(); p.item_base.assign(1, 0);
         for (int at = 0; at < n;) {
             int end = at;
             while (end < n && end - at < 32 && key(idx[end]) == key(idx[at])) ++end;
@@ -288,10 +290,14 @@ void plan_chunk(const trm_cuda_utterance *desc, int u0, int u1, ChunkPlan &p)
                 long long nt = (long long)((double)(trm::SRC_ROWS - 3 - 2 * reach) * 65536.0 / (double)d0.tri);
                 nt = std::min<long long>(nt, trm::SRC_NT_MAX);
                 nt = std::max<long long>(unit, nt / unit * unit);
+                long long first = d0.n_out;                  // streaming: the tile starts at its earliest missing output
+                for (int r = at; r < end; ++r) first = std::min<long long>(first, p.desc[idx[r]].out_start);
+                first = first / nt * nt;
                 for (int r = 0; r < 32; ++r) p.tile_utt.push_back(at + r < end ? idx[at + r] : -1);
                 p.tile_nt.push_back((int)nt);
                 p.tile_max_out.push_back(d0.n_out);
-                p.item_base.push_back(p.item_base.back() + (d0.n_out + nt - 1) / nt);
+                p.tile_first_out.push_back(first);
+                p.item_base.push_back(p.item_base.back() + (d0.n_out - first + nt - 1) / nt);
             }
             at = end;
         }
@@ -315,6 +321,7 @@ void carve(Arena &a, const ChunkPlan &p, size_t esz, bool want_pcm, DeviceChunk 
     dc.tile_utt = (int *)a.take(p.tile_utt.size() * sizeof(int));
     dc.tile_nt = (int *)a.take(p.tile_nt.size() * sizeof(int));
     dc.tile_max_out = (long long *)a.take(p.tile_max_out.size() * sizeof(long long));
+    dc.tile_first_out = (long long *)a.take(p.tile_first_out.size() * sizeof(long long));
     dc.item_base = (long long *)a.take(p.item_base.size() * sizeof(long long));
     dc.maxbits = (unsigned long long *)a.take(n * sizeof(unsigned long long));
     dc.frames = (double *)a.take(p.frame_rows * 128);
@@ -350,6 +357,7 @@ int upload_plan(const ChunkPlan &p, const DeviceChunk &dc, unsigned char *stage,
     if ((rc = put(dc.tile_utt, p.tile_utt.data(), p.tile_utt.size() * sizeof(int))) != 0) return rc;
     if ((rc = put(dc.tile_nt, p.tile_nt.data(), p.tile_nt.size() * sizeof(int))) != 0) return rc;
     if ((rc = put(dc.tile_max_out, p.tile_max_out.data(), p.tile_max_out.size() * sizeof(long long))) != 0) return rc;
+    if ((rc = put(dc.tile_first_out, p.tile_first_out.data(), p.tile_first_out.size() * sizeof(long long))) != 0) return rc;
     if ((rc = put(dc.item_base, p.item_base.data(), p.item_base.size() * sizeof(long long))) != 0) return rc;
     return 0;
 }
@@ -404,7 +412,8 @@ int launch_stage(trm_cuda_ctx *ctx, int precision, int stage, const DeviceChunk 
         trm::SrcArgs a{};
         a.desc = dc.desc; a.n_utt = dc.n; a.tube = dc.tube; a.out = dc.out; a.maxbits = dc.maxbits;
         a.table = f64 ? ctx->d_tab_f64 : ctx->d_tab_f32;
-        a.tile_utt = dc.tile_utt; a.tile_nt = dc.tile_nt; a.tile_max_out = dc.tile_max_out; a.item_base = dc.item_base;
+        a.tile_utt = dc.tile_utt; a.tile_nt = dc.tile_nt; a.tile_max_out = dc.tile_max_out; a.tile_first_out = dc.tile_first_out;
+        a.item_base = dc.item_base;
         a.n_tiles = dc.n_tiles; a.total_items = dc.total_items;
         const trm::KernelInfo &ki = f64 ? ctx->info64 : ctx->info32;
         const int grid = ctx->sm_count * std::max(1, ki.src_ctas_per_sm);

@@ -92,6 +92,16 @@ __device__ __forceinline__ void mbar_arrive(void *bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// streaming state of utterance u (kernel_args.h): header words and the R-typed part
+template <typename R> __device__ __forceinline__ unsigned long long *state_hdr(void *state, int u)
+{
+    return reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(state) + (size_t)u * (STATE_HDR * 8 + STATE_R * sizeof(R)));
+}
+template <typename R> __device__ __forceinline__ R *state_vals(void *state, int u)
+{
+    return reinterpret_cast<R *>(state_hdr<R>(state, u) + STATE_HDR);
+}
+
 struct WideArgs {
     TubeArgs t;
     int n_groups;      // CTAs; group g holds utterances order[start(g) .. start(g+1))
@@ -181,6 +191,15 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
             for (int q = 0; q < 6; ++q) { nt[q] = 0.0f; nb[q] = 0.0f; }
             float m_ry = 0.0f, m_rx = 0.0f, m_rY = 0.0f, n_ry = 0.0f, n_rx = 0.0f, n_rY = 0.0f;
             float y1 = 0.0f, y2 = 0.0f, thy = 0.0f;
+            float *const sv = (args.state && has) ? state_vals<float>(args.state, u) + STATE_SER : nullptr;
+            if (sv) {                                      // streaming: continue where the previous call stopped
+#pragma unroll
+                for (int q = 0; q < 10; ++q) { t[q] = sv[q]; bt[q] = sv[10 + q]; }
+#pragma unroll
+                for (int q = 0; q < 6; ++q) { nt[q] = sv[20 + q]; nb[q] = sv[26 + q]; }
+                m_ry = sv[32]; m_rx = sv[33]; m_rY = sv[34]; n_ry = sv[35]; n_rx = sv[36]; n_rY = sv[37];
+                y1 = sv[38]; y2 = sv[39]; thy = sv[40];
+            }
 
             for (int blk = 0; blk < n_blocks; ++blk) {
                 const int slot = blk & 1;
@@ -281,6 +300,14 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
                 }
                 __syncwarp(FULL);
             }
+            if (sv) {
+#pragma unroll
+                for (int q = 0; q < 10; ++q) { sv[q] = t[q]; sv[10 + q] = bt[q]; }
+#pragma unroll
+                for (int q = 0; q < 6; ++q) { sv[20 + q] = nt[q]; sv[26 + q] = nb[q]; }
+                sv[32] = m_ry; sv[33] = m_rx; sv[34] = m_rY; sv[35] = n_ry; sv[36] = n_rx; sv[37] = n_rY;
+                sv[38] = y1; sv[39] = y2; sv[40] = thy;
+            }
         } else {
             // ---- conformance mode: the reference's operations in the reference's order ---------------------------
             // The 16 junctions of one sample are independent; the code is written stage by stage ACROSS the junctions
@@ -306,6 +333,15 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
             double nt0 = 0, nt1 = 0, nt2 = 0, nt3 = 0, nt4 = 0, nt5 = 0, nb0 = 0, nb1 = 0, nb2 = 0, nb3 = 0, nb4 = 0, nb5 = 0;
             double m_ry = 0.0, m_rx = 0.0, m_rY = 0.0, n_ry = 0.0, n_rx = 0.0, n_rY = 0.0;
             double y1 = 0.0, y2 = 0.0, thy = 0.0;
+            double *const sv = (args.state && has) ? state_vals<double>(args.state, u) + STATE_SER : nullptr;
+            if (sv) {                                      // streaming: continue where the previous call stopped
+                t0 = sv[0]; t1 = sv[1]; t2 = sv[2]; t3 = sv[3]; t4 = sv[4]; t5 = sv[5]; t6 = sv[6]; t7 = sv[7]; t8 = sv[8]; t9 = sv[9];
+                b0 = sv[10]; b1 = sv[11]; b2 = sv[12]; b3 = sv[13]; b4 = sv[14]; b5 = sv[15]; b6 = sv[16]; b7 = sv[17]; b8 = sv[18]; b9 = sv[19];
+                nt0 = sv[20]; nt1 = sv[21]; nt2 = sv[22]; nt3 = sv[23]; nt4 = sv[24]; nt5 = sv[25];
+                nb0 = sv[26]; nb1 = sv[27]; nb2 = sv[28]; nb3 = sv[29]; nb4 = sv[30]; nb5 = sv[31];
+                m_ry = sv[32]; m_rx = sv[33]; m_rY = sv[34]; n_ry = sv[35]; n_rx = sv[36]; n_rY = sv[37];
+                y1 = sv[38]; y2 = sv[39]; thy = sv[40];
+            }
 
             for (int blk = 0; blk < n_blocks; ++blk) {
                 const int slot = blk & 1;
@@ -402,6 +438,14 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
                 }
                 __syncwarp(FULL);
             }
+            if (sv) {
+                sv[0] = t0; sv[1] = t1; sv[2] = t2; sv[3] = t3; sv[4] = t4; sv[5] = t5; sv[6] = t6; sv[7] = t7; sv[8] = t8; sv[9] = t9;
+                sv[10] = b0; sv[11] = b1; sv[12] = b2; sv[13] = b3; sv[14] = b4; sv[15] = b5; sv[16] = b6; sv[17] = b7; sv[18] = b8; sv[19] = b9;
+                sv[20] = nt0; sv[21] = nt1; sv[22] = nt2; sv[23] = nt3; sv[24] = nt4; sv[25] = nt5;
+                sv[26] = nb0; sv[27] = nb1; sv[28] = nb2; sv[29] = nb3; sv[30] = nb4; sv[31] = nb5;
+                sv[32] = m_ry; sv[33] = m_rx; sv[34] = m_rY; sv[35] = n_ry; sv[36] = n_rx; sv[37] = n_rY;
+                sv[38] = y1; sv[39] = y2; sv[40] = thy;
+            }
         }
         return;
     }
@@ -450,10 +494,32 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
     double pos = 0.0;
     unsigned long long pos_fx = 0ull;
     unsigned long long kb = args.noise_k0;
+    bool fresh = true;                     // no sample of this utterance exists yet (first-sample rule of the noise filter)
+    unsigned long long *const st_h = (args.state && has_utt) ? state_hdr<R>(args.state, u) : nullptr;
+    R *const st_v = st_h ? state_vals<R>(args.state, u) : nullptr;
     const unsigned long long MASK44 = (1ull << 44) - 1ull;
     const unsigned long long pw0 = c_noise_pow[hl], pw1 = c_noise_pow[hl + 1], pwB = c_noise_pow[TB];
     R xm1 = 0, xm2 = 0;
     const int pf = hl >> 1, pc = hl & 1;                   // parameter lane -> (unit, component) of the staged value
+    if (st_h) {
+        // streaming: oscillator position, noise generator, oscillator / band-pass input history of the previous call
+        pos = __longlong_as_double((long long)st_h[0]);
+        pos_fx = st_h[1];
+        kb = st_h[2];
+        fresh = st_h[3] != 0ull;
+        xm1 = st_v[STATE_XM]; xm2 = st_v[STATE_XM + 1];
+        for (int i = hl; i < FIR_HIST; i += TB) { S.HE[i] = st_v[STATE_HE + i]; S.HO[i] = st_v[STATE_HO + i]; }
+    }
+    if (feeds && D->jc0 > 0 && n_frames > 1) {
+        // the call starts inside a control interval: redo its jc0 interpolation adds (exactly the reference's sequence)
+        const double nxt = S.FR[0][1][hl];
+        p_cur = p_next;
+        p_delta = (nxt - p_cur) / (double)cp;
+        p_next = nxt;
+        for (int i = 0; i < D->jc0; ++i) p_cur += p_delta;
+        jc = D->jc0;
+    }
+    __syncwarp(FULL);
 
     for (int blk = 0; blk < n_blocks; ++blk) {
         const int slot = blk & 1;
@@ -638,7 +704,7 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
         {
             const unsigned long long kt = (kb * pw1) & MASK44, kp = (kb * pw0) & MASK44;
             const double nz = (double)(long long)kt * TWO_M44 - 0.5;
-            const double nzp = (n0 + hl == 0) ? 0.0 : ((double)(long long)kp * TWO_M44 - 0.5);
+            const double nzp = (fresh && n0 + hl == 0) ? 0.0 : ((double)(long long)kp * TWO_M44 - 0.5);
             lp_noise = (R)(nz + nzp);
             kb = (kb * pwB) & MASK44;
         }
@@ -768,6 +834,17 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
             if (hl < FIR_HIST - TB) { S.HE[TB + hl] = e1; S.HO[TB + hl] = o1; }
         }
         __syncwarp(FULL);
+    }
+    if (st_h) {
+        // streaming calls cover whole 16-sample blocks, so everything here is the state after the last sample
+        if (hl == 0) {
+            st_h[0] = (unsigned long long)__double_as_longlong(pos);
+            st_h[1] = pos_fx;
+            st_h[2] = kb;
+            st_h[3] = 0ull;
+            st_v[STATE_XM] = xm1; st_v[STATE_XM + 1] = xm2;
+        }
+        for (int i = hl; i < FIR_HIST; i += TB) { st_v[STATE_HE + i] = S.HE[i]; st_v[STATE_HO + i] = S.HO[i]; }
     }
 }
 

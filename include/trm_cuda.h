@@ -66,6 +66,11 @@ typedef struct trm_cuda_utterance {
     double   throatGain;
     double   volumeAmp;         /* amplitude(volume)                                                   */
     double   leftGain, rightGain; /* stereo factors applied on top of scale (TRMTubeModel.m:532-533)   */
+    /* streaming (trm_cuda_stream_*): a call continues an utterance.  All zero for whole utterances.              */
+    int64_t  out_start;         /* first output-rate sample this call produces (earlier ones exist already)       */
+    int64_t  in_start;          /* first tube-rate sample still in memory (multiple of 4; earlier ones are gone)  */
+    int32_t  jc0;               /* tube samples already produced inside the first control interval of `frames`    */
+    int32_t  reserved;
 } trm_cuda_utterance;
 
 /* Constant tables shared by all utterances; computed on the host by libtrm. */
