@@ -125,6 +125,10 @@ def lib():
     sig("TRMEventListFrameCount", i64, vp, i64)
     sig("TRMBatchGenerateFrames", C.c_int, vp, vp, vp, vp, vp, C.c_int, vp, vp, C.c_int)
     sig("TRMBatchSynthesizeEvents", C.c_int, vp, vp, vp, vp, vp, C.c_int, vp, vp, C.c_int)
+    sig("TRMStreamCreate", vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp)
+    sig("TRMStreamCapacity", i64, vp)
+    sig("TRMStreamPush", C.c_int, vp, vp, C.c_int, C.c_int, vp, vp)
+    sig("TRMStreamFree", None, vp)
     sig("TRMBatchSynthesizeAsync", vp, vp, vp, vp, vp, vp, C.c_int, vp)
     sig("TRMBatchWait", C.c_int, vp)
     sig("TRMBatchMakeResident", vp, vp, vp, C.c_int, P(C.c_int))

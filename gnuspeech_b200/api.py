@@ -473,6 +473,40 @@ class TRMBatch(object):
         return TRMResident(self, frames, device)
 
 
+class TRMStream(object):
+    """Streaming synthesis of n voices at once (TRMStreamCreate / TRMStreamPush): push control frames as they arrive,
+    get the un-normalised output-rate samples that became computable; pushes concatenate to exactly the one-shot
+    result.  TRAcT's mode of use (Applications/TRAcT/tube.c:1096-1191), batched."""
+
+    def __init__(self, n_streams, ip, precision=N.TRM_PRECISION_FP64, max_frames_per_push=64, device=0):
+        err = C.c_int(0)
+        self._ip = ip
+        self.n = n_streams
+        self.dtype = np.float64 if precision == N.TRM_PRECISION_FP64 else np.float32
+        self._h = N.lib().TRMStreamCreate(n_streams, C.byref(ip), precision, max_frames_per_push, device, C.byref(err))
+        if not self._h:
+            check(err.value or N.TRM_ERR_CUDA, "TRMStreamCreate")
+        self.capacity = int(N.lib().TRMStreamCapacity(self._h))
+        self._buf = np.zeros((n_streams, self.capacity), self.dtype)
+
+    def push(self, frames, flush=False):
+        """frames: (n_streams, m, 16) float64 (m may be 0 with flush).  Returns (n_streams, k) samples."""
+        frames = np.ascontiguousarray(frames, dtype=np.float64).reshape(self.n, -1, 16)
+        m = frames.shape[1]
+        k = C.c_int64(0)
+        check(N.lib().TRMStreamPush(self._h, _ptr(frames) if m else None, m, 1 if flush else 0, _ptr(self._buf), C.byref(k)),
+              "TRMStreamPush")
+        return self._buf[:, :k.value].copy()
+
+    def free(self):
+        if self._h:
+            N.lib().TRMStreamFree(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.free()
+
+
 class TRMBatchTicket(object):
     """Handle of an asynchronous TRMBatch call; keeps the call's buffers alive until wait() returns."""
 

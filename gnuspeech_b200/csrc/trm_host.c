@@ -977,6 +977,61 @@ int TRMBatchSynthesizeEvents(TRMBatch *b, const TRMEvent *events, const int64_t 
     return rc;
 }
 
+/* ---- streaming (TRAcT-style): many voices advanced together, state carried on the device ---- */
+struct TRMStream {
+    trm_cuda_stream *s;
+    voice_set voices;
+    int device, lane;
+};
+
+TRMStream *TRMStreamCreate(int n_streams, const TRMInputParameters *voice, int precision, int max_frames_per_push,
+                           int device, int *err)
+{
+    int dummy;
+    if (!err) err = &dummy;
+    if (n_streams <= 0 || max_frames_per_push <= 0 || !voice ||
+        (precision != TRM_PRECISION_FP64 && precision != TRM_PRECISION_FP32)) {
+        *err = set_err(TRM_ERR_PARAM, "bad stream arguments%s", "");
+        return NULL;
+    }
+    TRMStream *t = calloc(1, sizeof *t);
+    if (!t) { *err = set_err(TRM_ERR_NOMEM, "out of memory%s", ""); return NULL; }
+    trm_cuda_utterance d;
+    rates_t r;
+    if ((*err = describe(voice, 2, &t->voices, &d, &r)) != TRM_OK) { free(t); return NULL; }
+    trm_cuda_ctx *ctx;
+    if ((*err = acquire_ctx(device, &ctx, &t->lane)) != TRM_OK) { voice_set_free(&t->voices); free(t); return NULL; }
+    t->device = device;
+    if (trm_cuda_set_wavetables(ctx, t->voices.tables, t->voices.n) != 0 ||
+        trm_cuda_stream_create(ctx, precision, n_streams, &d, max_frames_per_push, &t->s) != 0) {
+        *err = cuda_err();
+        release_ctx(device, t->lane);
+        voice_set_free(&t->voices);
+        free(t);
+        return NULL;
+    }
+    *err = TRM_OK;
+    return t;      /* the context lane stays with the stream (its wavetables must not change under it) */
+}
+
+int64_t TRMStreamCapacity(const TRMStream *t) { return t ? trm_cuda_stream_capacity(t->s) : 0; }
+
+int TRMStreamPush(TRMStream *t, const TRMParameters *frames, int m, int flush, void *samples_out, int64_t *n_samples)
+{
+    if (!t) return set_err(TRM_ERR_PARAM, "null stream%s", "");
+    if (trm_cuda_stream_push(t->s, (const double *)frames, m, flush, samples_out, n_samples) != 0) return cuda_err();
+    return TRM_OK;
+}
+
+void TRMStreamFree(TRMStream *t)
+{
+    if (!t) return;
+    trm_cuda_stream_destroy(t->s);
+    release_ctx(t->device, t->lane);
+    voice_set_free(&t->voices);
+    free(t);
+}
+
 /* ---- asynchronous calls: one host thread per ticket; two tickets per device overlap (context lanes) ---- */
 struct TRMBatchTicket {
     pthread_t th;

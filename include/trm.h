@@ -275,6 +275,25 @@ int TRMBatchGenerateFrames(TRMBatch *batch, const TRMEvent *events, const int64_
 int TRMBatchSynthesizeEvents(TRMBatch *batch, const TRMEvent *events, const int64_t *event_offset, const int32_t *n_events,
                              const TRMFrameGeneration *fg, int shared_fg, int16_t *pcm_out, void *samples_out, int device);
 
+/* ---------------------------------------------------------------------------------------------
+ * Streaming synthesis: TRAcT's mode of use (Applications/TRAcT/tube.c:1096-1191) -- audio as
+ * it is produced, parameters arriving while it plays, no normalisation to a global maximum -- for many voices at once.
+ * n_streams independent streams with the same voice are advanced together: every push appends m control frames per
+ * stream and returns the un-normalised output-rate samples that became computable (what .resampledData holds for a
+ * whole utterance; double in FP64 mode, float in FP32 mode).  The state of every recurrence is carried on the device:
+ * the pushes, concatenated, are bit-identical to synthesizing the whole utterance at once.
+ * A stream object occupies one of its device's three context lanes until it is freed.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct TRMStream TRMStream;
+TRMStream *TRMStreamCreate(int n_streams, const TRMInputParameters *voice, int precision, int max_frames_per_push,
+                           int device, int *err);
+/* samples per stream one push can return = row stride (in samples) of samples_out */
+int64_t TRMStreamCapacity(const TRMStream *stream);
+/* frames: [stream][m] TRMParameters; samples_out: [stream][TRMStreamCapacity()] ; *n_samples = samples returned per
+ * stream by this push.  flush != 0 ends the streams (the converter's tail, as at the end of -synthesize). */
+int TRMStreamPush(TRMStream *stream, const TRMParameters *frames, int m, int flush, void *samples_out, int64_t *n_samples);
+void TRMStreamFree(TRMStream *stream);
+
 /* Debug / conformance variant on one device: additionally returns the tube-rate signal (what -synthesize
  * hands to dataFill:, TRMTubeModel.m:346) in the batch's arithmetic type; TRMBatchTubeElements() elements,
  * utterance u at TRMBatchTubeOffsets()[u]. */

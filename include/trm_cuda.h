@@ -134,6 +134,24 @@ int  trm_cuda_resident_run(trm_cuda_resident *res, void *stream);               
 int  trm_cuda_resident_fetch(trm_cuda_resident *res, int16_t *pcm_host, void *samples_host,
                              double *max_host, void *tube_host);                 /* blocking D2H          */
 int  trm_cuda_stage_launches(int stage);     /* kernel launches one stage issues */
+
+/*
+ * Streaming synthesis (TRAcT-style, Applications/TRAcT/tube.c:1096-1191: output as it is produced, no normalisation):
+ * n_streams voices with the SAME rates (one trm_cuda_utterance template: controlPeriod, converter signature ...) are
+ * advanced together.  Every push appends `m` control frames per stream (frames_host: [stream][m][16] doubles) and
+ * returns the un-normalised output-rate samples that became computable (samples_host: [stream][*n_samples], row
+ * stride = capacity given at creation; double or float by precision).  Calls cover whole 16-sample blocks of the
+ * waveguide, the state of every recurrence is carried on the device: the concatenation of all pushes plus the flush
+ * is bit-identical to synthesizing the whole utterance at once.  flush != 0 ends the streams (converter tail, as
+ * -synthesize does at the end of an utterance); the object can then be destroyed.
+ */
+typedef struct trm_cuda_stream trm_cuda_stream;
+int  trm_cuda_stream_create(trm_cuda_ctx *ctx, int precision, int n_streams, const trm_cuda_utterance *voice,
+                            int max_frames_per_push, trm_cuda_stream **out);
+int64_t trm_cuda_stream_capacity(const trm_cuda_stream *s);          /* samples per stream a push can return */
+int  trm_cuda_stream_push(trm_cuda_stream *s, const double *frames_host, int m, int flush, void *samples_host,
+                          int64_t *n_samples);
+void trm_cuda_stream_destroy(trm_cuda_stream *s);
 /*
  * Control frames on the device (replaces -[EventList generateOutputInTimeRange:...], EventList.m:883-1061): uploads
  * the event lists of the n utterances (utterance u: events[ev_offset[u] .. +ev_count[u]); fg: one entry per
