@@ -54,6 +54,8 @@ template <typename R>
 struct alignas(16) FFHalf {
     double FR[2][FRAME_CHUNK][16];           // TMA destination, double-buffered
     unsigned long long mbar[2];
+    double CST[12];                          // per-utterance constants of the feed-forward phases (global loads of the
+                                             // descriptor inside the block loop sat on the warp's critical path)
     double INC[TB];                          // oscillator increments of the block (conformance mode: every lane walks them)
     R HE[FIR_HIST + TB], HO[FIR_HIST + TB];  // oscillator history, even / odd 2x-rate samples
 };
@@ -472,6 +474,12 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
     const bool modulation = D->usesModulation != 0;
     const int div1 = D->div1, div2 = D->div2;
 
+    enum { C_BASICINC, C_TNDELTA, C_DAMP, C_SR, C_NR1SQ, C_APSCALE2, C_MOUTH0, C_BF, C_CMIX, C_TA0 };
+    if (hl == 0) {
+        S.CST[C_BASICINC] = D->basicIncrement; S.CST[C_TNDELTA] = D->tnDelta; S.CST[C_DAMP] = D->dampingFactor;
+        S.CST[C_SR] = D->sampleRate; S.CST[C_NR1SQ] = D->nr1sq; S.CST[C_APSCALE2] = D->apScale2; S.CST[C_MOUTH0] = D->mouth[0];
+        S.CST[C_BF] = D->breathinessFactor; S.CST[C_CMIX] = D->crossmixFactor; S.CST[C_TA0] = D->ta0;
+    }
     const bool feeds = n_tube > 0;
     const int n_chunks = (n_frames + FRAME_CHUNK - 1) / FRAME_CHUNK;
     if (hl == 0 && feeds) {
@@ -579,7 +587,7 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
         double inc_d;
         {
             const double f0 = 220.0 * exp2((prm[0] + 3.0) / 12.0);
-            inc_d = (f0 / 2.0) * D->basicIncrement;
+            inc_d = (f0 / 2.0) * S.CST[C_BASICINC];
             if constexpr (!FAST) S.INC[hl] = inc_d;
         }
         double ax_d;
@@ -589,14 +597,14 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
             const float axf = amplitude_f((float)prm[1]);
             ax_d = (double)axf;
             {
-                const float tq = axf * (float)D->tnDelta;
+                const float tq = axf * (float)S.CST[C_TNDELTA];
                 const float fr = tq - floorf(tq);
                 if (fabsf(fr - 0.5f) < 2e-3f) ax_d = amplitude_db(prm[1]);
             }
             ax = axf;
             ah1 = amplitude_f((float)prm[2]);
             const float fa = amplitude_f((float)prm[3]);
-            const float dd = (float)D->dampingFactor;
+            const float dd = (float)S.CST[C_DAMP];
             float r2[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) { const float r = (float)prm[7 + q]; r2[q] = r * r; }
@@ -615,7 +623,7 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
             };
             float beta2, gamma2;
             {
-                const float sr = (float)D->sampleRate;
+                const float sr = (float)S.CST[C_SR];
                 const float pi = 3.14159265358979323846f;
                 const float inv_sr = 1.0f / sr;
                 float su, cu;
@@ -636,12 +644,12 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
                 const float vel = (float)prm[15], v2 = vel * vel;
                 const float inv = __fdividef(dd, (r2[3] + r2[3]) + v2);
                 W.ring[slot][3][hl][ucol] = make_float4(2.0f * r2[3] * inv, -v2 * inv, 2.0f * v2 * inv, (v2 - (r2[3] + r2[3])) * inv);
-                W.ring[slot][9][hl][ucol] = two_port(v2, (float)D->nr1sq, beta2);
+                W.ring[slot][9][hl][ucol] = two_port(v2, (float)S.CST[C_NR1SQ], beta2);
             }
             {
-                const float ap2 = (float)D->apScale2;
+                const float ap2 = (float)S.CST[C_APSCALE2];
                 const float inv = __fdividef(1.0f, r2[7] + ap2);
-                W.ring[slot][8][hl][ucol] = make_float4(dd * (float)D->mouth[0] * ((r2[7] - ap2) * inv), 2.0f * r2[7] * inv, tap[2], gamma2);
+                W.ring[slot][8][hl][ucol] = make_float4(dd * (float)S.CST[C_MOUTH0] * ((r2[7] - ap2) * inv), 2.0f * r2[7] * inv, tap[2], gamma2);
             }
         } else {
             ax_d = amplitude_db(prm[1]);
@@ -657,13 +665,13 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
             const double k6 = (r2[4] - r2[5]) / (r2[4] + r2[5]);
             const double k7 = (r2[5] - r2[6]) / (r2[5] + r2[6]);
             const double k8 = (r2[6] - r2[7]) / (r2[6] + r2[7]);
-            const double ap2 = D->apScale2;
+            const double ap2 = S.CST[C_APSCALE2];
             const double k9 = (r2[7] - ap2) / (r2[7] + ap2);
             const double vel = prm[15];
             const double v2 = vel * vel;
             const double sum = 2.0 / ((r2[3] + r2[3]) + v2);
             const double aL = sum * r2[3], aU = sum * v2;
-            const double n2 = D->nr1sq;
+            const double n2 = S.CST[C_NR1SQ];
             const double k10 = (v2 - n2) / (v2 + n2);
             double tap[8];
             {
@@ -678,7 +686,7 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
             }
             double beta2, gamma2;
             {
-                const double sr = D->sampleRate;
+                const double sr = S.CST[C_SR];
                 const double pi = 3.14159265358979323846;
                 const double tanv = tan((pi * prm[6]) / sr);
                 const double cosv = cos(((2.0 * pi) * prm[5]) / sr);
@@ -742,7 +750,7 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
         // ---- A2: table look-ups, FIR, source mixing (TRMWavetable.m:174-195, m:305-337) --------------------------
         {
             if (!active) { p0 = 0.0; p1 = 0.0; }
-            const double newDiv2 = (double)div2 - rint(ax_d * D->tnDelta);
+            const double newDiv2 = (double)div2 - rint(ax_d * S.CST[C_TNDELTA]);
             const double Ld = newDiv2 - (double)div1;
             int lo0 = ((int)p0) & (TRM_TABLE_LENGTH - 1), lo1 = ((int)p1) & (TRM_TABLE_LENGTH - 1);
             int hi0 = lo0 + 1, hi1 = lo1 + 1;
@@ -794,17 +802,17 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
                 acc += ho[-FIR_HIST] * FirCoef<R>::at(2 * FIR_HIST);
                 pulse0 = acc;
             }
-            const R bf = (R)D->breathinessFactor, one_minus_bf = (R)(1.0 - D->breathinessFactor);
+            const R bf = (R)S.CST[C_BF], one_minus_bf = (R)(1.0 - S.CST[C_BF]);
             const R pulsed_noise = lp_noise * pulse0;
             const R pulse = ax * ((pulse0 * one_minus_bf) + (pulsed_noise * bf));
             if (modulation) {
-                R crossmix = ax * (R)D->crossmixFactor;
+                R crossmix = ax * (R)S.CST[C_CMIX];
                 crossmix = (crossmix < (R)1) ? crossmix : (R)1;
                 sig = (pulsed_noise * crossmix) + (lp_noise * ((R)1 - crossmix));
             } else
                 sig = lp_noise;
             const R tube_in = (pulse + (ah1 * sig)) * (R)0.125;
-            const R thr_in = (R)D->ta0 * (pulse * (R)0.125);
+            const R thr_in = (R)S.CST[C_TA0] * (pulse * (R)0.125);
             // band-pass feed-forward part alpha*(x[n]-x[n-2]); x[n-2] comes from two lanes down or the carry
             R x2 = __shfl_sync(FULL, sig, (lane & 16) | ((hl - 2) & 15));
             if (hl == 0) x2 = xm2;
