@@ -71,7 +71,6 @@ struct PcmArgs {
     const void *out;                 // Real[]
     const unsigned long long *maxbits;
     int16_t *pcm;
-    unsigned blocks_per_utt;         // CTAs covering the longest utterance
 };
 
 // control-frame generator (framegen_kernel.cuh)

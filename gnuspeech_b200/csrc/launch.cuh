@@ -102,10 +102,9 @@ template <typename R> static int launch_pcm(const PcmArgs &a, long long max_n_ou
     if (a.n_utt <= 0 || max_n_out <= 0) return 0;
     const long long per_cta = (long long)PCM_THREADS * PCM_PER_THREAD;
     const long long bpu = (max_n_out + per_cta - 1) / per_cta;
-    if (bpu * a.n_utt > 0x7FFFFFFFll) return (int)cudaErrorInvalidConfiguration;
-    PcmArgs b = a;
-    b.blocks_per_utt = (unsigned)bpu;
-    pcm_kernel<R><<<(unsigned)(bpu * a.n_utt), PCM_THREADS, 0, s>>>(b);
+    if (bpu > 0x7FFFFFFFll) return (int)cudaErrorInvalidConfiguration;
+    dim3 grid((unsigned)bpu, (unsigned)(a.n_utt < 65535 ? a.n_utt : 65535));
+    pcm_kernel<R><<<grid, PCM_THREADS, 0, s>>>(a);
     return (int)cudaGetLastError();
 }
 

@@ -337,13 +337,12 @@ __global__ void __launch_bounds__(SRC_THREADS, sizeof(R) == 4 ? 3 : 2) src_kerne
 template <typename R>
 __global__ void __launch_bounds__(PCM_THREADS) pcm_kernel(PcmArgs args)
 {
-    // 1-D grid: block -> (utterance, block inside the utterance); gridDim.y would cap a batch at 65,535 utterances
-    const int u = (int)(blockIdx.x / args.blocks_per_utt);
-    const long long blk = blockIdx.x % args.blocks_per_utt;
+  // blockIdx.y strides over the utterances (gridDim.y is capped at 65,535; larger batches loop)
+  for (int u = blockIdx.y; u < args.n_utt; u += gridDim.y) {
     const trm_cuda_utterance *__restrict__ D = args.desc + u;
     const long long n_out = D->n_out;
-    const long long n0 = (blk * PCM_THREADS + threadIdx.x) * PCM_PER_THREAD;
-    if (n0 >= n_out) return;
+    const long long n0 = ((long long)blockIdx.x * PCM_THREADS + threadIdx.x) * PCM_PER_THREAD;
+    if (n0 >= n_out) continue;
     const double mx = __longlong_as_double((long long)args.maxbits[u]);
     const double scale = (32767.0 / mx) * D->volumeAmp;                  // TRMTubeModel.m:515
     const R *__restrict__ z = reinterpret_cast<const R *>(args.out) + D->out_offset + n0;
@@ -387,6 +386,7 @@ __global__ void __launch_bounds__(PCM_THREADS) pcm_kernel(PcmArgs args)
             for (int i = 0; i < PCM_PER_THREAD && n0 + i < n_out; ++i) p[i] = q[i];
         }
     }
+  }
 }
 
 }  // namespace trm
