@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
     unsigned long long *const st_h = (args.state && has_utt) ? state_hdr<R>(args.state, u) : nullptr;
     R *const st_v = st_h ? state_vals<R>(args.state, u) : nullptr;
     const unsigned long long MASK44 = (1ull << 44) - 1ull;
-    const unsigned long long pw0 = c_noise_pow[hl], pw1 = c_noise_pow[hl + 1], pwB = c_noise_pow[TB];
+    const unsigned long long pw1 = c_noise_pow[hl + 1], pwB = c_noise_pow[TB];
     R xm1 = 0, xm2 = 0;
     const int pf = hl >> 1, pc = hl & 1;                   // parameter lane -> (unit, component) of the staged value
     if (st_h) {
@@ -561,9 +561,22 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
                 p_next = nxt;
             }
             const int run = min(TB - s, cp - jc);
-            for (int i = 0; i < run; ++i) {
-                reinterpret_cast<double *>(&W.ring[slot][pf][(s + i + pf) & (TB - 1)][ucol])[pc] = p_cur;
-                p_cur += p_delta;
+            if (run == TB) {
+                // the whole block lies inside one control interval (4 blocks out of 5 for the male voice): straight-line
+                // stores with constant offsets, the 16 dependent adds are all that is left on the chain
+                double *const row = reinterpret_cast<double *>(&W.ring[slot][pf][0][ucol]) + pc;
+                constexpr int RS = (int)(Wide<R>::UP * sizeof(typename Wide<R>::Unit) / sizeof(double));   // doubles per sample row
+                double *const r0 = row + pf * RS;                        // row of step 0; steps TB-pf .. wrap to the start
+#pragma unroll
+                for (int i = 0; i < TB; ++i) {
+                    (i + pf < TB ? r0 : r0 - TB * RS)[i * RS] = p_cur;
+                    p_cur += p_delta;
+                }
+            } else {
+                for (int i = 0; i < run; ++i) {
+                    reinterpret_cast<double *>(&W.ring[slot][pf][(s + i + pf) & (TB - 1)][ucol])[pc] = p_cur;
+                    p_cur += p_delta;
+                }
             }
             s += run;
             jc += run;
@@ -710,9 +723,11 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
         // noise (TRMUtility.m:71-85 as the MCG mod 2^44) + one-zero low-pass (TRMFilters.m:81-86)
         R lp_noise;
         {
-            const unsigned long long kt = (kb * pw1) & MASK44, kp = (kb * pw0) & MASK44;
+            const unsigned long long kt = (kb * pw1) & MASK44;
             const double nz = (double)(long long)kt * TWO_M44 - 0.5;
-            const double nzp = (fresh && n0 + hl == 0) ? 0.0 : ((double)(long long)kp * TWO_M44 - 0.5);
+            // x[n-1]: the draw of the lane below; lane 0 takes the last draw of the previous block (the state kb itself)
+            double nzp = __shfl_up_sync(FULL, nz, 1, 16);
+            if (hl == 0) nzp = (fresh && n0 == 0) ? 0.0 : ((double)(long long)kb * TWO_M44 - 0.5);
             lp_noise = (R)(nz + nzp);
             kb = (kb * pwB) & MASK44;
         }
