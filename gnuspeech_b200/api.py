@@ -337,7 +337,10 @@ class PinnedArray(object):
             self._p = None
 
     def __del__(self):
-        self.free()
+        try:
+            self.free()
+        except TypeError:       # interpreter shutdown: module globals are already gone, the process frees the memory
+            pass
 
 
 def _ptr(a):
@@ -377,7 +380,10 @@ class TRMBatch(object):
 
     def __del__(self):
         if getattr(self, "_h", None):
-            N.lib().TRMBatchFree(self._h)
+            try:
+                N.lib().TRMBatchFree(self._h)
+            except TypeError:   # interpreter shutdown
+                pass
             self._h = None
 
     def _arr(self, fn, ctype, dtype):

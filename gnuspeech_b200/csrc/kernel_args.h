@@ -46,7 +46,7 @@ struct TubeArgs {
     uint64_t noise_k0;
 };
 
-template <typename R> struct HD { R h, dh; };
+template <typename R> struct alignas(2 * sizeof(R)) HD { R h, dh; };   // one vector load per entry
 
 struct SrcArgs {
     const trm_cuda_utterance *desc;
@@ -54,7 +54,7 @@ struct SrcArgs {
     const void *tube;                // Real[]
     void *out;                       // Real[]
     unsigned long long *maxbits;     // [n_utt] bit pattern of the running max |y| as double
-    const void *table;               // HD<Real>[3328]
+    const void *table;               // HD<Real>[256][13]: filter index l + 256 k at [l][k]
     // work decomposition: tiles of <= 32 utterances that share the converter signature
     const int *tile_utt;             // [n_tiles][32] utterance index or -1
     const int *tile_nt;              // [n_tiles] outputs per work item of that tile (window fits SRC_ROWS)

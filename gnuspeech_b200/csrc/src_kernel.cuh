@@ -22,6 +22,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "kernel_args.h"
 #include "trm_cuda.h"
 #include "tube_kernel.cuh"   // mbarrier / TMA bulk-copy helpers
@@ -172,20 +174,28 @@ __global__ void __launch_bounds__(SRC_THREADS, sizeof(R) == 4 ? 3 : 2) src_kerne
             if (bytes)
                 tma_bulk_g2s(xU + lane * SRC_XLD + (int)(lo - qb), reinterpret_cast<const R *>(args.tube) + s_tube_off[lane] + lo, bytes, &s_bar);
         }
+        const int run = nt / (SRC_THREADS / 32);                         // consecutive outputs per warp (multiple of SRC_CHUNK)
         if (up) {
-            // coefficient table of the item, one output per thread: C[n][k] = h[l + 256 k] + dH[l + 256 k] * (m / 256),
-            // (l, m) from the fraction F of the time register for the left wing and from ~F for the right wing (m:179-203)
+            // coefficient table of the item: C[n][t] = h[l + 256 k] + dH[l + 256 k] * (m / 256), (l, m) from the fraction F
+            // of output n's time register for the left wing (t = k) and from ~F for the right wing (t = 13 + k)
+            // (m:179-203).  One coefficient per thread and step: consecutive threads read consecutive entries of the
+            // phase-major filter table, and the loads of one thread are independent of each other.
+            const int n_coef = n_item * SRC_TAPS;
+#pragma unroll 4
+            for (int i = threadIdx.x; i < n_coef; i += SRC_THREADS) {
+                const int nr = i / SRC_TAPS, t = i - nr * SRC_TAPS;
+                const bool right = t >= SRC_ZC;
+                unsigned F = (frac0 + (unsigned)nr * tri) & 0xFFFFu;
+                if (right) F = (~F) & 0xFFFFu;
+                const HD<R> a = tab[(F >> 8) * SRC_ZC + (right ? t - SRC_ZC : t)];
+                Cf[nr * SRC_CLD + t] = a.h + a.dh * ((R)(F & 255u) / (R)256);
+            }
+            // column 26 of a row tells the walking warp what follows the output: 0 = same input position, 1 = the
+            // integer part of the time register advances (slide the window), 2 = last output of the warp's run
             for (int nr = threadIdx.x; nr < n_item; nr += SRC_THREADS) {
-                const unsigned F = (frac0 + (unsigned)nr * tri) & 0xFFFFu, G = (~F) & 0xFFFFu;
-                const R il = (R)(F & 255u) / (R)256, ir = (R)(G & 255u) / (R)256;
-                const HD<R> *tl = tab + (F >> 8), *tr = tab + (G >> 8);
-                R *c = Cf + nr * SRC_CLD;
-#pragma unroll 2
-                for (int k = 0; k < SRC_ZC; ++k) {
-                    const HD<R> a = tl[256 * k], b2 = tr[256 * k];
-                    c[k] = a.h + a.dh * il;
-                    c[SRC_ZC + k] = b2.h + b2.dh * ir;
-                }
+                const unsigned f = frac0 + (unsigned)nr * tri;
+                const bool last = (nr + 1 == n_item) || ((nr + 1) % run == 0);
+                Cf[nr * SRC_CLD + SRC_TAPS] = last ? (R)2 : ((((f + tri) >> 16) != (f >> 16)) ? (R)1 : (R)0);
             }
         }
         __syncthreads();                                                 // descriptors + coefficients visible
@@ -213,9 +223,10 @@ __global__ void __launch_bounds__(SRC_THREADS, sizeof(R) == 4 ? 3 : 2) src_kerne
         R *yw = yT + warp * (32 * YLD);
         const R *xl = xU + lane * SRC_XLD + off;                         // xl[i] = window element i of this lane's utterance
         if (up) {
-            const int run = nt / (SRC_THREADS / 32);                     // consecutive outputs per warp (multiple of SRC_CHUNK)
             const int nr_first = warp * run;
-            const int nr_last = (nr_first + run < n_item) ? nr_first + run : n_item;
+            // every utterance of the tile has all outputs of this item and none of them exists already (streaming):
+            // no per-output or per-piece range checks
+            const bool interior = __all_sync(0xFFFFFFFFu, my_lo == 0 && my_out == n_item);
             // Register window of the 26 input samples under the filter.  Logical element i (= xb[P - 12 + i]; left wing
             // xb[P-k] is i = 12-k, right wing xb[P+1+k] is i = 13+k) lives in register W[(i + ph) % 26] where ph is the
             // window phase.  When the integer part P of the time register advances, the oldest sample's register
@@ -224,71 +235,105 @@ __global__ void __launch_bounds__(SRC_THREADS, sizeof(R) == 4 ? 3 : 2) src_kerne
             // xb[P0 + Prel + d] is window element reach + Prel + d.
             R W[SRC_TAPS];
             int nr = nr_first;
-            int Pc = (int)((frac0 + (unsigned)(nr_first < n_item ? nr_first : 0) * tri) >> 16);
+            const int Pc0 = (int)((frac0 + (unsigned)(nr_first < n_item ? nr_first : 0) * tri) >> 16);
             {
-                const R *xp = xl + (reach - (SRC_ZC - 1)) + Pc;
+                const R *xp = xl + (reach - (SRC_ZC - 1)) + Pc0;
 #pragma unroll
                 for (int i = 0; i < SRC_TAPS; ++i) W[i] = xp[i];
             }
+            const R *xn = xl + reach + SRC_ZC + Pc0;                     // newest window element; the next one enters on a slide
+            const R *crow = Cf + nr_first * SRC_CLD;
+            R *const ys = yw + lane * YLD;
             int c0 = nr_first, j = 0;                                    // start of the current write-back chunk, outputs in it
             constexpr int PIECES = SRC_CHUNK / A;                        // 16-byte pieces per utterance and chunk
-            auto write_back = [&]() {
+            // piece i of this lane: utterance row (32 / PIECES) * i + lane / PIECES, elements A * (lane % PIECES) ..
+            R *dstp[PIECES];
+#pragma unroll
+            for (int i = 0; i < PIECES; ++i)
+                dstp[i] = reinterpret_cast<R *>(args.out) + s_out_off[(32 / PIECES) * i + lane / PIECES] + n_s + nr_first + A * (lane % PIECES);
+            auto write_back = [&](bool fast) {
                 __syncwarp();
+                if (fast) {
 #pragma unroll
-                for (int i = 0; i < PIECES; ++i) {
-                    const int r = (32 / PIECES) * i + lane / PIECES, part = lane % PIECES;
-                    const long long left = s_n_out[r] - (n_s + c0) - A * part;        // valid samples from this piece on
-                    const long long skip = s_out_start[r] - (n_s + c0) - A * part;   // leading samples that exist already
-                    if (left > 0 && A * part < j && skip < A) {
-                        R *dst = reinterpret_cast<R *>(args.out) + s_out_off[r] + n_s + c0 + A * part;
-                        const R *src = yw + r * YLD + A * part;
-                        if (left >= A && A * part + A <= j && skip <= 0) {
-                            Vec16<R> v;
+                    for (int i = 0; i < PIECES; ++i) {
+                        const R *src = yw + ((32 / PIECES) * i + lane / PIECES) * YLD + A * (lane % PIECES);
+                        Vec16<R> v;
 #pragma unroll
-                            for (int e = 0; e < A; ++e) v.e[e] = src[e];
-                            v.store(dst);
-                        } else {
-                            for (int e = 0; e < A && e < left && A * part + e < j; ++e)
-                                if (e >= skip) dst[e] = src[e];
+                        for (int e = 0; e < A; ++e) v.e[e] = src[e];
+                        v.store(dstp[i]);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < PIECES; ++i) {
+                        const int r = (32 / PIECES) * i + lane / PIECES, part = lane % PIECES;
+                        const long long left = s_n_out[r] - (n_s + c0) - A * part;        // valid samples from this piece on
+                        const long long skip = s_out_start[r] - (n_s + c0) - A * part;   // leading samples that exist already
+                        if (left > 0 && A * part < j && skip < A) {
+                            R *dst = dstp[i];
+                            const R *src = yw + r * YLD + A * part;
+                            if (left >= A && A * part + A <= j && skip <= 0) {
+                                Vec16<R> v;
+#pragma unroll
+                                for (int e = 0; e < A; ++e) v.e[e] = src[e];
+                                v.store(dst);
+                            } else {
+                                for (int e = 0; e < A && e < left && A * part + e < j; ++e)
+                                    if (e >= skip) dst[e] = src[e];
+                            }
                         }
                     }
                 }
                 __syncwarp();
+#pragma unroll
+                for (int i = 0; i < PIECES; ++i) dstp[i] += j;
                 c0 += j;
                 j = 0;
             };
-            while (nr < nr_last) {
+            auto walk = [&](auto tag) {
+                constexpr bool INTERIOR = decltype(tag)::value;
+                for (;;) {
 #pragma unroll
-                for (int ph = 0; ph < SRC_TAPS; ++ph) {
-                    while (nr < nr_last && (int)((frac0 + (unsigned)nr * tri) >> 16) == Pc) {
-                        // coefficient row: broadcast 128-bit loads, consumed as they arrive (tap t: t < 13 is the left wing,
-                        // logical element 12-t; else the right wing, logical element t)
-                        const R *crow = Cf + nr * SRC_CLD;
-                        R acc = (R)0;
+                    for (int ph = 0; ph < SRC_TAPS; ++ph) {
+                        R flag;
+                        do {
+                            // coefficient row: broadcast 128-bit loads, consumed as they arrive (tap t: t < 13 is the left
+                            // wing, logical element 12-t; else the right wing, logical element t)
+                            R acc = (R)0;
+                            flag = (R)0;
 #pragma unroll
-                        for (int q = 0; q < (SRC_TAPS + A - 1) / A; ++q) {
-                            Vec16<R> cq;
-                            cq.load(crow + A * q);
+                            for (int q = 0; q < (SRC_TAPS + 1 + A - 1) / A; ++q) {
+                                Vec16<R> cq;
+                                cq.load(crow + A * q);
 #pragma unroll
-                            for (int e = 0; e < A; ++e) {
-                                const int t = A * q + e;
-                                if (t < SRC_ZC) acc += W[(SRC_ZC - 1 - t + ph) % SRC_TAPS] * cq.e[e];
-                                else if (t < SRC_TAPS) acc += W[(t + ph) % SRC_TAPS] * cq.e[e];
+                                for (int e = 0; e < A; ++e) {
+                                    const int t = A * q + e;
+                                    if (t < SRC_ZC) acc += W[(SRC_ZC - 1 - t + ph) % SRC_TAPS] * cq.e[e];
+                                    else if (t < SRC_TAPS) acc += W[(t + ph) % SRC_TAPS] * cq.e[e];
+                                    else if (t == SRC_TAPS) flag = cq.e[e];
+                                }
                             }
-                        }
-                        yw[lane * YLD + j] = acc;
-                        const R av = (nr < my_out && nr >= my_lo) ? r_abs<R>(acc) : (R)0;
-                        local_max = (av > local_max) ? av : local_max;   // NaN never wins, like the reference
-                        ++nr;
-                        if (++j == SRC_CHUNK) write_back();
+                            ys[j] = acc;
+                            if constexpr (INTERIOR) {
+                                const R av = r_abs<R>(acc);
+                                local_max = (av > local_max) ? av : local_max;   // NaN never wins, like the reference
+                            } else {
+                                const R av = (nr < my_out && nr >= my_lo) ? r_abs<R>(acc) : (R)0;
+                                local_max = (av > local_max) ? av : local_max;
+                                ++nr;
+                            }
+                            crow += SRC_CLD;
+                            if (++j == SRC_CHUNK) write_back(INTERIOR);
+                        } while (flag == (R)0);
+                        if (flag == (R)2) return;
+                        // slide: logical element 0 (register ph) leaves, xb[P + 14] enters as logical element 25 of phase ph+1
+                        W[ph] = *++xn;
                     }
-                    if (nr >= nr_last) break;
-                    // slide: logical element 0 (register ph) leaves, xb[P + 14] enters as logical element 25 of phase ph+1
-                    ++Pc;
-                    W[ph] = xl[reach + SRC_ZC + Pc];
                 }
+            };
+            if (nr_first < n_item) {
+                if (interior) walk(std::true_type{}); else walk(std::false_type{});
+                if (j > 0) write_back(false);
             }
-            if (j > 0) write_back();
         } else {
             // down-sampling (short tubes): chunks are dealt round-robin to the warps, taps walk the filter phase
             for (int c0 = warp * SRC_CHUNK; c0 < n_item; c0 += (SRC_THREADS / 32) * SRC_CHUNK) {
@@ -301,7 +346,7 @@ __global__ void __launch_bounds__(SRC_THREADS, sizeof(R) == 4 ? 3 : 2) src_kerne
                     unsigned ph = (unsigned)rint((double)F * ratio), ii;
                     const R *xq = xl + base;
                     while ((ii = (ph >> 8)) < (unsigned)TRM_SRC_FILTER_LEN) {
-                        const HD<R> c = tab[ii];
+                        const HD<R> c = tab[(ii & 255u) * SRC_ZC + (ii >> 8)];
                         const R impulse = c.h + (c.dh * ((R)(ph & 255u) / (R)256));
                         acc += (*xq * impulse);
                         xq -= 1;
@@ -310,7 +355,7 @@ __global__ void __launch_bounds__(SRC_THREADS, sizeof(R) == 4 ? 3 : 2) src_kerne
                     ph = (unsigned)rint((double)((~F) & 0xFFFFu) * ratio);
                     xq = xl + base + 1;
                     while ((ii = (ph >> 8)) < (unsigned)TRM_SRC_FILTER_LEN) {
-                        const HD<R> c = tab[ii];
+                        const HD<R> c = tab[(ii & 255u) * SRC_ZC + (ii >> 8)];
                         const R impulse = c.h + (c.dh * ((R)(ph & 255u) / (R)256));
                         acc += (*xq * impulse);
                         xq += 1;

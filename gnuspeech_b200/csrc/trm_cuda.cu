@@ -550,9 +550,11 @@ int trm_cuda_ctx_create(int device, const trm_cuda_tables *t, trm_cuda_ctx **out
     {
         std::vector<trm::HD<double>> td(TRM_SRC_FILTER_LEN);
         std::vector<trm::HD<float>> tf(TRM_SRC_FILTER_LEN);
+        // phase-major: entry (l, k) = filter index l + 256 k sits at l * 13 + k, so the 13 taps of one wing are contiguous
         for (int i = 0; i < TRM_SRC_FILTER_LEN; ++i) {
-            td[i].h = t->src_h[i]; td[i].dh = t->src_dh[i];
-            tf[i].h = (float)t->src_h[i]; tf[i].dh = (float)t->src_dh[i];
+            const int at = (i & 255) * trm::SRC_ZC + (i >> 8);
+            td[at].h = t->src_h[i]; td[at].dh = t->src_dh[i];
+            tf[at].h = (float)t->src_h[i]; tf[at].dh = (float)t->src_dh[i];
         }
         CK(cudaMalloc(&c->d_tab_f64, td.size() * sizeof(td[0])));
         CK(cudaMalloc(&c->d_tab_f32, tf.size() * sizeof(tf[0])));

@@ -33,10 +33,10 @@ namespace trm {
 template <typename R> struct Wide;
 template <> struct Wide<float> {
     using Unit = float4;
-    static constexpr int MAX_PAIRS = 15;
+    static constexpr int MAX_PAIRS = 14;
     static constexpr int NF = 11;                    // 16-byte units per utterance-sample
     static constexpr int UP = 2 * MAX_PAIRS + 1;     // padded utterance dimension: odd -> conflict-free writers
-    static constexpr int THREADS = 32 * (1 + MAX_PAIRS);
+    static constexpr int THREADS = 32 * (2 + MAX_PAIRS);   // recurrence warp + feed-forward warps + one idle warp
     static constexpr int OUT_LD = 20;                // 16-byte aligned rows of the output transpose tile
 };
 template <> struct Wide<double> {
@@ -44,10 +44,15 @@ template <> struct Wide<double> {
     static constexpr int MAX_PAIRS = 14;
     static constexpr int NF = 12;
     static constexpr int UP = 2 * MAX_PAIRS + 1;
-    static constexpr int THREADS = 32 * (1 + MAX_PAIRS);
+    static constexpr int THREADS = 32 * (2 + MAX_PAIRS);
     static constexpr int OUT_LD = 18;
 };
 constexpr int WIDE_SLOTS = 2;
+// Warp w is scheduled by SM sub-partition w % 4, and the recurrence warp (warp 0) alone keeps its partition's FP64
+// pipe busy for ~2.6 feed-forward warps' worth of a block.  Warp WIDE_IDLE_WARP (same partition) therefore exits at
+// once and its pair moves to warp 15: partitions carry {recurrence + 2, 4, 4, 4} feed-forward warps instead of
+// {recurrence + 3, 4, 4, 3}.
+constexpr int WIDE_IDLE_WARP = 12;
 
 // feed-forward state of one utterance that must be in shared memory
 template <typename R>
@@ -58,7 +63,10 @@ struct alignas(16) FFHalf {
                                              // descriptor inside the block loop sat on the warp's critical path)
     double INC[TB];                          // oscillator increments of the block (conformance mode: every lane walks them)
     R HE[FIR_HIST + TB], HO[FIR_HIST + TB];  // oscillator history, even / odd 2x-rate samples
+    R pad[16 / sizeof(R)];                   // FP32: size = 64 mod 128 bytes, so the two utterances of a warp (adjacent
+                                             // FFHalf's, 16 consecutive floats each) read disjoint bank halves
 };
+static_assert(sizeof(FFHalf<float>) % 128 == 64, "FFHalf<float> must offset its neighbour by 16 banks");
 
 template <typename R>
 struct WideSmem {
@@ -156,7 +164,8 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
     }
     __syncthreads();
     const int64_t n_cta = W.n_cta;
-    if (n_cta <= 0 || warp > n_pairs) return;
+    const int pair = warp - 1 - (warp > WIDE_IDLE_WARP ? 1 : 0);
+    if (n_cta <= 0 || warp == WIDE_IDLE_WARP || pair >= n_pairs) return;
     const int n_blocks = (int)((n_cta + TB - 1) / TB);
 
     if (warp == 0) {
@@ -456,7 +465,6 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
     // feed-forward warp: utterances 2*pair and 2*pair+1 of the group, lane = sample of a 16-sample block
     // (phases S0 / A1 / S1 / A2 of tube_kernel.cuh; the results go to the ring instead of the ladder's tables)
     // =========================================================================================================
-    const int pair = warp - 1;
     const int half = lane >> 4, hl = lane & 15;
     const int ucol = 2 * pair + half;                     // column of this half's utterance in the ring
     FFHalf<R> &S = W.ff[ucol];
