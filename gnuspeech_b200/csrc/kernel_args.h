@@ -55,6 +55,7 @@ struct SrcArgs {
     void *out;                       // Real[]
     unsigned long long *maxbits;     // [n_utt] bit pattern of the running max |y| as double
     const void *table;               // HD<Real>[256][13]: filter index l + 256 k at [l][k]
+    const void *ctab;                // Real[65536][SRC_CLD]: interpolated coefficients per time-register fraction
     // work decomposition: tiles of <= 32 utterances that share the converter signature
     const int *tile_utt;             // [n_tiles][32] utterance index or -1
     const int *tile_nt;              // [n_tiles] outputs per work item of that tile (window fits SRC_ROWS)

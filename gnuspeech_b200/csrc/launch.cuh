@@ -97,6 +97,13 @@ template <typename R> static int launch_src(const SrcArgs &a, int grid, cudaStre
     return (int)cudaGetLastError();
 }
 
+template <typename R> static int launch_src_ctab(const void *tab, void *ctab, cudaStream_t s)
+{
+    const unsigned n = 65536u * SRC_CLD;
+    src_ctab_kernel<R><<<(n + 255) / 256, 256, 0, s>>>(reinterpret_cast<const HD<R> *>(tab), reinterpret_cast<R *>(ctab));
+    return (int)cudaGetLastError();
+}
+
 template <typename R> static int launch_pcm(const PcmArgs &a, long long max_n_out, cudaStream_t s)
 {
     if (a.n_utt <= 0 || max_n_out <= 0) return 0;
@@ -124,6 +131,10 @@ template <typename R> static int launch_pcm(const PcmArgs &a, long long max_n_ou
     extern "C" int trm_k_src_##SUF(const trm::SrcArgs *a, int grid, cudaStream_t s)                               \
     {                                                                                                             \
         return trm::launch_src<R>(*a, grid, s);                                                                   \
+    }                                                                                                             \
+    extern "C" int trm_k_src_ctab_##SUF(const void *tab, void *ctab, cudaStream_t s)                              \
+    {                                                                                                             \
+        return trm::launch_src_ctab<R>(tab, ctab, s);                                                             \
     }                                                                                                             \
     extern "C" int trm_k_pcm_##SUF(const trm::PcmArgs *a, long long max_n_out, cudaStream_t s)                    \
     {                                                                                                             \

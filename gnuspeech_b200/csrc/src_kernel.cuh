@@ -46,6 +46,10 @@ template <> struct Vec16<double> {
 template <typename R> __device__ __forceinline__ R r_abs(R x);
 template <> __device__ __forceinline__ double r_abs<double>(double x) { return fabs(x); }
 template <> __device__ __forceinline__ float r_abs<float>(float x) { return fabsf(x); }
+// max(a, b) that returns a when b is NaN (a is never NaN here): the (b > a) ? b : a of the reference's running maximum
+template <typename R> __device__ __forceinline__ R r_max(R a, R b);
+template <> __device__ __forceinline__ double r_max<double>(double a, double b) { return fmax(a, b); }
+template <> __device__ __forceinline__ float r_max<float>(float a, float b) { return fmaxf(a, b); }
 
 // One work item = one tile of 32 utterances with the same converter signature (time-register increment, pad,
 // direction, phase increment) x one run of `nt` consecutive output samples.  Lane = utterance: every lane of a
@@ -176,26 +180,29 @@ __global__ void __launch_bounds__(SRC_THREADS, sizeof(R) == 4 ? 3 : 2) src_kerne
         }
         const int run = nt / (SRC_THREADS / 32);                         // consecutive outputs per warp (multiple of SRC_CHUNK)
         if (up) {
-            // coefficient table of the item: C[n][t] = h[l + 256 k] + dH[l + 256 k] * (m / 256), (l, m) from the fraction F
-            // of output n's time register for the left wing (t = k) and from ~F for the right wing (t = 13 + k)
-            // (m:179-203).  One coefficient per thread and step: consecutive threads read consecutive entries of the
-            // phase-major filter table, and the loads of one thread are independent of each other.
-            const int n_coef = n_item * SRC_TAPS;
+            // coefficient rows of the item: output n has C[n][t] = h[l + 256 k] + dH[l + 256 k] * (m / 256), (l, m) from
+            // the fraction F of its time register for the left wing (t = k) and from ~F for the right wing (t = 13 + k)
+            // (m:179-203) -- a function of F alone, so the rows come from the context's table of all 65,536 fractions
+            // (src_ctab_kernel below; a few MB that stay in L2) as 16-byte vectors.  Column 26 of a row tells the walking
+            // warp what follows the output: 0 = same input position, 1 = the integer part of the time register advances
+            // (slide the window), 2 = last output of the warp's run.
+            constexpr int VR = SRC_CLD / A;                              // vectors per row
+            const unsigned rcp_run = (65536u + (unsigned)run - 1u) / (unsigned)run;
+            const int n_vec = n_item * VR;
+            const R *__restrict__ ct = reinterpret_cast<const R *>(args.ctab);
 #pragma unroll 4
-            for (int i = threadIdx.x; i < n_coef; i += SRC_THREADS) {
-                const int nr = i / SRC_TAPS, t = i - nr * SRC_TAPS;
-                const bool right = t >= SRC_ZC;
-                unsigned F = (frac0 + (unsigned)nr * tri) & 0xFFFFu;
-                if (right) F = (~F) & 0xFFFFu;
-                const HD<R> a = tab[(F >> 8) * SRC_ZC + (right ? t - SRC_ZC : t)];
-                Cf[nr * SRC_CLD + t] = a.h + a.dh * ((R)(F & 255u) / (R)256);
-            }
-            // column 26 of a row tells the walking warp what follows the output: 0 = same input position, 1 = the
-            // integer part of the time register advances (slide the window), 2 = last output of the warp's run
-            for (int nr = threadIdx.x; nr < n_item; nr += SRC_THREADS) {
+            for (int i = threadIdx.x; i < n_vec; i += SRC_THREADS) {
+                const int nr = i / VR, q = i - nr * VR;
                 const unsigned f = frac0 + (unsigned)nr * tri;
-                const bool last = (nr + 1 == n_item) || ((nr + 1) % run == 0);
-                Cf[nr * SRC_CLD + SRC_TAPS] = last ? (R)2 : ((((f + tri) >> 16) != (f >> 16)) ? (R)1 : (R)0);
+                Vec16<R> v;
+                v.load(ct + (size_t)(f & 0xFFFFu) * SRC_CLD + A * q);
+                if (q == SRC_TAPS / A) {
+                    // (nr + 1) % run == 0 without a division: floor(n / run) = (n * ceil(2^16 / run)) >> 16 for n <= 256, run >= 8
+                    const unsigned k = ((unsigned)(nr + 1) * rcp_run) >> 16;
+                    const bool last = (nr + 1 == n_item) || (k * (unsigned)run == (unsigned)(nr + 1));
+                    v.e[SRC_TAPS % A] = last ? (R)2 : ((((f + tri) >> 16) != (f >> 16)) ? (R)1 : (R)0);
+                }
+                v.store(Cf + nr * SRC_CLD + A * q);
             }
         }
         __syncthreads();                                                 // descriptors + coefficients visible
@@ -314,8 +321,7 @@ __global__ void __launch_bounds__(SRC_THREADS, sizeof(R) == 4 ? 3 : 2) src_kerne
                             }
                             ys[j] = acc;
                             if constexpr (INTERIOR) {
-                                const R av = r_abs<R>(acc);
-                                local_max = (av > local_max) ? av : local_max;   // NaN never wins, like the reference
+                                local_max = r_max<R>(local_max, r_abs<R>(acc));   // NaN never wins, like the reference
                             } else {
                                 const R av = (nr < my_out && nr >= my_lo) ? r_abs<R>(acc) : (R)0;
                                 local_max = (av > local_max) ? av : local_max;
@@ -377,6 +383,25 @@ __global__ void __launch_bounds__(SRC_THREADS, sizeof(R) == 4 ? 3 : 2) src_kerne
         }
     }
     if (item_hi > item_lo) flush_max();
+}
+
+// All interpolated filter coefficients of the up-sampling converter: row F (the 16-bit fraction of the time register)
+// holds the 13 left-wing and 13 right-wing coefficients of an output with that fraction, computed with the reference's two
+// operations per coefficient (TRMSampleRateConverter.m:179-203).  Built once per context.
+template <typename R>
+__global__ void src_ctab_kernel(const HD<R> *__restrict__ tab, R *__restrict__ ctab)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned row = i / SRC_CLD, t = i - row * SRC_CLD;
+    if (row >= 65536u) return;
+    R c = (R)0;
+    if (t < (unsigned)SRC_TAPS) {
+        const bool right = t >= (unsigned)SRC_ZC;
+        const unsigned F = right ? ((~row) & 0xFFFFu) : row;
+        const HD<R> a = tab[(F >> 8) * SRC_ZC + (right ? t - SRC_ZC : t)];
+        c = a.h + a.dh * ((R)(F & 255u) / (R)256);
+    }
+    ctab[i] = c;
 }
 
 template <typename R>

@@ -26,6 +26,8 @@ int trm_k_tube_wide_f64(const trm::TubeArgs *, int, cudaStream_t);
 int trm_k_tube_wide_f32(const trm::TubeArgs *, int, cudaStream_t);
 int trm_k_src_f64(const trm::SrcArgs *, int, cudaStream_t);
 int trm_k_src_f32(const trm::SrcArgs *, int, cudaStream_t);
+int trm_k_src_ctab_f64(const void *, void *, cudaStream_t);
+int trm_k_src_ctab_f32(const void *, void *, cudaStream_t);
 int trm_k_pcm_f64(const trm::PcmArgs *, long long, cudaStream_t);
 int trm_k_pcm_f32(const trm::PcmArgs *, long long, cudaStream_t);
 int trm_k_framegen(const trm::FrameGenArgs *, cudaStream_t);
@@ -203,6 +205,7 @@ struct trm_cuda_ctx {
     std::vector<double> wt_host;      // what d_wavetables holds
     Arena gen;                        // frame generator: events, descriptors, generated frames
     void *d_tab_f64 = nullptr, *d_tab_f32 = nullptr;
+    void *d_ctab_f64 = nullptr, *d_ctab_f32 = nullptr;   // interpolated converter coefficients per time-register fraction
     uint64_t noise_k0 = 0;
     trm::KernelInfo info64{}, info32{};
     cudaStream_t streams[MAX_SLOTS]{};
@@ -412,6 +415,7 @@ int launch_stage(trm_cuda_ctx *ctx, int precision, int stage, const DeviceChunk 
         trm::SrcArgs a{};
         a.desc = dc.desc; a.n_utt = dc.n; a.tube = dc.tube; a.out = dc.out; a.maxbits = dc.maxbits;
         a.table = f64 ? ctx->d_tab_f64 : ctx->d_tab_f32;
+        a.ctab = f64 ? ctx->d_ctab_f64 : ctx->d_ctab_f32;
         a.tile_utt = dc.tile_utt; a.tile_nt = dc.tile_nt; a.tile_max_out = dc.tile_max_out; a.tile_first_out = dc.tile_first_out;
         a.item_base = dc.item_base;
         a.n_tiles = dc.n_tiles; a.total_items = dc.total_items;
@@ -560,6 +564,13 @@ int trm_cuda_ctx_create(int device, const trm_cuda_tables *t, trm_cuda_ctx **out
         CK(cudaMalloc(&c->d_tab_f32, tf.size() * sizeof(tf[0])));
         CK(cudaMemcpy(c->d_tab_f64, td.data(), td.size() * sizeof(td[0]), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->d_tab_f32, tf.data(), tf.size() * sizeof(tf[0]), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&c->d_ctab_f64, (size_t)65536 * trm::SRC_CLD * sizeof(double)));
+        CK(cudaMalloc(&c->d_ctab_f32, (size_t)65536 * trm::SRC_CLD * sizeof(float)));
+        if ((rc = trm_k_src_ctab_f64(c->d_tab_f64, c->d_ctab_f64, 0)) != 0 || (rc = trm_k_src_ctab_f32(c->d_tab_f32, c->d_ctab_f32, 0)) != 0) {
+            delete c;
+            return fail("converter coefficient table", (cudaError_t)rc);
+        }
+        CK(cudaDeviceSynchronize());
     }
     {
         // streams[2] = copy-out of the chunk pipeline (trm_cuda_synthesize_host); frames and kernels go to the device's
@@ -623,6 +634,8 @@ void trm_cuda_ctx_destroy(trm_cuda_ctx *c)
     if (c->d_wavetables) cudaFree(c->d_wavetables);
     if (c->d_tab_f64) cudaFree(c->d_tab_f64);
     if (c->d_tab_f32) cudaFree(c->d_tab_f32);
+    if (c->d_ctab_f64) cudaFree(c->d_ctab_f64);
+    if (c->d_ctab_f32) cudaFree(c->d_ctab_f32);
     delete c;
 }
 
@@ -1002,6 +1015,7 @@ int trm_cuda_stream_push(trm_cuda_stream *s, const double *frames_host, int m, i
         trm::SrcArgs a{};
         a.desc = dc.desc; a.n_utt = n; a.tube = s->d_tube[s->cur]; a.out = s->d_out; a.maxbits = dc.maxbits;
         a.table = f64 ? ctx->d_tab_f64 : ctx->d_tab_f32;
+        a.ctab = f64 ? ctx->d_ctab_f64 : ctx->d_ctab_f32;
         a.tile_utt = dc.tile_utt; a.tile_nt = dc.tile_nt; a.tile_max_out = dc.tile_max_out; a.tile_first_out = dc.tile_first_out;
         a.item_base = dc.item_base; a.n_tiles = dc.n_tiles; a.total_items = dc.total_items;
         const int grid = ctx->sm_count * std::max(1, ki.src_ctas_per_sm);
