@@ -57,7 +57,7 @@ struct SrcArgs {
     const void *table;               // HD<Real>[256][13]: filter index l + 256 k at [l][k]
     const void *ctab;                // Real[65536][SRC_CLD]: interpolated coefficients per time-register fraction
     // work decomposition: tiles of <= 32 utterances that share the converter signature
-    const int *tile_utt;             // [n_tiles][32] utterance index or -1
+    const int *tile_utt;             // [n_tiles][tile width] utterance index or -1 (width: KernelInfo.src_tile)
     const int *tile_nt;              // [n_tiles] outputs per work item of that tile (window fits SRC_ROWS)
     const long long *tile_max_out;   // [n_tiles] longest utterance of the tile
     const long long *tile_first_out; // [n_tiles] first output of the tile's first work item (0 unless streaming)
@@ -94,6 +94,7 @@ struct KernelInfo {
     int src_smem_bytes;
     int src_threads;
     int src_ctas_per_sm;
+    int src_tile;                  // utterances per resampler tile (32 x utterances per lane)
     int tube_ctas_per_sm;
     int tube_regs, src_regs, pcm_regs;
     int wide_smem_bytes, wide_threads, wide_max_utt, wide_regs;   // batch-throughput waveguide mapping (tube_wide.cuh)

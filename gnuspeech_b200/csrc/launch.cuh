@@ -13,7 +13,8 @@ namespace trm {
 
 template <typename R> constexpr int src_smem_bytes()
 {
-    return (32 * SRC_XLD + SRC_NT_MAX * SRC_CLD + (SRC_THREADS / 32) * 32 * (SRC_CHUNK + 1)) * (int)sizeof(R);
+    return (SrcCfg<R>::WINDOWS * SrcCfg<R>::TILE * SRC_XLD + SRC_NT_MAX * SRC_CLD + (SRC_THREADS / 32) * SrcCfg<R>::TILE * (SRC_CHUNK + 1)) *
+           (int)sizeof(R);
 }
 
 template <typename R> static int configure_kernels(KernelInfo *info)
@@ -43,6 +44,7 @@ template <typename R> static int configure_kernels(KernelInfo *info)
         info->tube_utt_per_cta = UTT_PER_CTA;
         info->src_smem_bytes = src_smem;
         info->src_threads = SRC_THREADS;
+        info->src_tile = SrcCfg<R>::TILE;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&info->src_ctas_per_sm, src_kernel<R>, SRC_THREADS, src_smem);
         if (e != cudaSuccess) return (int)e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&info->tube_ctas_per_sm, tube_kernel<R>, WARPS_PER_CTA * 32, tube_smem);

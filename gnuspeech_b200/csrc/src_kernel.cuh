@@ -43,6 +43,18 @@ template <> struct Vec16<double> {
     __device__ __forceinline__ void store(double *p) const { *reinterpret_cast<double2 *>(p) = make_double2(e[0], e[1]); }
 };
 
+// Shape of the resampler per precision.  U = utterances per lane: a coefficient read from shared memory (a broadcast
+// 16-byte load returns 512 bytes to the warp's registers, and the SM delivers 128 bytes per clock) serves U multiply-adds;
+// with U = 1 that return path, not the arithmetic, bounded both precisions.  The FP64 register window (26 doubles per
+// utterance) leaves room for one utterance per lane only.  WINDOWS = 2 prefetches the next work item's window into a
+// second buffer (measured: no gain, the copy latency was already hidden by the other CTAs of the SM).
+template <typename R> struct SrcCfg {
+    static constexpr int U = sizeof(R) == 4 ? 2 : 1;
+    static constexpr int TILE = 32 * U;                 // utterances per tile
+    static constexpr int WINDOWS = 1;
+    static constexpr int MIN_CTAS = 2;
+};
+
 template <typename R> __device__ __forceinline__ R r_abs(R x);
 template <> __device__ __forceinline__ double r_abs<double>(double x) { return fabs(x); }
 template <> __device__ __forceinline__ float r_abs<float>(float x) { return fabsf(x); }
@@ -71,25 +83,31 @@ template <> __device__ __forceinline__ float r_max<float>(float a, float b) { re
 // Accumulation order (left wing first, newest -> oldest, from 0.0) is the reference's; one multiply and one add per
 // tap.  Outputs go back through a small per-warp transpose tile and leave as 128-bit stores.
 template <typename R>
-__global__ void __launch_bounds__(SRC_THREADS, sizeof(R) == 4 ? 3 : 2) src_kernel(SrcArgs args)
+__global__ void __launch_bounds__(SRC_THREADS, SrcCfg<R>::MIN_CTAS) src_kernel(SrcArgs args)
 {
     constexpr int A = 16 / (int)sizeof(R);                               // elements per 16 bytes
     constexpr int YLD = SRC_CHUNK + 1;
+    constexpr int U = SrcCfg<R>::U, TW = SrcCfg<R>::TILE;
+    constexpr int NBUF = SrcCfg<R>::WINDOWS;
+    constexpr unsigned FULL = 0xFFFFFFFFu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    R *xU = reinterpret_cast<R *>(smem_raw);                             // [32][SRC_XLD] input windows, utterance-major
-    R *Cf = xU + 32 * SRC_XLD;                                           // [SRC_NT_MAX][SRC_CLD] coefficients
-    R *yT = Cf + SRC_NT_MAX * SRC_CLD;                                   // [warps][32][YLD]
-    __shared__ long long s_tube_off[32], s_out_off[32], s_n_in[32], s_n_out[32], s_out_start[32], s_in_start[32];
+    R *xU0 = reinterpret_cast<R *>(smem_raw);                            // [NBUF][TW][SRC_XLD] input windows, utterance-major
+    R *Cf = xU0 + NBUF * TW * SRC_XLD;                                   // [SRC_NT_MAX][SRC_CLD] coefficients
+    R *yT = Cf + SRC_NT_MAX * SRC_CLD;                                   // [warps][TW][YLD]
+    __shared__ long long s_tube_off[TW], s_out_off[TW], s_n_in[TW], s_n_out[TW], s_out_start[TW], s_in_start[TW];
     __shared__ int s_tile;
-    __shared__ unsigned long long s_bar;
+    __shared__ unsigned long long s_bar[2];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const HD<R> *__restrict__ tab = reinterpret_cast<const HD<R> *>(args.table);
     if (threadIdx.x == 0) {
-        mbar_init(&s_bar, 1);
+        mbar_init(&s_bar[0], U);                                         // one arrival per requesting warp
+        mbar_init(&s_bar[1], U);
         mbar_fence_init();
     }
-    uint32_t bar_phase = 0;
+    uint32_t bar_phase = 0;                                              // bit b: parity to wait for on s_bar[b]
+    int buf = 0;                                                         // window buffer of the current item
+    bool in_flight = false;                                              // its window was requested during the previous item
 
     // every CTA takes a contiguous range of work items: consecutive items belong to the same tile, whose descriptors
     // are read from global memory once and kept in shared memory
@@ -103,14 +121,20 @@ __global__ void __launch_bounds__(SRC_THREADS, sizeof(R) == 4 ? 3 : 2) src_kerne
     bool up = true;
     double ratio = 1.0;
     long long tile_max = 0, tile_out0 = 0;
-    R local_max = (R)0;
+    // lane l owns the utterances in rows l, l + 32, .. of the tile
+    R local_max[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) local_max[k] = (R)0;
     auto flush_max = [&]() {
         // per-utterance maximum: integer atomicMax on the bit pattern (order independent for non-negative doubles)
-        if (local_max > (R)0) {
-            const int u = args.tile_utt[tile * 32 + lane];
-            if (u >= 0) atomicMax(args.maxbits + u, (unsigned long long)__double_as_longlong((double)local_max));
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            if (local_max[k] > (R)0) {
+                const int u = args.tile_utt[tile * TW + lane + 32 * k];
+                if (u >= 0) atomicMax(args.maxbits + u, (unsigned long long)__double_as_longlong((double)local_max[k]));
+            }
+            local_max[k] = (R)0;
         }
-        local_max = (R)0;
     };
 
     for (long long item = item_lo; item < item_hi; ++item) {
@@ -127,18 +151,19 @@ __global__ void __launch_bounds__(SRC_THREADS, sizeof(R) == 4 ? 3 : 2) src_kerne
             }
             __syncthreads();
             tile = s_tile;
-            if (warp == 0) {
-                const int u = args.tile_utt[tile * 32 + lane];
+            if (warp < U) {
+                const int row = warp * 32 + lane;
+                const int u = args.tile_utt[tile * TW + row];
                 const trm_cuda_utterance *D = args.desc + (u >= 0 ? u : 0);
-                s_tube_off[lane] = D->tube_offset;
-                s_out_off[lane] = D->out_offset;
-                s_n_in[lane] = u >= 0 ? D->n_tube : -1;
-                s_n_out[lane] = u >= 0 ? D->n_out : 0;
-                s_out_start[lane] = u >= 0 ? D->out_start : 0;      // streaming: earlier outputs exist already,
-                s_in_start[lane] = u >= 0 ? D->in_start : 0;        // earlier inputs are no longer in memory
+                s_tube_off[row] = D->tube_offset;
+                s_out_off[row] = D->out_offset;
+                s_n_in[row] = u >= 0 ? D->n_tube : -1;
+                s_n_out[row] = u >= 0 ? D->n_out : 0;
+                s_out_start[row] = u >= 0 ? D->out_start : 0;       // streaming: earlier outputs exist already,
+                s_in_start[row] = u >= 0 ? D->in_start : 0;         // earlier inputs are no longer in memory
             }
             // signature of the tile (row 0 is always a real utterance)
-            const trm_cuda_utterance *__restrict__ D0 = args.desc + args.tile_utt[tile * 32];
+            const trm_cuda_utterance *__restrict__ D0 = args.desc + args.tile_utt[tile * TW];
             tri = D0->tri;
             pad = D0->padSize; reach = pad + 1;
             up = D0->upsample != 0;
@@ -151,33 +176,48 @@ __global__ void __launch_bounds__(SRC_THREADS, sizeof(R) == 4 ? 3 : 2) src_kerne
             tile_out0 = args.tile_first_out[tile];
             __syncthreads();
         }
-        const long long n_s = tile_out0 + (item - tile_first) * nt;
-        const int n_item = (int)((n_s + nt < tile_max) ? nt : tile_max - n_s);         // outputs of this item
-        const unsigned long long T0 = (unsigned long long)n_s * tri;
-        const long long P0 = (long long)(T0 >> 16);
-        const unsigned frac0 = (unsigned)(T0 & 0xFFFFull);
-        const int rows = (int)((((unsigned long long)frac0 + (unsigned long long)(n_item - 1) * tri) >> 16)) + 2 * reach + 2;
-        // window of utterance r: elements q0 .. q0+rows-1 of its tube-rate signal, q = p - pad (xb[p] = x[p - pad])
-        const long long q0 = P0 - reach - pad;
-        const long long qb = (q0 >= 0) ? q0 / A * A : -((-q0 + A - 1) / A * A);        // 16-byte aligned start (floor)
-        const int off = (int)(q0 - qb);                                                // window element i sits at xU[r][off + i]
-        const int span = (off + rows + A - 1) / A * A;
-        if (warp == 0) {
-            // bulk copy of [lo, hi) (clipped to the utterance's 16-byte-padded extent)
-            const long long n_in = s_n_in[lane];
+        // geometry of a work item of the current tile: its outputs and the window of input samples under them
+        struct Geo { long long n_s, P0, q0, qb; int n_item, off, span; unsigned frac0; };
+        auto geometry = [&](long long it) {
+            Geo g;
+            g.n_s = tile_out0 + (it - tile_first) * nt;
+            g.n_item = (int)((g.n_s + nt < tile_max) ? nt : tile_max - g.n_s);         // outputs of this item
+            const unsigned long long T0 = (unsigned long long)g.n_s * tri;
+            g.P0 = (long long)(T0 >> 16);
+            g.frac0 = (unsigned)(T0 & 0xFFFFull);
+            const int rows = (int)((((unsigned long long)g.frac0 + (unsigned long long)(g.n_item - 1) * tri) >> 16)) + 2 * reach + 2;
+            // window of utterance r: elements q0 .. q0+rows-1 of its tube-rate signal, q = p - pad (xb[p] = x[p - pad])
+            g.q0 = g.P0 - reach - pad;
+            g.qb = (g.q0 >= 0) ? g.q0 / A * A : -((-g.q0 + A - 1) / A * A);            // 16-byte aligned start (floor)
+            g.off = (int)(g.q0 - g.qb);                                                // window element i sits at xU[r][off + i]
+            g.span = (g.off + rows + A - 1) / A * A;
+            return g;
+        };
+        // warps 0..U-1: bulk copies of [lo, hi) of every utterance (clipped to its 16-byte-padded extent) into window buffer b
+        auto request_window = [&](const Geo &g, int b) {
+            const int row = warp * 32 + lane;
+            const long long n_in = s_n_in[row];
             const long long n_al = (n_in + A - 1) / A * A;
-            long long lo = qb > 0 ? qb : 0;
-            if (lo < s_in_start[lane]) lo = s_in_start[lane];            // (a multiple of A; only discarded outputs look below it)
-            const long long hi = (qb + span < n_al) ? qb + span : n_al;
+            long long lo = g.qb > 0 ? g.qb : 0;
+            if (lo < s_in_start[row]) lo = s_in_start[row];              // (a multiple of A; only discarded outputs look below it)
+            const long long hi = (g.qb + g.span < n_al) ? g.qb + g.span : n_al;
             const unsigned bytes = (hi > lo) ? (unsigned)(hi - lo) * (unsigned)sizeof(R) : 0u;
             unsigned total = bytes;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
-            if (lane == 0) mbar_expect_tx(&s_bar, total);
+            for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(FULL, total, o);
+            if (lane == 0) mbar_expect_tx(&s_bar[b], total);
             __syncwarp();
             if (bytes)
-                tma_bulk_g2s(xU + lane * SRC_XLD + (int)(lo - qb), reinterpret_cast<const R *>(args.tube) + s_tube_off[lane] + lo, bytes, &s_bar);
-        }
+                tma_bulk_g2s(xU0 + (b * TW + row) * SRC_XLD + (int)(lo - g.qb), reinterpret_cast<const R *>(args.tube) + s_tube_off[row] + lo,
+                             bytes, &s_bar[b]);
+        };
+        const Geo geo = geometry(item);
+        const long long n_s = geo.n_s, P0 = geo.P0, q0 = geo.q0, qb = geo.qb;
+        const int n_item = geo.n_item, off = geo.off, span = geo.span;
+        const unsigned frac0 = geo.frac0;
+        const unsigned long long T0 = (unsigned long long)n_s * tri;
+        R *const xU = xU0 + buf * TW * SRC_XLD;
+        if (warp < U && !in_flight) request_window(geo, buf);
         const int run = nt / (SRC_THREADS / 32);                         // consecutive outputs per warp (multiple of SRC_CHUNK)
         if (up) {
             // coefficient rows of the item: output n has C[n][t] = h[l + 256 k] + dH[l + 256 k] * (m / 256), (l, m) from
@@ -206,14 +246,19 @@ __global__ void __launch_bounds__(SRC_THREADS, sizeof(R) == 4 ? 3 : 2) src_kerne
             }
         }
         __syncthreads();                                                 // descriptors + coefficients visible
-        mbar_wait(&s_bar, bar_phase);
-        bar_phase ^= 1u;
+        // (WINDOWS = 2) the next item's window is requested now and lands while this item is computed; its buffer was last
+        // read by the item before this one, which every warp has left
+        const bool prefetch = NBUF == 2 && item + 1 < item_hi && item + 1 < tile_end;
+        if (prefetch && warp < U) request_window(geometry(item + 1), buf ^ 1);
+        mbar_wait(&s_bar[buf], (bar_phase >> buf) & 1u);
+        bar_phase ^= 1u << buf;
         {
             // zero-fill outside [0, n_in): only the first / last items of an utterance have such positions
-            const long long n_in = s_n_in[lane];
-            const bool mine = (q0 < 0) || (qb + span > n_in);
-            if (__any_sync(0xFFFFFFFFu, mine)) {
-                for (int r = warp; r < 32; r += SRC_THREADS / 32) {
+            bool mine = false;
+#pragma unroll
+            for (int k = 0; k < U; ++k) mine = mine || (q0 < 0) || (qb + span > s_n_in[lane + 32 * k]);
+            if (__any_sync(FULL, mine)) {
+                for (int r = warp; r < TW; r += SRC_THREADS / 32) {
                     const long long nin = s_n_in[r];
                     if (qb >= 0 && qb + span <= nin) continue;
                     for (int i = lane; i < span; i += 32) {
@@ -225,44 +270,54 @@ __global__ void __launch_bounds__(SRC_THREADS, sizeof(R) == 4 ? 3 : 2) src_kerne
             }
         }
 
-        const int my_out = (int)((s_n_out[lane] - n_s < (long long)n_item) ? (s_n_out[lane] - n_s > 0 ? s_n_out[lane] - n_s : 0) : n_item);
-        const int my_lo = (int)((s_out_start[lane] - n_s > 0) ? ((s_out_start[lane] - n_s < (long long)n_item) ? s_out_start[lane] - n_s : n_item) : 0);
-        R *yw = yT + warp * (32 * YLD);
-        const R *xl = xU + lane * SRC_XLD + off;                         // xl[i] = window element i of this lane's utterance
+        // this lane's utterances: outputs [my_lo, my_out) of the item are theirs to produce
+        int my_out[U], my_lo[U];
+        bool all_mine = true;
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const long long no = s_n_out[lane + 32 * k] - n_s, os = s_out_start[lane + 32 * k] - n_s;
+            my_out[k] = (int)((no < (long long)n_item) ? (no > 0 ? no : 0) : n_item);
+            my_lo[k] = (int)((os > 0) ? ((os < (long long)n_item) ? os : n_item) : 0);
+            all_mine = all_mine && my_lo[k] == 0 && my_out[k] == n_item;
+        }
+        R *yw = yT + warp * (TW * YLD);
+        const R *xl = xU + lane * SRC_XLD + off;                         // xl[32 k SRC_XLD + i] = window element i of utterance k
         if (up) {
             const int nr_first = warp * run;
             // every utterance of the tile has all outputs of this item and none of them exists already (streaming):
             // no per-output or per-piece range checks
-            const bool interior = __all_sync(0xFFFFFFFFu, my_lo == 0 && my_out == n_item);
+            const bool interior = __all_sync(FULL, all_mine);
             // Register window of the 26 input samples under the filter.  Logical element i (= xb[P - 12 + i]; left wing
             // xb[P-k] is i = 12-k, right wing xb[P+1+k] is i = 13+k) lives in register W[(i + ph) % 26] where ph is the
             // window phase.  When the integer part P of the time register advances, the oldest sample's register
             // receives the new one and ph increases: the loop below is unrolled over the 26 phases, so every register
             // index is a compile-time constant and sliding the window costs one shared-memory load and no moves.
             // xb[P0 + Prel + d] is window element reach + Prel + d.
-            R W[SRC_TAPS];
+            R W[U][SRC_TAPS];
             int nr = nr_first;
             const int Pc0 = (int)((frac0 + (unsigned)(nr_first < n_item ? nr_first : 0) * tri) >> 16);
-            {
-                const R *xp = xl + (reach - (SRC_ZC - 1)) + Pc0;
 #pragma unroll
-                for (int i = 0; i < SRC_TAPS; ++i) W[i] = xp[i];
+            for (int k = 0; k < U; ++k) {
+                const R *xp = xl + 32 * k * SRC_XLD + (reach - (SRC_ZC - 1)) + Pc0;
+#pragma unroll
+                for (int i = 0; i < SRC_TAPS; ++i) W[k][i] = xp[i];
             }
             const R *xn = xl + reach + SRC_ZC + Pc0;                     // newest window element; the next one enters on a slide
             const R *crow = Cf + nr_first * SRC_CLD;
-            R *const ys = yw + lane * YLD;
+            R *const ys = yw + lane * YLD;                               // utterance k: row lane + 32 k of the warp's tile
             int c0 = nr_first, j = 0;                                    // start of the current write-back chunk, outputs in it
             constexpr int PIECES = SRC_CHUNK / A;                        // 16-byte pieces per utterance and chunk
-            // piece i of this lane: utterance row (32 / PIECES) * i + lane / PIECES, elements A * (lane % PIECES) ..
-            R *dstp[PIECES];
+            constexpr int NP = U * PIECES;                               // pieces per lane and chunk
+            // piece i of this lane: tile row (32 / PIECES) * i + lane / PIECES, elements A * (lane % PIECES) ..
+            R *dstp[NP];
 #pragma unroll
-            for (int i = 0; i < PIECES; ++i)
+            for (int i = 0; i < NP; ++i)
                 dstp[i] = reinterpret_cast<R *>(args.out) + s_out_off[(32 / PIECES) * i + lane / PIECES] + n_s + nr_first + A * (lane % PIECES);
             auto write_back = [&](bool fast) {
                 __syncwarp();
                 if (fast) {
 #pragma unroll
-                    for (int i = 0; i < PIECES; ++i) {
+                    for (int i = 0; i < NP; ++i) {
                         const R *src = yw + ((32 / PIECES) * i + lane / PIECES) * YLD + A * (lane % PIECES);
                         Vec16<R> v;
 #pragma unroll
@@ -271,7 +326,7 @@ __global__ void __launch_bounds__(SRC_THREADS, sizeof(R) == 4 ? 3 : 2) src_kerne
                     }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < PIECES; ++i) {
+                    for (int i = 0; i < NP; ++i) {
                         const int r = (32 / PIECES) * i + lane / PIECES, part = lane % PIECES;
                         const long long left = s_n_out[r] - (n_s + c0) - A * part;        // valid samples from this piece on
                         const long long skip = s_out_start[r] - (n_s + c0) - A * part;   // leading samples that exist already
@@ -292,7 +347,7 @@ __global__ void __launch_bounds__(SRC_THREADS, sizeof(R) == 4 ? 3 : 2) src_kerne
                 }
                 __syncwarp();
 #pragma unroll
-                for (int i = 0; i < PIECES; ++i) dstp[i] += j;
+                for (int i = 0; i < NP; ++i) dstp[i] += j;
                 c0 += j;
                 j = 0;
             };
@@ -304,8 +359,11 @@ __global__ void __launch_bounds__(SRC_THREADS, sizeof(R) == 4 ? 3 : 2) src_kerne
                         R flag;
                         do {
                             // coefficient row: broadcast 128-bit loads, consumed as they arrive (tap t: t < 13 is the left
-                            // wing, logical element 12-t; else the right wing, logical element t)
-                            R acc = (R)0;
+                            // wing, logical element 12-t; else the right wing, logical element t); every coefficient
+                            // serves the lane's U utterances
+                            R acc[U];
+#pragma unroll
+                            for (int k = 0; k < U; ++k) acc[k] = (R)0;
                             flag = (R)0;
 #pragma unroll
                             for (int q = 0; q < (SRC_TAPS + 1 + A - 1) / A; ++q) {
@@ -314,25 +372,33 @@ __global__ void __launch_bounds__(SRC_THREADS, sizeof(R) == 4 ? 3 : 2) src_kerne
 #pragma unroll
                                 for (int e = 0; e < A; ++e) {
                                     const int t = A * q + e;
-                                    if (t < SRC_ZC) acc += W[(SRC_ZC - 1 - t + ph) % SRC_TAPS] * cq.e[e];
-                                    else if (t < SRC_TAPS) acc += W[(t + ph) % SRC_TAPS] * cq.e[e];
-                                    else if (t == SRC_TAPS) flag = cq.e[e];
+#pragma unroll
+                                    for (int k = 0; k < U; ++k) {
+                                        if (t < SRC_ZC) acc[k] += W[k][(SRC_ZC - 1 - t + ph) % SRC_TAPS] * cq.e[e];
+                                        else if (t < SRC_TAPS) acc[k] += W[k][(t + ph) % SRC_TAPS] * cq.e[e];
+                                    }
+                                    if (t == SRC_TAPS) flag = cq.e[e];
                                 }
                             }
-                            ys[j] = acc;
-                            if constexpr (INTERIOR) {
-                                local_max = r_max<R>(local_max, r_abs<R>(acc));   // NaN never wins, like the reference
-                            } else {
-                                const R av = (nr < my_out && nr >= my_lo) ? r_abs<R>(acc) : (R)0;
-                                local_max = (av > local_max) ? av : local_max;
-                                ++nr;
+#pragma unroll
+                            for (int k = 0; k < U; ++k) {
+                                ys[32 * k * YLD + j] = acc[k];
+                                if constexpr (INTERIOR) {
+                                    local_max[k] = r_max<R>(local_max[k], r_abs<R>(acc[k]));   // NaN never wins, like the reference
+                                } else {
+                                    const R av = (nr < my_out[k] && nr >= my_lo[k]) ? r_abs<R>(acc[k]) : (R)0;
+                                    local_max[k] = (av > local_max[k]) ? av : local_max[k];
+                                }
                             }
+                            if constexpr (!INTERIOR) ++nr;
                             crow += SRC_CLD;
                             if (++j == SRC_CHUNK) write_back(INTERIOR);
                         } while (flag == (R)0);
                         if (flag == (R)2) return;
                         // slide: logical element 0 (register ph) leaves, xb[P + 14] enters as logical element 25 of phase ph+1
-                        W[ph] = *++xn;
+                        ++xn;
+#pragma unroll
+                        for (int k = 0; k < U; ++k) W[k][ph] = xn[32 * k * SRC_XLD];
                     }
                 }
             };
@@ -348,32 +414,35 @@ __global__ void __launch_bounds__(SRC_THREADS, sizeof(R) == 4 ? 3 : 2) src_kerne
                     const unsigned long long T = T0 + (unsigned long long)(c0 + j) * tri;
                     const int base = (int)((long long)(T >> 16) - P0) + reach;
                     const unsigned F = (unsigned)(T & 0xFFFFull);
-                    R acc = (R)0;
-                    unsigned ph = (unsigned)rint((double)F * ratio), ii;
-                    const R *xq = xl + base;
-                    while ((ii = (ph >> 8)) < (unsigned)TRM_SRC_FILTER_LEN) {
-                        const HD<R> c = tab[(ii & 255u) * SRC_ZC + (ii >> 8)];
-                        const R impulse = c.h + (c.dh * ((R)(ph & 255u) / (R)256));
-                        acc += (*xq * impulse);
-                        xq -= 1;
-                        ph += phaseIncrement;
+#pragma unroll
+                    for (int k = 0; k < U; ++k) {
+                        R acc = (R)0;
+                        unsigned ph = (unsigned)rint((double)F * ratio), ii;
+                        const R *xq = xl + 32 * k * SRC_XLD + base;
+                        while ((ii = (ph >> 8)) < (unsigned)TRM_SRC_FILTER_LEN) {
+                            const HD<R> c = tab[(ii & 255u) * SRC_ZC + (ii >> 8)];
+                            const R impulse = c.h + (c.dh * ((R)(ph & 255u) / (R)256));
+                            acc += (*xq * impulse);
+                            xq -= 1;
+                            ph += phaseIncrement;
+                        }
+                        ph = (unsigned)rint((double)((~F) & 0xFFFFu) * ratio);
+                        xq = xl + 32 * k * SRC_XLD + base + 1;
+                        while ((ii = (ph >> 8)) < (unsigned)TRM_SRC_FILTER_LEN) {
+                            const HD<R> c = tab[(ii & 255u) * SRC_ZC + (ii >> 8)];
+                            const R impulse = c.h + (c.dh * ((R)(ph & 255u) / (R)256));
+                            acc += (*xq * impulse);
+                            xq += 1;
+                            ph += phaseIncrement;
+                        }
+                        yw[(lane + 32 * k) * YLD + j] = acc;
+                        const R av = (c0 + j < my_out[k] && c0 + j >= my_lo[k]) ? r_abs<R>(acc) : (R)0;
+                        local_max[k] = (av > local_max[k]) ? av : local_max[k];
                     }
-                    ph = (unsigned)rint((double)((~F) & 0xFFFFu) * ratio);
-                    xq = xl + base + 1;
-                    while ((ii = (ph >> 8)) < (unsigned)TRM_SRC_FILTER_LEN) {
-                        const HD<R> c = tab[(ii & 255u) * SRC_ZC + (ii >> 8)];
-                        const R impulse = c.h + (c.dh * ((R)(ph & 255u) / (R)256));
-                        acc += (*xq * impulse);
-                        xq += 1;
-                        ph += phaseIncrement;
-                    }
-                    yw[lane * YLD + j] = acc;
-                    const R av = (c0 + j < my_out && c0 + j >= my_lo) ? r_abs<R>(acc) : (R)0;
-                    local_max = (av > local_max) ? av : local_max;
                 }
                 __syncwarp();
 #pragma unroll
-                for (int i = 0; i < SRC_CHUNK; ++i) {
+                for (int i = 0; i < U * SRC_CHUNK; ++i) {
                     const int r = (32 / SRC_CHUNK) * i + lane / SRC_CHUNK, cc = lane % SRC_CHUNK;
                     if (n_s + c0 + cc < s_n_out[r] && n_s + c0 + cc >= s_out_start[r])
                         (reinterpret_cast<R *>(args.out) + s_out_off[r])[n_s + c0 + cc] = yw[r * YLD + cc];
@@ -381,6 +450,8 @@ __global__ void __launch_bounds__(SRC_THREADS, sizeof(R) == 4 ? 3 : 2) src_kerne
                 __syncwarp();
             }
         }
+        in_flight = prefetch;
+        buf = (NBUF == 2) ? buf ^ 1 : 0;
     }
     if (item_hi > item_lo) flush_max();
 }

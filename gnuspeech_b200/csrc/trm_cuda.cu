@@ -226,7 +226,7 @@ struct trm_cuda_resident {
 
 namespace {
 
-void plan_chunk(const trm_cuda_utterance *desc, int u0, int u1, ChunkPlan &p)
+void plan_chunk(const trm_cuda_utterance *desc, int u0, int u1, int tile_width, ChunkPlan &p)
 {
     const int n = u1 - u0;
     p.u0 = u0;
@@ -266,7 +266,7 @@ void plan_chunk(const trm_cuda_utterance *desc, int u0, int u1, ChunkPlan &p)
     }
     {
         // resampler tiles: utterances that share (time-register increment, pad, direction, phase increment,
-        // ratio) share every filter coefficient; longest first so the 32 lanes of a tile finish together
+        // ratio) share every filter coefficient; longest first so the rows of a tile finish together
         std::vector<int> idx(n);
         std::iota(idx.begin(), idx.end(), 0);
         auto key = [&](int a) {
@@ -283,7 +283,7 @@ void plan_chunk(const trm_cuda_utterance *desc, int u0, int u1, ChunkPlan &p)
         p.tile_utt.clear(); p.tile_nt.clear(); p.tile_max_out.clear(); p.tile_first_out.clear(); p.item_base.assign(1, 0);
         for (int at = 0; at < n;) {
             int end = at;
-            while (end < n && end - at < 32 && key(idx[end]) == key(idx[at])) ++end;
+            while (end < n && end - at < tile_width && key(idx[end]) == key(idx[at])) ++end;
             const auto &d0 = p.desc[idx[at]];
             if (d0.n_out > 0) {
                 const int reach = d0.padSize + 1;
@@ -296,7 +296,7 @@ void plan_chunk(const trm_cuda_utterance *desc, int u0, int u1, ChunkPlan &p)
                 long long first = d0.n_out;                  // streaming: the tile starts at its earliest missing output
                 for (int r = at; r < end; ++r) first = std::min<long long>(first, p.desc[idx[r]].out_start);
                 first = first / nt * nt;
-                for (int r = 0; r < 32; ++r) p.tile_utt.push_back(at + r < end ? idx[at + r] : -1);
+                for (int r = 0; r < tile_width; ++r) p.tile_utt.push_back(at + r < end ? idx[at + r] : -1);
                 p.tile_nt.push_back((int)nt);
                 p.tile_max_out.push_back(d0.n_out);
                 p.tile_first_out.push_back(first);
@@ -695,7 +695,7 @@ int trm_cuda_synthesize_host(trm_cuda_ctx *ctx, int precision, int n, const trm_
         if (slot_chunk[slot] >= 0 && (rc = finish_slot(slot)) != 0) return rc;
         ChunkPlan &p = plans[slot];
         const int u0 = ci * per_chunk, u1 = std::min(n, u0 + per_chunk);
-        plan_chunk(desc, u0, u1, p);
+        plan_chunk(desc, u0, u1, (precision == 0 ? ctx->info64 : ctx->info32).src_tile, p);
         if ((rc = ctx->arenas[slot].reserve(p.arena_bytes(esz, want_pcm))) != 0) return rc;
         if ((rc = ctx->stages[slot].reserve(p.stage_bytes())) != 0) return rc;
         DeviceChunk dc;
@@ -955,7 +955,7 @@ int trm_cuda_stream_push(trm_cuda_stream *s, const double *frames_host, int m, i
     }
     if (target - s->in_start > s->cap_tube || out_total - s->out_done / 4 * 4 > s->cap_out) return fail_msg("trm_cuda_stream_push: internal capacity");
     ChunkPlan plan;
-    plan_chunk(ds.data(), 0, n, plan);
+    plan_chunk(ds.data(), 0, n, ki.src_tile, plan);
     // plan_chunk rebases offsets to the chunk's span: streaming keeps its own (virtual) offsets
     for (int u = 0; u < n; ++u) { plan.desc[u].tube_offset = ds[u].tube_offset; plan.desc[u].out_offset = ds[u].out_offset; plan.desc[u].frame_offset = 0; }
     size_t bytes = plan.stage_bytes() + align_up((size_t)n * sizeof(trm_cuda_utterance), 256) + 1024;
@@ -1069,7 +1069,7 @@ int trm_cuda_resident_create(trm_cuda_ctx *ctx, int precision, int n, const trm_
     trm_cuda_resident *r = new trm_cuda_resident();
     r->ctx = ctx;
     r->precision = precision;
-    plan_chunk(desc, 0, n, r->plan);
+    plan_chunk(desc, 0, n, (precision == 0 ? ctx->info64 : ctx->info32).src_tile, r->plan);
     int rc;
     if ((rc = r->arena.reserve(r->plan.arena_bytes(esz, true))) != 0) { delete r; return rc; }
     carve(r->arena, r->plan, esz, true, r->dc);
