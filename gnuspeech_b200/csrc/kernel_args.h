@@ -14,14 +14,13 @@ constexpr int FRAME_CHUNK = 2;   // control frames per bulk copy (256 B)
 constexpr int WARPS_PER_CTA = 2;
 constexpr int UTT_PER_CTA = WARPS_PER_CTA * 2;
 
-constexpr int SRC_THREADS = 256;
+
 constexpr int SRC_ROWS = 128;        // staged input rows per work item
-constexpr int SRC_XLD = 132;         // elements per utterance row of the staged windows (SRC_ROWS + 16-byte alignment slack)
 constexpr int SRC_CHUNK = 8;         // consecutive outputs a warp finishes before the transposed write-back
 constexpr int SRC_ZC = 13;           // zero crossings -> 13 taps per wing when up-sampling
 constexpr int SRC_TAPS = 2 * SRC_ZC; // coefficients per output
 constexpr int SRC_CLD = 28;          // row stride of the coefficient table (16-byte aligned rows in both precisions)
-constexpr int SRC_NT_MAX = 256;      // outputs per work item (bounded by SRC_ROWS and by this)
+constexpr int SRC_NT_MAX = 192;      // outputs per work item (bounded by SRC_ROWS and by this)
 constexpr int PCM_THREADS = 256;
 constexpr int PCM_PER_THREAD = 8;
 

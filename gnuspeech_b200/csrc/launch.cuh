@@ -13,7 +13,7 @@ namespace trm {
 
 template <typename R> constexpr int src_smem_bytes()
 {
-    return (SrcCfg<R>::WINDOWS * SrcCfg<R>::TILE * SRC_XLD + SRC_NT_MAX * SRC_CLD + (SRC_THREADS / 32) * SrcCfg<R>::TILE * (SRC_CHUNK + 1)) *
+    return (SrcCfg<R>::WINDOWS * SrcCfg<R>::TILE * SrcCfg<R>::XLD + SrcCfg<R>::CBUFS * SRC_NT_MAX * SRC_CLD + (SrcCfg<R>::THREADS / 32) * SrcCfg<R>::TILE * (SRC_CHUNK + 1)) *
            (int)sizeof(R);
 }
 
@@ -43,9 +43,9 @@ template <typename R> static int configure_kernels(KernelInfo *info)
         info->tube_threads = WARPS_PER_CTA * 32;
         info->tube_utt_per_cta = UTT_PER_CTA;
         info->src_smem_bytes = src_smem;
-        info->src_threads = SRC_THREADS;
+        info->src_threads = SrcCfg<R>::THREADS;
         info->src_tile = SrcCfg<R>::TILE;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&info->src_ctas_per_sm, src_kernel<R>, SRC_THREADS, src_smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&info->src_ctas_per_sm, src_kernel<R>, SrcCfg<R>::THREADS, src_smem);
         if (e != cudaSuccess) return (int)e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&info->tube_ctas_per_sm, tube_kernel<R>, WARPS_PER_CTA * 32, tube_smem);
         if (e != cudaSuccess) return (int)e;
@@ -95,7 +95,7 @@ template <typename R> static int launch_src(const SrcArgs &a, int grid, cudaStre
     if (a.total_items <= 0) return 0;
     if ((long long)grid > a.total_items) grid = (int)a.total_items;
     const size_t smem = src_smem_bytes<R>();
-    src_kernel<R><<<grid, SRC_THREADS, smem, s>>>(a);
+    src_kernel<R><<<grid, SrcCfg<R>::THREADS, smem, s>>>(a);
     return (int)cudaGetLastError();
 }
 

@@ -50,8 +50,14 @@ template <> struct Vec16<double> {
 // second buffer (measured: no gain, the copy latency was already hidden by the other CTAs of the SM).
 template <typename R> struct SrcCfg {
     static constexpr int U = sizeof(R) == 4 ? 2 : 1;
+    static constexpr int CBUFS = sizeof(R) == 4 ? 2 : 1;   // coefficient-row buffers (2: the next item's rows are prefetched)
     static constexpr int TILE = 32 * U;                 // utterances per tile
     static constexpr int WINDOWS = 1;
+    // elements per utterance row of the staged windows (SRC_ROWS + alignment slack).  Rows start on 16-byte boundaries
+    // (bulk-copy destinations), so the lanes of a warp reading the same element of their rows always collide somewhat;
+    // 132 floats / 130 doubles (= 4 banks mod 32) keep that to 4 / 2 lanes per bank
+    static constexpr int XLD = sizeof(R) == 4 ? 132 : 130;
+    static constexpr int THREADS = 256;
     static constexpr int MIN_CTAS = 2;
 };
 
@@ -60,7 +66,7 @@ template <> __device__ __forceinline__ double r_abs<double>(double x) { return f
 template <> __device__ __forceinline__ float r_abs<float>(float x) { return fabsf(x); }
 // max(a, b) that returns a when b is NaN (a is never NaN here): the (b > a) ? b : a of the reference's running maximum
 template <typename R> __device__ __forceinline__ R r_max(R a, R b);
-template <> __device__ __forceinline__ double r_max<double>(double a, double b) { return fmax(a, b); }
+template <> __device__ __forceinline__ double r_max<double>(double a, double b) { return (b > a) ? b : a; }
 template <> __device__ __forceinline__ float r_max<float>(float a, float b) { return fmaxf(a, b); }
 
 // One work item = one tile of 32 utterances with the same converter signature (time-register increment, pad,
@@ -83,31 +89,39 @@ template <> __device__ __forceinline__ float r_max<float>(float a, float b) { re
 // Accumulation order (left wing first, newest -> oldest, from 0.0) is the reference's; one multiply and one add per
 // tap.  Outputs go back through a small per-warp transpose tile and leave as 128-bit stores.
 template <typename R>
-__global__ void __launch_bounds__(SRC_THREADS, SrcCfg<R>::MIN_CTAS) src_kernel(SrcArgs args)
+__global__ void __launch_bounds__(SrcCfg<R>::THREADS, SrcCfg<R>::MIN_CTAS) src_kernel(SrcArgs args)
 {
     constexpr int A = 16 / (int)sizeof(R);                               // elements per 16 bytes
     constexpr int YLD = SRC_CHUNK + 1;
     constexpr int U = SrcCfg<R>::U, TW = SrcCfg<R>::TILE;
     constexpr int NBUF = SrcCfg<R>::WINDOWS;
     constexpr unsigned FULL = 0xFFFFFFFFu;
+    constexpr int SRC_THREADS = SrcCfg<R>::THREADS, SRC_XLD = SrcCfg<R>::XLD;
+    static_assert(SRC_THREADS >= SRC_NT_MAX, "one coefficient row per thread");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R *xU0 = reinterpret_cast<R *>(smem_raw);                            // [NBUF][TW][SRC_XLD] input windows, utterance-major
-    R *Cf = xU0 + NBUF * TW * SRC_XLD;                                   // [SRC_NT_MAX][SRC_CLD] coefficients
-    R *yT = Cf + SRC_NT_MAX * SRC_CLD;                                   // [warps][TW][YLD]
+    R *Cf0 = xU0 + NBUF * TW * SRC_XLD;                                  // [CBUFS][SRC_NT_MAX][SRC_CLD] coefficient rows
+    R *yT = Cf0 + SrcCfg<R>::CBUFS * SRC_NT_MAX * SRC_CLD;                              // [warps][TW][YLD]
     __shared__ long long s_tube_off[TW], s_out_off[TW], s_n_in[TW], s_n_out[TW], s_out_start[TW], s_in_start[TW];
     __shared__ int s_tile;
-    __shared__ unsigned long long s_bar[2];
+    __shared__ unsigned long long s_bar[2], s_cbar[2];
+    __shared__ unsigned char s_flag[SRC_NT_MAX];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const HD<R> *__restrict__ tab = reinterpret_cast<const HD<R> *>(args.table);
     if (threadIdx.x == 0) {
         mbar_init(&s_bar[0], U);                                         // one arrival per requesting warp
         mbar_init(&s_bar[1], U);
+        mbar_init(&s_cbar[0], 1);
+        mbar_init(&s_cbar[1], 1);
         mbar_fence_init();
     }
     uint32_t bar_phase = 0;                                              // bit b: parity to wait for on s_bar[b]
     int buf = 0;                                                         // window buffer of the current item
     bool in_flight = false;                                              // its window was requested during the previous item
+    uint32_t cbar_phase = 0;
+    int cb = 0;                                                          // coefficient buffer of the current item
+    bool c_in_flight = false;                                            // its coefficient rows were requested during the previous item
 
     // every CTA takes a contiguous range of work items: consecutive items belong to the same tile, whose descriptors
     // are read from global memory once and kept in shared memory
@@ -219,30 +233,32 @@ __global__ void __launch_bounds__(SRC_THREADS, SrcCfg<R>::MIN_CTAS) src_kernel(S
         R *const xU = xU0 + buf * TW * SRC_XLD;
         if (warp < U && !in_flight) request_window(geo, buf);
         const int run = nt / (SRC_THREADS / 32);                         // consecutive outputs per warp (multiple of SRC_CHUNK)
+        // Coefficient rows of an item: output n has C[n][t] = h[l + 256 k] + dH[l + 256 k] * (m / 256), (l, m) from the
+        // fraction F of its time register for the left wing (t = k) and from ~F for the right wing (t = 13 + k)
+        // (m:179-203) -- a function of F alone, so the rows come from the context's table of all 65,536 fractions
+        // (src_ctab_kernel below; a few MB that stay in L2), one bulk copy per row, one row per thread.  The rows of the
+        // NEXT item are requested before this one is computed and land in the other buffer meanwhile.
+        constexpr unsigned ROWB = SRC_CLD * (unsigned)sizeof(R);
+        const R *__restrict__ ct = reinterpret_cast<const R *>(args.ctab);
+        auto request_rows = [&](const Geo &g, int b) {
+            if (threadIdx.x == 0) mbar_expect_tx(&s_cbar[b], (unsigned)g.n_item * ROWB);
+            if ((int)threadIdx.x < g.n_item) {
+                const unsigned f = g.frac0 + threadIdx.x * tri;
+                tma_bulk_g2s(Cf0 + (b * SRC_NT_MAX + (int)threadIdx.x) * SRC_CLD, ct + (size_t)(f & 0xFFFFu) * SRC_CLD, ROWB, &s_cbar[b]);
+            }
+        };
+        const bool more = item + 1 < item_hi && item + 1 < tile_end;     // the next item belongs to this tile too
+        const R *const Cf = Cf0 + cb * SRC_NT_MAX * SRC_CLD;
         if (up) {
-            // coefficient rows of the item: output n has C[n][t] = h[l + 256 k] + dH[l + 256 k] * (m / 256), (l, m) from
-            // the fraction F of its time register for the left wing (t = k) and from ~F for the right wing (t = 13 + k)
-            // (m:179-203) -- a function of F alone, so the rows come from the context's table of all 65,536 fractions
-            // (src_ctab_kernel below; a few MB that stay in L2) as 16-byte vectors.  Column 26 of a row tells the walking
-            // warp what follows the output: 0 = same input position, 1 = the integer part of the time register advances
-            // (slide the window), 2 = last output of the warp's run.
-            constexpr int VR = SRC_CLD / A;                              // vectors per row
-            const unsigned rcp_run = (65536u + (unsigned)run - 1u) / (unsigned)run;
-            const int n_vec = n_item * VR;
-            const R *__restrict__ ct = reinterpret_cast<const R *>(args.ctab);
-#pragma unroll 4
-            for (int i = threadIdx.x; i < n_vec; i += SRC_THREADS) {
-                const int nr = i / VR, q = i - nr * VR;
+            if (!c_in_flight) request_rows(geo, cb);
+            if (SrcCfg<R>::CBUFS == 2 && more) request_rows(geometry(item + 1), cb ^ 1);
+            // what follows output n for the warp that walks it: 0 = same input position, 1 = the integer part of the time
+            // register advances (slide the window), 2 = last output of the warp's run
+            if ((int)threadIdx.x < n_item) {
+                const int nr = threadIdx.x;
                 const unsigned f = frac0 + (unsigned)nr * tri;
-                Vec16<R> v;
-                v.load(ct + (size_t)(f & 0xFFFFu) * SRC_CLD + A * q);
-                if (q == SRC_TAPS / A) {
-                    // (nr + 1) % run == 0 without a division: floor(n / run) = (n * ceil(2^16 / run)) >> 16 for n <= 256, run >= 8
-                    const unsigned k = ((unsigned)(nr + 1) * rcp_run) >> 16;
-                    const bool last = (nr + 1 == n_item) || (k * (unsigned)run == (unsigned)(nr + 1));
-                    v.e[SRC_TAPS % A] = last ? (R)2 : ((((f + tri) >> 16) != (f >> 16)) ? (R)1 : (R)0);
-                }
-                v.store(Cf + nr * SRC_CLD + A * q);
+                const bool last = (nr + 1 == n_item) || ((nr + 1) % run == 0);
+                s_flag[nr] = last ? 2 : ((((f + tri) >> 16) != (f >> 16)) ? 1 : 0);
             }
         }
         __syncthreads();                                                 // descriptors + coefficients visible
@@ -252,6 +268,10 @@ __global__ void __launch_bounds__(SRC_THREADS, SrcCfg<R>::MIN_CTAS) src_kernel(S
         if (prefetch && warp < U) request_window(geometry(item + 1), buf ^ 1);
         mbar_wait(&s_bar[buf], (bar_phase >> buf) & 1u);
         bar_phase ^= 1u << buf;
+        if (up) {
+            mbar_wait(&s_cbar[cb], (cbar_phase >> cb) & 1u);
+            cbar_phase ^= 1u << cb;
+        }
         {
             // zero-fill outside [0, n_in): only the first / last items of an utterance have such positions
             bool mine = false;
@@ -304,6 +324,7 @@ __global__ void __launch_bounds__(SRC_THREADS, SrcCfg<R>::MIN_CTAS) src_kernel(S
             }
             const R *xn = xl + reach + SRC_ZC + Pc0;                     // newest window element; the next one enters on a slide
             const R *crow = Cf + nr_first * SRC_CLD;
+            const unsigned char *fl = s_flag + nr_first;
             R *const ys = yw + lane * YLD;                               // utterance k: row lane + 32 k of the warp's tile
             int c0 = nr_first, j = 0;                                    // start of the current write-back chunk, outputs in it
             constexpr int PIECES = SRC_CHUNK / A;                        // 16-byte pieces per utterance and chunk
@@ -356,7 +377,7 @@ __global__ void __launch_bounds__(SRC_THREADS, SrcCfg<R>::MIN_CTAS) src_kernel(S
                 for (;;) {
 #pragma unroll
                     for (int ph = 0; ph < SRC_TAPS; ++ph) {
-                        R flag;
+                        int flag;
                         do {
                             // coefficient row: broadcast 128-bit loads, consumed as they arrive (tap t: t < 13 is the left
                             // wing, logical element 12-t; else the right wing, logical element t); every coefficient
@@ -364,9 +385,9 @@ __global__ void __launch_bounds__(SRC_THREADS, SrcCfg<R>::MIN_CTAS) src_kernel(S
                             R acc[U];
 #pragma unroll
                             for (int k = 0; k < U; ++k) acc[k] = (R)0;
-                            flag = (R)0;
+                            flag = *fl++;
 #pragma unroll
-                            for (int q = 0; q < (SRC_TAPS + 1 + A - 1) / A; ++q) {
+                            for (int q = 0; q < (SRC_TAPS + A - 1) / A; ++q) {
                                 Vec16<R> cq;
                                 cq.load(crow + A * q);
 #pragma unroll
@@ -377,7 +398,6 @@ __global__ void __launch_bounds__(SRC_THREADS, SrcCfg<R>::MIN_CTAS) src_kernel(S
                                         if (t < SRC_ZC) acc[k] += W[k][(SRC_ZC - 1 - t + ph) % SRC_TAPS] * cq.e[e];
                                         else if (t < SRC_TAPS) acc[k] += W[k][(t + ph) % SRC_TAPS] * cq.e[e];
                                     }
-                                    if (t == SRC_TAPS) flag = cq.e[e];
                                 }
                             }
 #pragma unroll
@@ -393,8 +413,8 @@ __global__ void __launch_bounds__(SRC_THREADS, SrcCfg<R>::MIN_CTAS) src_kernel(S
                             if constexpr (!INTERIOR) ++nr;
                             crow += SRC_CLD;
                             if (++j == SRC_CHUNK) write_back(INTERIOR);
-                        } while (flag == (R)0);
-                        if (flag == (R)2) return;
+                        } while (flag == 0);
+                        if (flag == 2) return;
                         // slide: logical element 0 (register ph) leaves, xb[P + 14] enters as logical element 25 of phase ph+1
                         ++xn;
 #pragma unroll
@@ -452,6 +472,8 @@ __global__ void __launch_bounds__(SRC_THREADS, SrcCfg<R>::MIN_CTAS) src_kernel(S
         }
         in_flight = prefetch;
         buf = (NBUF == 2) ? buf ^ 1 : 0;
+        c_in_flight = SrcCfg<R>::CBUFS == 2 && up && more;
+        cb = (SrcCfg<R>::CBUFS == 2) ? cb ^ 1 : 0;
     }
     if (item_hi > item_lo) flush_max();
 }

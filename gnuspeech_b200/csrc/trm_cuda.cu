@@ -226,9 +226,9 @@ struct trm_cuda_resident {
 
 namespace {
 
-void plan_chunk(const trm_cuda_utterance *desc, int u0, int u1, int tile_width, ChunkPlan &p)
+void plan_chunk(const trm_cuda_utterance *desc, int u0, int u1, const trm::KernelInfo &ki, ChunkPlan &p)
 {
-    const int n = u1 - u0;
+    const int n = u1 - u0, tile_width = ki.src_tile;
     p.u0 = u0;
     p.u1 = u1;
     p.desc.assign(desc + u0, desc + u1);
@@ -289,7 +289,7 @@ void plan_chunk(const trm_cuda_utterance *desc, int u0, int u1, int tile_width, 
                 const int reach = d0.padSize + 1;
                 // outputs per work item: the input window must fit SRC_ROWS, every warp of the CTA gets the same
                 // whole number of SRC_CHUNK-sized runs
-                const long long unit = d0.upsample ? (long long)trm::SRC_CHUNK * (trm::SRC_THREADS / 32) : (long long)trm::SRC_CHUNK;
+                const long long unit = d0.upsample ? (long long)trm::SRC_CHUNK * (ki.src_threads / 32) : (long long)trm::SRC_CHUNK;
                 long long nt = (long long)((double)(trm::SRC_ROWS - 3 - 2 * reach) * 65536.0 / (double)d0.tri);
                 nt = std::min<long long>(nt, trm::SRC_NT_MAX);
                 nt = std::max<long long>(unit, nt / unit * unit);
@@ -695,7 +695,7 @@ int trm_cuda_synthesize_host(trm_cuda_ctx *ctx, int precision, int n, const trm_
         if (slot_chunk[slot] >= 0 && (rc = finish_slot(slot)) != 0) return rc;
         ChunkPlan &p = plans[slot];
         const int u0 = ci * per_chunk, u1 = std::min(n, u0 + per_chunk);
-        plan_chunk(desc, u0, u1, (precision == 0 ? ctx->info64 : ctx->info32).src_tile, p);
+        plan_chunk(desc, u0, u1, precision == 0 ? ctx->info64 : ctx->info32, p);
         if ((rc = ctx->arenas[slot].reserve(p.arena_bytes(esz, want_pcm))) != 0) return rc;
         if ((rc = ctx->stages[slot].reserve(p.stage_bytes())) != 0) return rc;
         DeviceChunk dc;
@@ -955,7 +955,7 @@ int trm_cuda_stream_push(trm_cuda_stream *s, const double *frames_host, int m, i
     }
     if (target - s->in_start > s->cap_tube || out_total - s->out_done / 4 * 4 > s->cap_out) return fail_msg("trm_cuda_stream_push: internal capacity");
     ChunkPlan plan;
-    plan_chunk(ds.data(), 0, n, ki.src_tile, plan);
+    plan_chunk(ds.data(), 0, n, ki, plan);
     // plan_chunk rebases offsets to the chunk's span: streaming keeps its own (virtual) offsets
     for (int u = 0; u < n; ++u) { plan.desc[u].tube_offset = ds[u].tube_offset; plan.desc[u].out_offset = ds[u].out_offset; plan.desc[u].frame_offset = 0; }
     size_t bytes = plan.stage_bytes() + align_up((size_t)n * sizeof(trm_cuda_utterance), 256) + 1024;
@@ -1069,7 +1069,7 @@ int trm_cuda_resident_create(trm_cuda_ctx *ctx, int precision, int n, const trm_
     trm_cuda_resident *r = new trm_cuda_resident();
     r->ctx = ctx;
     r->precision = precision;
-    plan_chunk(desc, 0, n, (precision == 0 ? ctx->info64 : ctx->info32).src_tile, r->plan);
+    plan_chunk(desc, 0, n, precision == 0 ? ctx->info64 : ctx->info32, r->plan);
     int rc;
     if ((rc = r->arena.reserve(r->plan.arena_bytes(esz, true))) != 0) { delete r; return rc; }
     carve(r->arena, r->plan, esz, true, r->dc);
