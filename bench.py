@@ -42,7 +42,7 @@ FLOP_PER_OUT_SAMPLE = 110.0      # up-sampling converter, per output sample
 # DRAM traffic per unit measured with `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum of the
 # 4096 x 1 s launch, profiles/prof_r1b_{fp64,fp32}_summary.txt) -- linear in the number of samples:
 #   waveguide: bytes per tube-rate sample, resampler / PCM: bytes per output sample
-TRAFFIC_PER_UNIT = {"fp64": {"tube": 8.95, "src": 11.34, "pcm": 9.97}, "fp32": {"tube": 5.07, "src": 5.55, "pcm": 5.86}}
+TRAFFIC_PER_UNIT = {"fp64": {"tube": 8.95, "src": 12.08, "pcm": 9.96}, "fp32": {"tube": 5.04, "src": 5.85, "pcm": 5.85}}
 
 
 def host_cores():

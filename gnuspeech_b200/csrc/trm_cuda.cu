@@ -658,7 +658,8 @@ int trm_cuda_synthesize_host(trm_cuda_ctx *ctx, int precision, int n, const trm_
     // TRM_TRACE=1: per-chunk timeline of the pipeline stages (CUDA events), printed to stderr
     const bool trace = getenv("TRM_TRACE") != nullptr;
     std::vector<cudaEvent_t> tev;
-    cudaEvent_t t_origin = nullptr;
+    static cudaEvent_t t_origin = nullptr;          // one time axis for every traced call of the process
+    static std::mutex t_mutex;
     auto mark = [&](cudaStream_t st) {
         if (!trace) return;
         cudaEvent_t e;
@@ -666,7 +667,10 @@ int trm_cuda_synthesize_host(trm_cuda_ctx *ctx, int precision, int n, const trm_
         cudaEventRecord(e, st);
         tev.push_back(e);
     };
-    if (trace) { cudaEventCreate(&t_origin); cudaEventRecord(t_origin, s_out); }
+    if (trace) {
+        std::lock_guard<std::mutex> lk(t_mutex);
+        if (!t_origin) { cudaEventCreate(&t_origin); cudaEventRecord(t_origin, s_out); cudaEventSynchronize(t_origin); }
+    }
     std::vector<ChunkPlan> plans(N_SLOTS);
     std::vector<int> slot_chunk(N_SLOTS, -1);
     int64_t n_launch = 0;
@@ -751,14 +755,14 @@ int trm_cuda_synthesize_host(trm_cuda_ctx *ctx, int precision, int n, const trm_
         if (slot_chunk[slot] >= 0 && (rc = finish_slot(slot)) != 0) return rc;
     }
     if (trace) {
-        fprintf(stderr, "[trm trace] chunk: start h2d_done tube_done src_done pcm_done d2h_done (ms)\n");
+        std::lock_guard<std::mutex> lk(t_mutex);
+        fprintf(stderr, "[trm trace] ctx %p chunk: start h2d_done tube_done src_done pcm_done d2h_done (ms since the first traced call)\n", (void *)ctx);
         for (size_t i = 0; i + 6 <= tev.size(); i += 6) {
             float t[6];
             for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&t[k], t_origin, tev[i + k]);
-            fprintf(stderr, "[trm trace] %2zu: %7.2f %7.2f %7.2f %7.2f %7.2f %7.2f\n", i / 6, t[0], t[1], t[2], t[3], t[4], t[5]);
+            fprintf(stderr, "[trm trace] %2zu: %8.2f %8.2f %8.2f %8.2f %8.2f %8.2f\n", i / 6, t[0], t[1], t[2], t[3], t[4], t[5]);
         }
         for (auto e : tev) cudaEventDestroy(e);
-        cudaEventDestroy(t_origin);
     }
     if (launches) *launches = n_launch;
     return 0;
