@@ -134,12 +134,24 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 // ---------------------------------------------------------------------------------------------
 // amplitude(): TRMUtility.m:26-41.  Always evaluated in double (it is off the serial chain and the
 // glottal-closure decision rint(ax*tnDelta) must not move).
+// a / c for a divisor known in advance, rc = RN(1 / c): one multiply and two fused operations instead of the ~26
+// instructions of a general IEEE division.  q' = RN(q + (a - c q) rc) with the residual exact is the correctly rounded
+// quotient (Markstein's correction step; Brisebarre, Muller & Raina 2004): the value rounded last differs from a / c by
+// <= 2^-105 |a / c|, closer than a quotient of two doubles comes to a rounding boundary except for isolated operand
+// pairs.  Same result as `a / c`, so the conformance arithmetic is unchanged.
+__device__ __forceinline__ double div_known(double a, double c, double rc)
+{
+    const double q = a * rc;
+    const double r = fma(-c, q, a);
+    return fma(r, rc, q);
+}
+
 __device__ __forceinline__ double amplitude_db(double dB)
 {
     double x = dB - 60.0;
     if (x <= -60.0) return 0.0;
     if (x >= 0.0) return 1.0;
-    return exp10(x / 20.0);
+    return exp10(div_known(x, 20.0, 1.0 / 20.0));
 }
 // Bit-wise select (one LOP3 per 32 bits): m = all ones -> x, m = 0 -> y.  Used instead of ?: in the junction
 // loop so that the per-lane roles stay straight-line code (the compiler turns lane-dependent ternaries into
@@ -356,7 +368,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) tube_kernel(TubeArgs ar
         {
             // pitch -> f0 -> increment: always double (a relative error here is a frequency error whose phase
             // drift grows with the length of the utterance)
-            const double f0 = 220.0 * exp2((prm[0] + 3.0) / 12.0);
+            const double f0 = 220.0 * exp2(div_known(prm[0] + 3.0, 12.0, 1.0 / 12.0));
             S.INC[hl] = (f0 / 2.0) * D->basicIncrement;
         }
         double ax_d;

@@ -482,10 +482,10 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
     const bool modulation = D->usesModulation != 0;
     const int div1 = D->div1, div2 = D->div2;
 
-    enum { C_BASICINC, C_TNDELTA, C_DAMP, C_SR, C_NR1SQ, C_APSCALE2, C_MOUTH0, C_BF, C_CMIX, C_TA0 };
+    enum { C_BASICINC, C_TNDELTA, C_DAMP, C_SR, C_NR1SQ, C_APSCALE2, C_MOUTH0, C_BF, C_CMIX, C_TA0, C_RSR };
     if (hl == 0) {
         S.CST[C_BASICINC] = D->basicIncrement; S.CST[C_TNDELTA] = D->tnDelta; S.CST[C_DAMP] = D->dampingFactor;
-        S.CST[C_SR] = D->sampleRate; S.CST[C_NR1SQ] = D->nr1sq; S.CST[C_APSCALE2] = D->apScale2; S.CST[C_MOUTH0] = D->mouth[0];
+        S.CST[C_SR] = D->sampleRate; S.CST[C_RSR] = 1.0 / D->sampleRate; S.CST[C_NR1SQ] = D->nr1sq; S.CST[C_APSCALE2] = D->apScale2; S.CST[C_MOUTH0] = D->mouth[0];
         S.CST[C_BF] = D->breathinessFactor; S.CST[C_CMIX] = D->crossmixFactor; S.CST[C_TA0] = D->ta0;
     }
     const bool feeds = n_tube > 0;
@@ -607,7 +607,7 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
         __syncwarp(FULL);                                   // every staged value is in registers: records may be written
         double inc_d;
         {
-            const double f0 = 220.0 * exp2((prm[0] + 3.0) / 12.0);
+            const double f0 = 220.0 * exp2(div_known(prm[0] + 3.0, 12.0, 1.0 / 12.0));
             inc_d = (f0 / 2.0) * S.CST[C_BASICINC];
             if constexpr (!FAST) S.INC[hl] = inc_d;
         }
@@ -709,8 +709,9 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
             {
                 const double sr = S.CST[C_SR];
                 const double pi = 3.14159265358979323846;
-                const double tanv = tan((pi * prm[6]) / sr);
-                const double cosv = cos(((2.0 * pi) * prm[5]) / sr);
+                const double rsr = S.CST[C_RSR];                 // RN(1 / sr)
+                const double tanv = tan(div_known(pi * prm[6], sr, rsr));
+                const double cosv = cos(div_known((2.0 * pi) * prm[5], sr, rsr));
                 const double beta = (1.0 - tanv) / (2.0 * (1.0 + tanv));
                 beta2 = 2.0 * beta;
                 gamma2 = 2.0 * ((0.5 + beta) * cosv);

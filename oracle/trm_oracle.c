@@ -1185,3 +1185,22 @@ int64_t oracle_generate_frames(const oracle_event *events, int64_t n_events, con
 {
     return generate_frames(events, n_events, fg, out, max_frames, seed_out);
 }
+
+/* see trm_oracle.h: exactness check of the kernels' known-divisor division */
+int64_t oracle_div_known_mismatches(double c, double lo, double hi, int64_t n, uint64_t seed)
+{
+    const volatile double rc = 1.0 / c;
+    int64_t bad = 0;
+    uint64_t s = seed * 2862933555777941757ULL + 3037000493ULL;
+    for (int64_t i = 0; i < n; ++i) {
+        s = s * 6364136223846793005ULL + 1442695040888963407ULL;
+        const double u = (double)(s >> 11) * (1.0 / 9007199254740992.0);
+        const volatile double a = lo + (hi - lo) * u;
+        const volatile double q = a * rc;
+        const double r = fma(-c, q, a);
+        const double q2 = fma(r, rc, q);
+        const volatile double ref = a / c;
+        if (q2 != ref) ++bad;
+    }
+    return bad;
+}

@@ -137,6 +137,14 @@ int64_t oracle_frame_count(const oracle_event *events, int64_t n_events);
 int64_t oracle_generate_frames(const oracle_event *events, int64_t n_events, const oracle_framegen *fg,
                                oracle_frame *out, int64_t max_frames, float *seed_out);
 
+/* ------------------------------------------------------------------------------------------------
+ * Checker for a kernel shortcut, not reference behaviour: the CUDA feed-forward code divides by divisors known in
+ * advance (20, 12, the tube sample rate) as q = a*rc, r = fma(-c, q, a), q' = fma(r, rc, q) with rc = RN(1/c)
+ * (div_known(), gnuspeech_b200/csrc/tube_kernel.cuh).  Returns how many of n pseudo-random numerators in [lo, hi)
+ * give a result different from the IEEE division a / c (expected: 0).
+ * ---------------------------------------------------------------------------------------------- */
+int64_t oracle_div_known_mismatches(double c, double lo, double hi, int64_t n, uint64_t seed);
+
 #ifdef __cplusplus
 }
 #endif

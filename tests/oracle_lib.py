@@ -65,6 +65,8 @@ def lib():
         L.oracle_synthesize_batch.restype = C.c_int
         L.oracle_synthesize_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                               C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_div_known_mismatches.restype = C.c_int64
+        L.oracle_div_known_mismatches.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int64, C.c_uint64]
         _lib = L
     return _lib
 

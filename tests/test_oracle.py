@@ -261,3 +261,16 @@ def test_frame_generator_restatement_properties():
         t = np.concatenate(([0], np.cumsum(rng.integers(0, 30, n - 1))))
         ev = g.make_events(t, np.zeros((n, 36)))
         assert O.frame_count(ev) == g.event_list_frame_count(ev), t
+
+
+def test_known_divisor_division_is_ieee_division():
+    """The kernels divide by 20, 12 and the tube sample rate with a multiply and two fused operations
+    (div_known(), tube_kernel.cuh); the result must be the IEEE quotient for the numerators the path produces."""
+    L = O.lib()
+    cases = [(20.0, -60.0, 0.0),                  # amplitude(): (dB - 60) / 20
+             (12.0, -30.0, 30.0),                 # frequency(): (pitch + 3) / 12
+             (19750.0, 0.0, 40000.0), (17500.0, 0.0, 40000.0), (22050.0, 0.0, 40000.0),   # pi*bw/sr, 2*pi*fc/sr
+             (35110.0, 0.0, 40000.0), (14041.3, 0.0, 40000.0), (44100.0, 0.0, 1.0e5)]
+    for k, (c, lo, hi) in enumerate(cases):
+        assert L.oracle_div_known_mismatches(c, lo, hi, 2_000_000, 1234 + k) == 0, c
+
