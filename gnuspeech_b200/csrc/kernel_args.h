@@ -15,12 +15,11 @@ constexpr int WARPS_PER_CTA = 2;
 constexpr int UTT_PER_CTA = WARPS_PER_CTA * 2;
 
 
-constexpr int SRC_ROWS = 128;        // staged input rows per work item
+constexpr int SRC_ROWS = TRM_SRC_ROWS; // staged input rows per work item (include/trm_cuda.h: the host checks rate ratios against it)
 constexpr int SRC_CHUNK = 8;         // consecutive outputs a warp finishes before the transposed write-back
 constexpr int SRC_ZC = 13;           // zero crossings -> 13 taps per wing when up-sampling
 constexpr int SRC_TAPS = 2 * SRC_ZC; // coefficients per output
 constexpr int SRC_CLD = 28;          // row stride of the coefficient table (16-byte aligned rows in both precisions)
-constexpr int SRC_NT_MAX = 192;      // outputs per work item (bounded by SRC_ROWS and by this)
 constexpr int PCM_THREADS = 256;
 constexpr int PCM_PER_THREAD = 8;
 
@@ -56,7 +55,7 @@ struct SrcArgs {
     const void *table;               // HD<Real>[256][13]: filter index l + 256 k at [l][k]
     const void *ctab;                // Real[65536][SRC_CLD]: interpolated coefficients per time-register fraction
     // work decomposition: tiles of <= 32 utterances that share the converter signature
-    const int *tile_utt;             // [n_tiles][tile width] utterance index or -1 (width: KernelInfo.src_tile)
+    const int *tile_utt;             // [n_tiles][tile width] utterance index or -1 (width: KernelInfo.src[shape].tile)
     const int *tile_nt;              // [n_tiles] outputs per work item of that tile (window fits SRC_ROWS)
     const long long *tile_max_out;   // [n_tiles] longest utterance of the tile
     const long long *tile_first_out; // [n_tiles] first output of the tile's first work item (0 unless streaming)
@@ -90,12 +89,17 @@ struct KernelInfo {
     int tube_smem_bytes;
     int tube_threads;
     int tube_utt_per_cta;
-    int src_smem_bytes;
-    int src_threads;
-    int src_ctas_per_sm;
-    int src_tile;                  // utterances per resampler tile (32 x utterances per lane)
+    // resampler shapes (src_kernel.cuh SrcCfg): [0] handles every converter signature, [1] (if n_src_shapes == 2) is
+    // the faster shape for up-sampling signatures whose work-item window fits its smaller staging buffer
+    struct SrcShape {
+        int smem_bytes, threads, ctas_per_sm, regs;
+        int tile;                  // utterances per tile (32 x utterances per lane)
+        int rows;                  // tube-rate samples per utterance staged for one work item
+        int nt_max;                // outputs per work item, at most
+    } src[2];
+    int n_src_shapes;
     int tube_ctas_per_sm;
-    int tube_regs, src_regs, pcm_regs;
+    int tube_regs, pcm_regs;
     int wide_smem_bytes, wide_threads, wide_max_utt, wide_regs;   // batch-throughput waveguide mapping (tube_wide.cuh)
 };
 

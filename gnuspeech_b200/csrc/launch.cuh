@@ -11,25 +11,48 @@
 
 namespace trm {
 
-template <typename R> constexpr int src_smem_bytes()
+template <typename R, int SHAPE> constexpr int src_smem_bytes()
 {
-    return (SrcCfg<R>::WINDOWS * SrcCfg<R>::TILE * SrcCfg<R>::XLD + SrcCfg<R>::CBUFS * SRC_NT_MAX * SRC_CLD + (SrcCfg<R>::THREADS / 32) * SrcCfg<R>::TILE * (SRC_CHUNK + 1)) *
+    using Cfg = SrcCfg<R, SHAPE>;
+    return (Cfg::WINDOWS * 32 * Cfg::U * Cfg::XLD + Cfg::CBUFS * Cfg::NT_MAX * SRC_CLD + (Cfg::THREADS / 32) * 32 * Cfg::U * (SRC_CHUNK + 1)) *
            (int)sizeof(R);
+}
+
+template <typename R, int SHAPE> static int configure_src(KernelInfo *info)
+{
+    using Cfg = SrcCfg<R, SHAPE>;
+    const int smem = src_smem_bytes<R, SHAPE>();
+    cudaError_t e = cudaFuncSetAttribute(src_kernel<R, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(src_kernel<R, SHAPE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return (int)e;
+    if (info) {
+        KernelInfo::SrcShape &sh = info->src[SHAPE];
+        sh.smem_bytes = smem; sh.threads = Cfg::THREADS; sh.tile = 32 * Cfg::U; sh.rows = Cfg::ROWS; sh.nt_max = Cfg::NT_MAX;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sh.ctas_per_sm, src_kernel<R, SHAPE>, Cfg::THREADS, smem);
+        if (e != cudaSuccess) return (int)e;
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, src_kernel<R, SHAPE>) == cudaSuccess) sh.regs = fa.numRegs;
+    }
+    return 0;
 }
 
 template <typename R> static int configure_kernels(KernelInfo *info)
 {
     const int tube_smem = UTT_PER_CTA * (int)sizeof(UttSmem<R>);
-    const int src_smem = src_smem_bytes<R>();
     cudaError_t e;
     e = cudaFuncSetAttribute(tube_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, tube_smem);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(tube_kernel<R>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(src_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, src_smem);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(src_kernel<R>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return (int)e;
+    {
+        int rc = configure_src<R, 0>(info);
+        if (rc != 0) return rc;
+        if constexpr (SrcShapes<R>::N == 2) {
+            if ((rc = configure_src<R, 1>(info)) != 0) return rc;
+        }
+        if (info) info->n_src_shapes = SrcShapes<R>::N;
+    }
     const int wide_smem = (int)sizeof(WideSmem<R>);
     e = cudaFuncSetAttribute(tube_wide_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, wide_smem);
     if (e != cudaSuccess) return (int)e;
@@ -42,17 +65,11 @@ template <typename R> static int configure_kernels(KernelInfo *info)
         info->tube_smem_bytes = tube_smem;
         info->tube_threads = WARPS_PER_CTA * 32;
         info->tube_utt_per_cta = UTT_PER_CTA;
-        info->src_smem_bytes = src_smem;
-        info->src_threads = SrcCfg<R>::THREADS;
-        info->src_tile = SrcCfg<R>::TILE;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&info->src_ctas_per_sm, src_kernel<R>, SrcCfg<R>::THREADS, src_smem);
-        if (e != cudaSuccess) return (int)e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&info->tube_ctas_per_sm, tube_kernel<R>, WARPS_PER_CTA * 32, tube_smem);
         if (e != cudaSuccess) return (int)e;
         cudaFuncAttributes fa;
         if (cudaFuncGetAttributes(&fa, tube_kernel<R>) == cudaSuccess) info->tube_regs = fa.numRegs;
         if (cudaFuncGetAttributes(&fa, tube_wide_kernel<R>) == cudaSuccess) info->wide_regs = fa.numRegs;
-        if (cudaFuncGetAttributes(&fa, src_kernel<R>) == cudaSuccess) info->src_regs = fa.numRegs;
         if (cudaFuncGetAttributes(&fa, pcm_kernel<R>) == cudaSuccess) info->pcm_regs = fa.numRegs;
     }
     return 0;
@@ -90,12 +107,17 @@ template <typename R> static int launch_tube_wide(const TubeArgs &a, int n_group
     return (int)cudaGetLastError();
 }
 
-template <typename R> static int launch_src(const SrcArgs &a, int grid, cudaStream_t s)
+template <typename R> static int launch_src(const SrcArgs &a, int grid, int shape, cudaStream_t s)
 {
     if (a.total_items <= 0) return 0;
     if ((long long)grid > a.total_items) grid = (int)a.total_items;
-    const size_t smem = src_smem_bytes<R>();
-    src_kernel<R><<<grid, SrcCfg<R>::THREADS, smem, s>>>(a);
+    if (shape == 0) {
+        src_kernel<R, 0><<<grid, SrcCfg<R, 0>::THREADS, src_smem_bytes<R, 0>(), s>>>(a);
+    } else if (shape == 1 && SrcShapes<R>::N == 2) {
+        if constexpr (SrcShapes<R>::N == 2) src_kernel<R, 1><<<grid, SrcCfg<R, 1>::THREADS, src_smem_bytes<R, 1>(), s>>>(a);
+    } else {
+        return (int)cudaErrorInvalidValue;
+    }
     return (int)cudaGetLastError();
 }
 
@@ -130,9 +152,9 @@ template <typename R> static int launch_pcm(const PcmArgs &a, long long max_n_ou
     {                                                                                                             \
         return trm::launch_tube_wide<R>(*a, n_groups, s);                                                         \
     }                                                                                                             \
-    extern "C" int trm_k_src_##SUF(const trm::SrcArgs *a, int grid, cudaStream_t s)                               \
+    extern "C" int trm_k_src_##SUF(const trm::SrcArgs *a, int grid, int shape, cudaStream_t s)                    \
     {                                                                                                             \
-        return trm::launch_src<R>(*a, grid, s);                                                                   \
+        return trm::launch_src<R>(*a, grid, shape, s);                                                            \
     }                                                                                                             \
     extern "C" int trm_k_src_ctab_##SUF(const void *tab, void *ctab, cudaStream_t s)                              \
     {                                                                                                             \

@@ -43,23 +43,30 @@ template <> struct Vec16<double> {
     __device__ __forceinline__ void store(double *p) const { *reinterpret_cast<double2 *>(p) = make_double2(e[0], e[1]); }
 };
 
-// Shape of the resampler per precision.  U = utterances per lane: a coefficient read from shared memory (a broadcast
-// 16-byte load returns 512 bytes to the warp's registers, and the SM delivers 128 bytes per clock) serves U multiply-adds;
-// with U = 1 that return path, not the arithmetic, bounded both precisions.  The FP64 register window (26 doubles per
-// utterance) leaves room for one utterance per lane only.  WINDOWS = 2 prefetches the next work item's window into a
-// second buffer (measured: no gain, the copy latency was already hidden by the other CTAs of the SM).
-template <typename R> struct SrcCfg {
-    static constexpr int U = sizeof(R) == 4 ? 2 : 1;
-    static constexpr int CBUFS = sizeof(R) == 4 ? 2 : 1;   // coefficient-row buffers (2: the next item's rows are prefetched)
-    static constexpr int TILE = 32 * U;                 // utterances per tile
-    static constexpr int WINDOWS = 1;
-    // elements per utterance row of the staged windows (SRC_ROWS + alignment slack).  Rows start on 16-byte boundaries
-    // (bulk-copy destinations), so the lanes of a warp reading the same element of their rows always collide somewhat;
-    // 132 floats / 130 doubles (= 4 banks mod 32) keep that to 4 / 2 lanes per bank
-    static constexpr int XLD = sizeof(R) == 4 ? 132 : 130;
-    static constexpr int THREADS = 256;
-    static constexpr int MIN_CTAS = 2;
+// Shapes of the resampler.  U = utterances per lane: a coefficient read from shared memory (a broadcast 16-byte load
+// returns 512 bytes to the warp's registers, and the SM delivers 128 bytes per clock) serves U multiply-adds; with U = 1
+// that return path, not the arithmetic, bounded both precisions.
+//   shape 0 handles every converter signature (both directions, windows up to TRM_SRC_ROWS rows).  FP32: U = 2.  FP64:
+//           U = 1 -- the register window is 52 registers per utterance.
+//   A second shape can be added per precision (SrcShapes<R>::N = 2; the launcher picks shape 1 for chunks whose
+//   utterances all up-sample with a window that fits it, trm_cuda.cu plan_chunk()).  Measured and not kept: FP64 with
+//   U = 2 -- 166 registers, so either one 12-warp CTA per SM (14.1 ms on 4096 x 10 s) or two 6-warp CTAs with work items
+//   half as long (<= 96 outputs, 76 staged rows: 12.0 ms), against 11.6 ms for shape 0.
+// WINDOWS = 2 prefetches the next work item's window into a second buffer (measured: no gain, the copy latency was
+// already hidden by the SM's other CTA).  CBUFS = 2 does the same for the coefficient rows (gain in FP32).
+// XLD: elements per utterance row of the staged windows (rows + alignment slack).  Rows start on 16-byte boundaries
+// (bulk-copy destinations), so the lanes of a warp reading the same element of their rows always collide somewhat;
+// strides of 4 banks mod 32 keep that to 4 (FP32) / 2 (FP64) lanes per bank.
+template <typename R, int SHAPE> struct SrcCfg;
+template <> struct SrcCfg<float, 0> {
+    static constexpr int U = 2, WINDOWS = 1, CBUFS = 2, THREADS = 256, MIN_CTAS = 2;
+    static constexpr int ROWS = SRC_ROWS, XLD = 132, NT_MAX = 192;
 };
+template <> struct SrcCfg<double, 0> {
+    static constexpr int U = 1, WINDOWS = 1, CBUFS = 1, THREADS = 256, MIN_CTAS = 2;
+    static constexpr int ROWS = SRC_ROWS, XLD = 130, NT_MAX = 192;
+};
+template <typename R> struct SrcShapes { static constexpr int N = 1; };
 
 template <typename R> __device__ __forceinline__ R r_abs(R x);
 template <> __device__ __forceinline__ double r_abs<double>(double x) { return fabs(x); }
@@ -88,20 +95,21 @@ template <> __device__ __forceinline__ float r_max<float>(float a, float b) { re
 //     items of an utterance only).
 // Accumulation order (left wing first, newest -> oldest, from 0.0) is the reference's; one multiply and one add per
 // tap.  Outputs go back through a small per-warp transpose tile and leave as 128-bit stores.
-template <typename R>
-__global__ void __launch_bounds__(SrcCfg<R>::THREADS, SrcCfg<R>::MIN_CTAS) src_kernel(SrcArgs args)
+template <typename R, int SHAPE>
+__global__ void __launch_bounds__(SrcCfg<R, SHAPE>::THREADS, SrcCfg<R, SHAPE>::MIN_CTAS) src_kernel(SrcArgs args)
 {
+    using Cfg = SrcCfg<R, SHAPE>;
     constexpr int A = 16 / (int)sizeof(R);                               // elements per 16 bytes
     constexpr int YLD = SRC_CHUNK + 1;
-    constexpr int U = SrcCfg<R>::U, TW = SrcCfg<R>::TILE;
-    constexpr int NBUF = SrcCfg<R>::WINDOWS;
+    constexpr int U = Cfg::U, TW = 32 * Cfg::U;
+    constexpr int NBUF = Cfg::WINDOWS, SRC_NT_MAX = Cfg::NT_MAX;
     constexpr unsigned FULL = 0xFFFFFFFFu;
-    constexpr int SRC_THREADS = SrcCfg<R>::THREADS, SRC_XLD = SrcCfg<R>::XLD;
+    constexpr int SRC_THREADS = Cfg::THREADS, SRC_XLD = Cfg::XLD;
     static_assert(SRC_THREADS >= SRC_NT_MAX, "one coefficient row per thread");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R *xU0 = reinterpret_cast<R *>(smem_raw);                            // [NBUF][TW][SRC_XLD] input windows, utterance-major
     R *Cf0 = xU0 + NBUF * TW * SRC_XLD;                                  // [CBUFS][SRC_NT_MAX][SRC_CLD] coefficient rows
-    R *yT = Cf0 + SrcCfg<R>::CBUFS * SRC_NT_MAX * SRC_CLD;                              // [warps][TW][YLD]
+    R *yT = Cf0 + Cfg::CBUFS * SRC_NT_MAX * SRC_CLD;                              // [warps][TW][YLD]
     __shared__ long long s_tube_off[TW], s_out_off[TW], s_n_in[TW], s_n_out[TW], s_out_start[TW], s_in_start[TW];
     __shared__ int s_tile;
     __shared__ unsigned long long s_bar[2], s_cbar[2];
@@ -251,7 +259,7 @@ __global__ void __launch_bounds__(SrcCfg<R>::THREADS, SrcCfg<R>::MIN_CTAS) src_k
         const R *const Cf = Cf0 + cb * SRC_NT_MAX * SRC_CLD;
         if (up) {
             if (!c_in_flight) request_rows(geo, cb);
-            if (SrcCfg<R>::CBUFS == 2 && more) request_rows(geometry(item + 1), cb ^ 1);
+            if (Cfg::CBUFS == 2 && more) request_rows(geometry(item + 1), cb ^ 1);
             // what follows output n for the warp that walks it: 0 = same input position, 1 = the integer part of the time
             // register advances (slide the window), 2 = last output of the warp's run
             if ((int)threadIdx.x < n_item) {
@@ -472,8 +480,8 @@ __global__ void __launch_bounds__(SrcCfg<R>::THREADS, SrcCfg<R>::MIN_CTAS) src_k
         }
         in_flight = prefetch;
         buf = (NBUF == 2) ? buf ^ 1 : 0;
-        c_in_flight = SrcCfg<R>::CBUFS == 2 && up && more;
-        cb = (SrcCfg<R>::CBUFS == 2) ? cb ^ 1 : 0;
+        c_in_flight = Cfg::CBUFS == 2 && up && more;
+        cb = (Cfg::CBUFS == 2) ? cb ^ 1 : 0;
     }
     if (item_hi > item_lo) flush_max();
 }

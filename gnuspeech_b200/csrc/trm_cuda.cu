@@ -24,8 +24,8 @@ int trm_k_tube_f64(const trm::TubeArgs *, cudaStream_t);
 int trm_k_tube_f32(const trm::TubeArgs *, cudaStream_t);
 int trm_k_tube_wide_f64(const trm::TubeArgs *, int, cudaStream_t);
 int trm_k_tube_wide_f32(const trm::TubeArgs *, int, cudaStream_t);
-int trm_k_src_f64(const trm::SrcArgs *, int, cudaStream_t);
-int trm_k_src_f32(const trm::SrcArgs *, int, cudaStream_t);
+int trm_k_src_f64(const trm::SrcArgs *, int, int, cudaStream_t);
+int trm_k_src_f32(const trm::SrcArgs *, int, int, cudaStream_t);
 int trm_k_src_ctab_f64(const void *, void *, cudaStream_t);
 int trm_k_src_ctab_f32(const void *, void *, cudaStream_t);
 int trm_k_pcm_f64(const trm::PcmArgs *, long long, cudaStream_t);
@@ -137,6 +137,7 @@ struct DeviceChunk {
     int16_t *pcm = nullptr;
     long long total_items = 0, max_n_out = 0;
     int n_tiles = 0;
+    int src_shape = 0;                      // resampler shape the tiles were built for (KernelInfo::src[])
     size_t tube_elems = 0, out_elems = 0, pcm_elems = 0, frame_rows = 0;
 };
 
@@ -153,6 +154,7 @@ struct ChunkPlan {
     size_t frame_rows = 0;
     long long tube_lo = 0, out_lo = 0, pcm_lo = 0;   // host element offsets of the spans
     size_t tube_elems = 0, out_elems = 0, pcm_elems = 0;
+    int src_shape = 0;
     long long total_items = 0, max_n_out = 0;
     size_t n_tiles() const { return tile_nt.size(); }
     size_t arena_bytes(size_t esz, bool want_pcm) const
@@ -226,9 +228,20 @@ struct trm_cuda_resident {
 
 namespace {
 
-void plan_chunk(const trm_cuda_utterance *desc, int u0, int u1, const trm::KernelInfo &ki, ChunkPlan &p)
+int plan_chunk(const trm_cuda_utterance *desc, int u0, int u1, const trm::KernelInfo &ki, ChunkPlan &p)
 {
-    const int n = u1 - u0, tile_width = ki.src_tile;
+    const int n = u1 - u0;
+    // The faster up-sampling shape needs every utterance of the chunk to up-sample with a work-item window that fits it.
+    int shape = ki.n_src_shapes > 1 ? 1 : 0;
+    for (int u = u0; u < u1 && shape == 1; ++u) {
+        const auto &d = desc[u];
+        const trm::KernelInfo::SrcShape &s1 = ki.src[1];
+        const long long unit = (long long)trm::SRC_CHUNK * (s1.threads / 32);
+        if (!d.upsample || d.tri == 0 || (long long)((double)(s1.rows - 3 - 2 * (d.padSize + 1)) * 65536.0 / (double)d.tri) < unit) shape = 0;
+    }
+    const trm::KernelInfo::SrcShape &sh = ki.src[shape];
+    const int tile_width = sh.tile;
+    p.src_shape = shape;
     p.u0 = u0;
     p.u1 = u1;
     p.desc.assign(desc + u0, desc + u1);
@@ -289,10 +302,12 @@ void plan_chunk(const trm_cuda_utterance *desc, int u0, int u1, const trm::Kerne
                 const int reach = d0.padSize + 1;
                 // outputs per work item: the input window must fit SRC_ROWS, every warp of the CTA gets the same
                 // whole number of SRC_CHUNK-sized runs
-                const long long unit = d0.upsample ? (long long)trm::SRC_CHUNK * (ki.src_threads / 32) : (long long)trm::SRC_CHUNK;
-                long long nt = (long long)((double)(trm::SRC_ROWS - 3 - 2 * reach) * 65536.0 / (double)d0.tri);
-                nt = std::min<long long>(nt, trm::SRC_NT_MAX);
-                nt = std::max<long long>(unit, nt / unit * unit);
+                const long long unit = d0.upsample ? (long long)trm::SRC_CHUNK * (sh.threads / 32) : (long long)trm::SRC_CHUNK;
+                long long nt = (long long)((double)(sh.rows - 3 - 2 * reach) * 65536.0 / (double)d0.tri);
+                // (libtrm refuses such rate pairs when it derives the descriptor; this guards the C-ABI itself)
+                if (nt < unit) return fail_msg("resampler: the input window of one work item does not fit the staged rows (rate ratio too small)");
+                nt = std::min<long long>(nt, sh.nt_max);
+                nt = nt / unit * unit;
                 long long first = d0.n_out;                  // streaming: the tile starts at its earliest missing output
                 for (int r = at; r < end; ++r) first = std::min<long long>(first, p.desc[idx[r]].out_start);
                 first = first / nt * nt;
@@ -312,6 +327,7 @@ void plan_chunk(const trm_cuda_utterance *desc, int u0, int u1, const trm::Kerne
     std::iota(p.order.begin(), p.order.end(), 0);
     std::stable_sort(p.order.begin(), p.order.end(),
                      [&](int a, int b) { return p.desc[a].n_tube > p.desc[b].n_tube; });
+    return 0;
 }
 
 void carve(Arena &a, const ChunkPlan &p, size_t esz, bool want_pcm, DeviceChunk &dc)
@@ -333,6 +349,7 @@ void carve(Arena &a, const ChunkPlan &p, size_t esz, bool want_pcm, DeviceChunk 
     dc.pcm = want_pcm ? (int16_t *)a.take(p.pcm_elems * sizeof(int16_t)) : nullptr;
     dc.total_items = p.total_items;
     dc.n_tiles = (int)p.n_tiles();
+    dc.src_shape = p.src_shape;
     dc.max_n_out = p.max_n_out;
     dc.tube_elems = p.tube_elems; dc.out_elems = p.out_elems; dc.pcm_elems = p.pcm_elems; dc.frame_rows = p.frame_rows;
 }
@@ -420,8 +437,8 @@ int launch_stage(trm_cuda_ctx *ctx, int precision, int stage, const DeviceChunk 
         a.item_base = dc.item_base;
         a.n_tiles = dc.n_tiles; a.total_items = dc.total_items;
         const trm::KernelInfo &ki = f64 ? ctx->info64 : ctx->info32;
-        const int grid = ctx->sm_count * std::max(1, ki.src_ctas_per_sm);
-        rc = f64 ? trm_k_src_f64(&a, grid, s) : trm_k_src_f32(&a, grid, s);
+        const int grid = ctx->sm_count * std::max(1, ki.src[dc.src_shape].ctas_per_sm);
+        rc = f64 ? trm_k_src_f64(&a, grid, dc.src_shape, s) : trm_k_src_f32(&a, grid, dc.src_shape, s);
     } else if (stage == TRM_STAGE_PCM) {
         if (!dc.pcm) return 0;
         trm::PcmArgs a{};
@@ -699,7 +716,7 @@ int trm_cuda_synthesize_host(trm_cuda_ctx *ctx, int precision, int n, const trm_
         if (slot_chunk[slot] >= 0 && (rc = finish_slot(slot)) != 0) return rc;
         ChunkPlan &p = plans[slot];
         const int u0 = ci * per_chunk, u1 = std::min(n, u0 + per_chunk);
-        plan_chunk(desc, u0, u1, precision == 0 ? ctx->info64 : ctx->info32, p);
+        if ((rc = plan_chunk(desc, u0, u1, precision == 0 ? ctx->info64 : ctx->info32, p)) != 0) return rc;
         if ((rc = ctx->arenas[slot].reserve(p.arena_bytes(esz, want_pcm))) != 0) return rc;
         if ((rc = ctx->stages[slot].reserve(p.stage_bytes())) != 0) return rc;
         DeviceChunk dc;
@@ -959,7 +976,7 @@ int trm_cuda_stream_push(trm_cuda_stream *s, const double *frames_host, int m, i
     }
     if (target - s->in_start > s->cap_tube || out_total - s->out_done / 4 * 4 > s->cap_out) return fail_msg("trm_cuda_stream_push: internal capacity");
     ChunkPlan plan;
-    plan_chunk(ds.data(), 0, n, ki, plan);
+    if (plan_chunk(ds.data(), 0, n, ki, plan) != 0) return -1;
     // plan_chunk rebases offsets to the chunk's span: streaming keeps its own (virtual) offsets
     for (int u = 0; u < n; ++u) { plan.desc[u].tube_offset = ds[u].tube_offset; plan.desc[u].out_offset = ds[u].out_offset; plan.desc[u].frame_offset = 0; }
     size_t bytes = plan.stage_bytes() + align_up((size_t)n * sizeof(trm_cuda_utterance), 256) + 1024;
@@ -978,7 +995,7 @@ int trm_cuda_stream_push(trm_cuda_stream *s, const double *frames_host, int m, i
     dc.item_base = (long long *)s->scratch.take(plan.item_base.size() * sizeof(long long));
     dc.maxbits = (unsigned long long *)s->scratch.take((size_t)n * sizeof(unsigned long long));
     auto *d_dt = (trm_cuda_utterance *)s->scratch.take((size_t)n * sizeof(trm_cuda_utterance));
-    dc.total_items = plan.total_items; dc.n_tiles = (int)plan.n_tiles(); dc.max_n_out = plan.max_n_out;
+    dc.total_items = plan.total_items; dc.n_tiles = (int)plan.n_tiles(); dc.max_n_out = plan.max_n_out; dc.src_shape = plan.src_shape;
     {
         unsigned char *q = s->stage.base;
         auto put = [&](void *dst, const void *src, size_t b) -> int {
@@ -1022,8 +1039,8 @@ int trm_cuda_stream_push(trm_cuda_stream *s, const double *frames_host, int m, i
         a.ctab = f64 ? ctx->d_ctab_f64 : ctx->d_ctab_f32;
         a.tile_utt = dc.tile_utt; a.tile_nt = dc.tile_nt; a.tile_max_out = dc.tile_max_out; a.tile_first_out = dc.tile_first_out;
         a.item_base = dc.item_base; a.n_tiles = dc.n_tiles; a.total_items = dc.total_items;
-        const int grid = ctx->sm_count * std::max(1, ki.src_ctas_per_sm);
-        rc = f64 ? trm_k_src_f64(&a, grid, st) : trm_k_src_f32(&a, grid, st);
+        const int grid = ctx->sm_count * std::max(1, ki.src[dc.src_shape].ctas_per_sm);
+        rc = f64 ? trm_k_src_f64(&a, grid, dc.src_shape, st) : trm_k_src_f32(&a, grid, dc.src_shape, st);
         if (rc != 0) return fail("stream resampler launch", (cudaError_t)rc);
         if (samples_host)
             CK(cudaMemcpy2DAsync(samples_host, (size_t)s->cap_out * s->esz, s->d_out + (size_t)(s->out_done % 4) * s->esz,
@@ -1073,8 +1090,8 @@ int trm_cuda_resident_create(trm_cuda_ctx *ctx, int precision, int n, const trm_
     trm_cuda_resident *r = new trm_cuda_resident();
     r->ctx = ctx;
     r->precision = precision;
-    plan_chunk(desc, 0, n, precision == 0 ? ctx->info64 : ctx->info32, r->plan);
     int rc;
+    if ((rc = plan_chunk(desc, 0, n, precision == 0 ? ctx->info64 : ctx->info32, r->plan)) != 0) { delete r; return rc; }
     if ((rc = r->arena.reserve(r->plan.arena_bytes(esz, true))) != 0) { delete r; return rc; }
     carve(r->arena, r->plan, esz, true, r->dc);
     if ((rc = upload_plan(r->plan, r->dc, nullptr, 0)) != 0 || (rc = upload_frames(r->plan, r->dc, desc, frames_host, 0)) != 0) {

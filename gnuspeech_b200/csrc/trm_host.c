@@ -351,7 +351,6 @@ static int voice_lookup(voice_set *vs, const TRMInputParameters *ip, voice_key *
 /* ------------------------------------------------------------------------------------------------
  * per-utterance descriptor: -initWithInputData: (TRMTubeModel.m:196-241)
  * ---------------------------------------------------------------------------------------------- */
-#define SRC_ROWS 256          /* input rows the resampler stages per work item (kernel_args.h) */
 
 static void radrefl_coefficients(double coeff, double *f)
 {
@@ -370,7 +369,9 @@ static int describe(const TRMInputParameters *ip, int32_t n_frames, voice_set *v
     if (n_frames < 0) return set_err(TRM_ERR_PARAM, "negative frame count%s", "");
     if (ip->channels != 1 && ip->channels != 2) return set_err(TRM_ERR_PARAM, "channels must be 1 or 2%s", "");
     /* the resampler stages a bounded input window per output tile */
-    if ((double)(SRC_ROWS - 3 - 2 * (r.padSize + 1)) * r.ratio < 16.0)
+    /* (an item's outputs span (rows - halo) * ratio of them; the kernels need at least 8 when down-sampling and one
+     * 8-output run per warp, up to 12 warps, when up-sampling) */
+    if ((double)(TRM_SRC_ROWS - 3 - 2 * (r.padSize + 1)) * r.ratio < (r.upsample ? 96.0 : 8.0))
         return set_err(TRM_ERR_PARAM, "outputRate / tube sample rate below the supported ratio%s", "");
     voice_key vk;
     const int voice = voice_lookup(vs, ip, &vk);

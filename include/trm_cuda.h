@@ -28,6 +28,9 @@ extern "C" {
 #define TRM_TABLE_LENGTH     512       /* TRMWavetable.m:22 */
 #define TRM_NOISE_JUMP       16        /* noise powers 377^0..377^16 mod 2^44 */
 #define TRM_ALIGN_ELEMS      32        /* every per-utterance buffer offset is a multiple of this */
+#define TRM_SRC_ROWS         128       /* tube-rate samples per utterance the converter kernel stages for one work item;
+                                          bounds the rate ratios libtrm accepts (an item needs 2*(padSize+1)+3 rows of
+                                          halo plus its outputs' span) */
 
 enum { TRM_STAGE_TUBE = 0, TRM_STAGE_SRC = 1, TRM_STAGE_PCM = 2, TRM_STAGE_COUNT = 3 };
 

@@ -115,6 +115,8 @@ def test_mixed_voices_down_sampling_stereo_sine(precision):
         g.TRMInputParameters(44100.0, waveform=1),
         g.TRMInputParameters(44100.0, usesModulation=0, breathiness=4.0, lossFactor=1.5),
         g.TRMInputParameters(44100.0, tp=30.0, tnMin=12.0, tnMax=40.0, mixOffset=48.0, throatVol=12.0),
+        g.TRMInputParameters(22050.0, length=5.0),     # 70 kHz tube rate: ratio 0.315, pad 42 -- the converter window nearly
+                                                       # fills the 128 staged rows (8 outputs per work item)
     ]
     n_frames = [101] * len(ips)
     frames = W.random_walk(len(ips), 101, seed=33)

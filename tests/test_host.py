@@ -122,6 +122,17 @@ def test_error_behaviour_mirrors_reference():
         g.TRMTubeModel(dl)
     assert e.value.code == -4
     dl.inputParameters.channels = 1
+    # rate pairs whose converter window (2*(padSize+1)+3 halo rows + the outputs' span) cannot fit the TRM_SRC_ROWS = 128
+    # rows the kernel stages are refused when the descriptor is derived; a 5 cm tube at 22.05 kHz still fits
+    dl.inputParameters.outputRate = 22050.0
+    dl.inputParameters.length = 4.0                           # 87.5 kHz tube rate: ratio 0.25, 52 pad samples per wing
+    with pytest.raises(g.TRMError) as e:
+        g.TRMTubeModel(dl)
+    assert e.value.code == -4
+    dl.inputParameters.length = 5.0
+    assert g.TRMTubeModel(dl) is not None
+    dl.inputParameters.length = 17.5
+    dl.inputParameters.outputRate = 44100.0
     m = g.TRMTubeModel(dl)                                    # zero frames: synthesize returns without output
     m.synthesize()
     assert m.numberSamples == 0
