@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <mutex>
 #include <numeric>
 #include <string>
@@ -660,6 +661,14 @@ int trm_cuda_synthesize_host(trm_cuda_ctx *ctx, int precision, int n, const trm_
                              const double *frames_host, int16_t *pcm_host, void *samples_host, double *max_host,
                              void *tube_host, int64_t *launches)
 {
+    return trm_cuda_synthesize_host_ex(ctx, precision, n, desc, frames_host, pcm_host, samples_host, max_host, tube_host, launches,
+                                       nullptr, nullptr);
+}
+
+int trm_cuda_synthesize_host_ex(trm_cuda_ctx *ctx, int precision, int n, const trm_cuda_utterance *desc,
+                                const double *frames_host, int16_t *pcm_host, void *samples_host, double *max_host,
+                                void *tube_host, int64_t *launches, void (*enqueued)(void *), void *enqueued_arg)
+{
     if (launches) *launches = 0;
     if (n <= 0) return 0;
     CK(cudaSetDevice(ctx->device));
@@ -677,6 +686,8 @@ int trm_cuda_synthesize_host(trm_cuda_ctx *ctx, int precision, int n, const trm_
     std::vector<cudaEvent_t> tev;
     static cudaEvent_t t_origin = nullptr;          // one time axis for every traced call of the process
     static std::mutex t_mutex;
+    static double t_host0 = 0.0;
+    auto now_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec; };
     auto mark = [&](cudaStream_t st) {
         if (!trace) return;
         cudaEvent_t e;
@@ -686,8 +697,9 @@ int trm_cuda_synthesize_host(trm_cuda_ctx *ctx, int precision, int n, const trm_
     };
     if (trace) {
         std::lock_guard<std::mutex> lk(t_mutex);
-        if (!t_origin) { cudaEventCreate(&t_origin); cudaEventRecord(t_origin, s_out); cudaEventSynchronize(t_origin); }
+        if (!t_origin) { cudaEventCreate(&t_origin); cudaEventRecord(t_origin, s_out); cudaEventSynchronize(t_origin); t_host0 = now_ms(); }
     }
+    const double t_enter = trace ? now_ms() - t_host0 : 0.0;
     std::vector<ChunkPlan> plans(N_SLOTS);
     std::vector<int> slot_chunk(N_SLOTS, -1);
     int64_t n_launch = 0;
@@ -766,7 +778,9 @@ int trm_cuda_synthesize_host(trm_cuda_ctx *ctx, int precision, int n, const trm_
         CK(cudaEventRecord(ctx->ev_out[slot], s_out));
         mark(s_out);
         slot_chunk[slot] = ci;
+        if (ci == 0 && enqueued) enqueued(enqueued_arg);
     }
+    const double t_enqueued = trace ? now_ms() - t_host0 : 0.0;
     for (int slot = 0; slot < N_SLOTS; ++slot) {
         int rc;
         if (slot_chunk[slot] >= 0 && (rc = finish_slot(slot)) != 0) return rc;
@@ -779,6 +793,7 @@ int trm_cuda_synthesize_host(trm_cuda_ctx *ctx, int precision, int n, const trm_
             for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&t[k], t_origin, tev[i + k]);
             fprintf(stderr, "[trm trace] %2zu: %8.2f %8.2f %8.2f %8.2f %8.2f %8.2f\n", i / 6, t[0], t[1], t[2], t[3], t[4], t[5]);
         }
+        fprintf(stderr, "[trm trace] host: entered %.2f, everything enqueued %.2f, outputs complete %.2f\n", t_enter, t_enqueued, now_ms() - t_host0);
         for (auto e : tev) cudaEventDestroy(e);
     }
     if (launches) *launches = n_launch;

@@ -18,6 +18,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <strings.h>
 
 /* ------------------------------------------------------------------------------------------------
@@ -829,6 +830,8 @@ typedef struct {
     int device, u0, u1, rc;
     int64_t launches;
     char msg[512];
+    void (*enqueued)(void *);      /* asynchronous tickets: called when the shard's first chunk is in the device queues */
+    void *enqueued_arg;
 } shard_job;
 
 static void *shard_main(void *arg)
@@ -839,8 +842,9 @@ static void *shard_main(void *arg)
     j->rc = acquire_ctx(j->device, &ctx, &lane);
     if (j->rc == TRM_OK) {
         if (trm_cuda_set_wavetables(ctx, j->b->voices.tables, j->b->voices.n) != 0 ||
-            trm_cuda_synthesize_host(ctx, j->b->precision, j->u1 - j->u0, j->b->desc + j->u0, (const double *)j->frames,
-                                     j->pcm, j->samples, j->b->maxima + j->u0, j->tube, &j->launches) != 0)
+            trm_cuda_synthesize_host_ex(ctx, j->b->precision, j->u1 - j->u0, j->b->desc + j->u0, (const double *)j->frames,
+                                        j->pcm, j->samples, j->b->maxima + j->u0, j->tube, &j->launches, j->enqueued,
+                                        j->enqueued_arg) != 0)
             j->rc = cuda_err();
         release_ctx(j->device, lane);
     }
@@ -848,13 +852,42 @@ static void *shard_main(void *arg)
     return NULL;
 }
 
+/* Asynchronous tickets start in submission order: ticket k's shards put their first chunk into the device queues before
+ * ticket k+1 is let in.  (The copy-in and compute queues are shared per device, so without this the order in which the
+ * host threads happen to be scheduled decides which call runs first, and a caller waiting for its oldest ticket can
+ * find it executed last.) */
+static pthread_mutex_t g_order_mu = PTHREAD_MUTEX_INITIALIZER;
+static pthread_cond_t g_order_cv = PTHREAD_COND_INITIALIZER;
+static unsigned long long g_order_next = 0, g_order_turn = 0;
+typedef struct { unsigned long long seq; int pending, passed; } order_gate;
+
+static void gate_pass(order_gate *g)
+{
+    pthread_mutex_lock(&g_order_mu);
+    if (!g->passed) {
+        g->passed = 1;
+        g_order_turn = g->seq + 1;
+        pthread_cond_broadcast(&g_order_cv);
+    }
+    pthread_mutex_unlock(&g_order_mu);
+}
+static void gate_shard_enqueued(void *arg)
+{
+    order_gate *g = arg;
+    pthread_mutex_lock(&g_order_mu);
+    const int last = --g->pending <= 0;
+    pthread_mutex_unlock(&g_order_mu);
+    if (last) gate_pass(g);
+}
+
 static int batch_run(TRMBatch *b, const TRMParameters *frames, int16_t *pcm, void *samples, void *tube,
-                     const int *devices, int n_devices)
+                     const int *devices, int n_devices, order_gate *gate)
 {
     if (b->n == 0) return TRM_OK;
     if (n_devices < 1) n_devices = 1;
     if (n_devices > b->n) n_devices = b->n;
     if (n_devices > MAX_DEVICES) n_devices = MAX_DEVICES;
+    if (gate) gate->pending = n_devices;
     shard_job jobs[MAX_DEVICES];
     pthread_t th[MAX_DEVICES];
     /* contiguous shards with equal shares of the tube-rate work; no data crosses devices */
@@ -865,6 +898,7 @@ static int batch_run(TRMBatch *b, const TRMParameters *frames, int16_t *pcm, voi
         memset(&jobs[k], 0, sizeof jobs[k]);
         jobs[k].b = b; jobs[k].frames = frames; jobs[k].pcm = pcm; jobs[k].samples = samples; jobs[k].tube = tube;
         jobs[k].device = devices ? devices[k] : k;
+        if (gate) { jobs[k].enqueued = gate_shard_enqueued; jobs[k].enqueued_arg = gate; }
         jobs[k].u0 = u;
         if (k == n_devices - 1) u = b->n;
         else {
@@ -894,7 +928,7 @@ static int batch_run(TRMBatch *b, const TRMParameters *frames, int16_t *pcm, voi
 int TRMBatchSynthesize(TRMBatch *b, const TRMParameters *frames, int16_t *pcm_out, void *samples_out,
                        const int *devices, int n_devices)
 {
-    return batch_run(b, frames, pcm_out, samples_out, NULL, devices, n_devices);
+    return batch_run(b, frames, pcm_out, samples_out, NULL, devices, n_devices, NULL);
 }
 
 /* ---- control frames from event lists (EventList.m:883-1061) ---- */
@@ -1043,13 +1077,27 @@ struct TRMBatchTicket {
     int devices[MAX_DEVICES], n_devices, has_devices;
     int rc;
     char msg[512];
+    order_gate gate;
+    int inline_run;
 };
+
+static double host_ms(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec;
+}
 
 static void *ticket_main(void *arg)
 {
     TRMBatchTicket *t = arg;
-    t->rc = batch_run(t->b, t->frames, t->pcm, t->samples, NULL, t->has_devices ? t->devices : NULL, t->n_devices);
+    pthread_mutex_lock(&g_order_mu);
+    while (g_order_turn != t->gate.seq) pthread_cond_wait(&g_order_cv, &g_order_mu);
+    pthread_mutex_unlock(&g_order_mu);
+    t->rc = batch_run(t->b, t->frames, t->pcm, t->samples, NULL, t->has_devices ? t->devices : NULL, t->n_devices, &t->gate);
+    gate_pass(&t->gate);          /* (empty batches and error paths never reached the queues) */
     if (t->rc) snprintf(t->msg, sizeof t->msg, "%s", g_errmsg);
+    if (getenv("TRM_TRACE")) fprintf(stderr, "[trm trace] ticket %p: thread returns at %.2f (CLOCK_MONOTONIC ms)\n", (void *)t, host_ms());
     return NULL;
 }
 
@@ -1064,10 +1112,12 @@ TRMBatchTicket *TRMBatchSynthesizeAsync(TRMBatch *b, const TRMParameters *frames
     t->n_devices = n_devices > MAX_DEVICES ? MAX_DEVICES : n_devices;
     t->has_devices = devices != NULL;
     for (int k = 0; devices && k < t->n_devices; k++) t->devices[k] = devices[k];
+    pthread_mutex_lock(&g_order_mu);
+    t->gate.seq = g_order_next++;
+    pthread_mutex_unlock(&g_order_mu);
     if (pthread_create(&t->th, NULL, ticket_main, t) != 0) {
-        free(t);
-        *err = set_err(TRM_ERR_NOMEM, "cannot start a host thread%s", "");
-        return NULL;
+        t->inline_run = 1;        /* no thread: the call runs here, in its turn, and the ticket is complete on return */
+        ticket_main(t);
     }
     *err = TRM_OK;
     return t;
@@ -1076,7 +1126,9 @@ TRMBatchTicket *TRMBatchSynthesizeAsync(TRMBatch *b, const TRMParameters *frames
 int TRMBatchWait(TRMBatchTicket *t)
 {
     if (!t) return set_err(TRM_ERR_PARAM, "null ticket%s", "");
-    pthread_join(t->th, NULL);
+    const double t0 = getenv("TRM_TRACE") ? host_ms() : 0.0;
+    if (!t->inline_run) pthread_join(t->th, NULL);
+    if (getenv("TRM_TRACE")) fprintf(stderr, "[trm trace] ticket %p: wait entered %.2f, joined %.2f\n", (void *)t, t0, host_ms());
     const int rc = t->rc;
     if (rc) snprintf(g_errmsg, sizeof g_errmsg, "%s", t->msg);
     free(t);
@@ -1087,7 +1139,7 @@ int TRMBatchWait(TRMBatchTicket *t)
 int TRMBatchSynthesizeDebug(TRMBatch *b, const TRMParameters *frames, int16_t *pcm_out, void *samples_out,
                             void *tube_out, int device)
 {
-    return batch_run(b, frames, pcm_out, samples_out, tube_out, &device, 1);
+    return batch_run(b, frames, pcm_out, samples_out, tube_out, &device, 1, NULL);
 }
 
 /* ---- device-resident batches (bench `value`, per-stage timing) ---- */

@@ -124,6 +124,14 @@ int trm_cuda_synthesize_host(trm_cuda_ctx *ctx, int precision, int n, const trm_
                              const double *frames_host, int16_t *pcm_host, void *samples_host,
                              double *max_host, void *tube_host, int64_t *launches);
 
+/* Same call; `enqueued(arg)` (may be NULL) is invoked once, from the calling thread, as soon as the first chunk's copies
+ * and kernels are in the device queues -- libtrm's asynchronous tickets use it to start concurrent calls in submission
+ * order (the queues are shared per device, so the order of arrival there is the order of execution). */
+int trm_cuda_synthesize_host_ex(trm_cuda_ctx *ctx, int precision, int n, const trm_cuda_utterance *desc,
+                                const double *frames_host, int16_t *pcm_host, void *samples_host,
+                                double *max_host, void *tube_host, int64_t *launches,
+                                void (*enqueued)(void *), void *arg);
+
 /*
  * Device-resident path (bench `value`, roofline timing): inputs uploaded once, stages launched on the
  * caller's stream (a cudaStream_t passed as void*, NULL = the legacy default stream) without any
