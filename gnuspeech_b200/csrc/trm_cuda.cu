@@ -884,7 +884,6 @@ int trm_cuda_stream_create(trm_cuda_ctx *ctx, int precision, int n_streams, cons
 {
     *out = nullptr;
     if (n_streams <= 0 || max_frames_per_push <= 0) return fail_msg("trm_cuda_stream_create: bad sizes");
-    if (!voice->upsample) return fail_msg("trm_cuda_stream_create: streaming supports up-sampling voices (tube rate <= output rate) only");
     CK(cudaSetDevice(ctx->device));
     trm_cuda_stream *s = new trm_cuda_stream();
     s->ctx = ctx; s->precision = precision; s->n = n_streams; s->max_m = max_frames_per_push;

@@ -71,3 +71,27 @@ def test_stream_latency_and_other_voice():
     y = np.concatenate(got, axis=1)
     for u in range(n):
         assert np.array_equal(y[u], want[u]), u
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_down_sampling_voice_streams_too(precision):
+    """A 10 cm tract at 22.05 kHz output: the tube runs at 35 kHz and the converter down-samples (phase-walking taps, 22
+    pad samples per wing).  Same contract: the pushes concatenate to the one-shot result, bit for bit."""
+    g = _g()
+    from gnuspeech_b200 import workloads as W
+    ip = g.TRMInputParameters(22050.0, length=10.0)
+    pushes = [9, 1, 2, 30, 5, 17]
+    n, nf = 3, sum(pushes)
+    frames = W.random_walk(n, nf, seed=29).reshape(n, nf, 16)
+    want = _one_shot(ip, frames, n, nf, precision)
+    st = g.TRMStream(n, ip, precision=precision, max_frames_per_push=max(pushes))
+    got, at = [], 0
+    for k, m in enumerate(pushes):
+        got.append(st.push(frames[:, at:at + m], flush=(k == len(pushes) - 1)))
+        at += m
+    st.free()
+    y = np.concatenate(got, axis=1)
+    for u in range(n):
+        assert y[u].shape == want[u].shape, (u, y[u].shape, want[u].shape)
+        assert np.array_equal(y[u], want[u]), "stream %d: %d samples differ, first at %d" % (
+            u, int((y[u] != want[u]).sum()), int(np.nonzero(y[u] != want[u])[0][0]))
