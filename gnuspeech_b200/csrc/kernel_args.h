@@ -62,6 +62,7 @@ struct SrcArgs {
     const long long *item_base;      // [n_tiles+1] prefix sum of work items
     int n_tiles;
     long long total_items;
+    long long item_begin, item_end;  // work items this launch processes ([0, total_items) when item_end == 0)
 };
 
 struct PcmArgs {
@@ -70,6 +71,7 @@ struct PcmArgs {
     const void *out;                 // Real[]
     const unsigned long long *maxbits;
     int16_t *pcm;
+    int u_begin;                     // utterances [u_begin, n_utt) are scaled by this launch
 };
 
 // control-frame generator (framegen_kernel.cuh)

@@ -109,8 +109,9 @@ template <typename R> static int launch_tube_wide(const TubeArgs &a, int n_group
 
 template <typename R> static int launch_src(const SrcArgs &a, int grid, int shape, cudaStream_t s)
 {
-    if (a.total_items <= 0) return 0;
-    if ((long long)grid > a.total_items) grid = (int)a.total_items;
+    const long long items = (a.item_end > 0 ? a.item_end : a.total_items) - a.item_begin;
+    if (items <= 0) return 0;
+    if ((long long)grid > items) grid = (int)items;
     if (shape == 0) {
         src_kernel<R, 0><<<grid, SrcCfg<R, 0>::THREADS, src_smem_bytes<R, 0>(), s>>>(a);
     } else if (shape == 1 && SrcShapes<R>::N == 2) {
@@ -130,11 +131,11 @@ template <typename R> static int launch_src_ctab(const void *tab, void *ctab, cu
 
 template <typename R> static int launch_pcm(const PcmArgs &a, long long max_n_out, cudaStream_t s)
 {
-    if (a.n_utt <= 0 || max_n_out <= 0) return 0;
+    if (a.n_utt - a.u_begin <= 0 || max_n_out <= 0) return 0;
     const long long per_cta = (long long)PCM_THREADS * PCM_PER_THREAD;
     const long long bpu = (max_n_out + per_cta - 1) / per_cta;
     if (bpu > 0x7FFFFFFFll) return (int)cudaErrorInvalidConfiguration;
-    dim3 grid((unsigned)bpu, (unsigned)(a.n_utt < 65535 ? a.n_utt : 65535));
+    dim3 grid((unsigned)bpu, (unsigned)(a.n_utt - a.u_begin < 65535 ? a.n_utt - a.u_begin : 65535));
     pcm_kernel<R><<<grid, PCM_THREADS, 0, s>>>(a);
     return (int)cudaGetLastError();
 }

@@ -133,9 +133,10 @@ __global__ void __launch_bounds__(SrcCfg<R, SHAPE>::THREADS, SrcCfg<R, SHAPE>::M
 
     // every CTA takes a contiguous range of work items: consecutive items belong to the same tile, whose descriptors
     // are read from global memory once and kept in shared memory
-    const long long per_cta = (args.total_items + gridDim.x - 1) / gridDim.x;
-    const long long item_lo = (long long)blockIdx.x * per_cta;
-    const long long item_hi = (item_lo + per_cta < args.total_items) ? item_lo + per_cta : args.total_items;
+    const long long range_lo = args.item_begin, range_hi = args.item_end > 0 ? args.item_end : args.total_items;
+    const long long per_cta = (range_hi - range_lo + gridDim.x - 1) / gridDim.x;
+    const long long item_lo = range_lo + (long long)blockIdx.x * per_cta;
+    const long long item_hi = (item_lo + per_cta < range_hi) ? item_lo + per_cta : range_hi;
     long long tile_first = 0, tile_end = 0;                              // items [tile_first, tile_end) belong to `tile`
     int tile = 0;
     unsigned tri = 0, phaseIncrement = 0;
@@ -509,7 +510,7 @@ template <typename R>
 __global__ void __launch_bounds__(PCM_THREADS) pcm_kernel(PcmArgs args)
 {
   // blockIdx.y strides over the utterances (gridDim.y is capped at 65,535; larger batches loop)
-  for (int u = blockIdx.y; u < args.n_utt; u += gridDim.y) {
+  for (int u = args.u_begin + blockIdx.y; u < args.n_utt; u += gridDim.y) {
     const trm_cuda_utterance *__restrict__ D = args.desc + u;
     const long long n_out = D->n_out;
     const long long n0 = ((long long)blockIdx.x * PCM_THREADS + threadIdx.x) * PCM_PER_THREAD;

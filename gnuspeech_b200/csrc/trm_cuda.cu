@@ -71,6 +71,7 @@ int fail_msg(const char *what)
     } while (0)
 
 constexpr int MAX_SLOTS = 16;  // upper bound of chunks in flight (each on its own stream and arena)
+constexpr int MAX_OUT_GROUPS = 4;   // output groups of a chunk (ChunkPlan::groups)
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -156,6 +157,10 @@ struct ChunkPlan {
     long long tube_lo = 0, out_lo = 0, pcm_lo = 0;   // host element offsets of the spans
     size_t tube_elems = 0, out_elems = 0, pcm_elems = 0;
     int src_shape = 0;
+    // Output groups: contiguous utterance ranges whose resampling + scaling is launched separately, so that the PCM of
+    // one group can leave for the host while the next group is still being resampled (tiles never span groups).
+    struct Group { int u_begin, u_end; long long item_begin, item_end, max_n_out, pcm_lo, pcm_hi; };
+    std::vector<Group> groups;
     long long total_items = 0, max_n_out = 0;
     size_t n_tiles() const { return tile_nt.size(); }
     size_t arena_bytes(size_t esz, bool want_pcm) const
@@ -216,6 +221,7 @@ struct trm_cuda_ctx {
     HostStage stages[MAX_SLOTS];
     int n_slots = 3;              // chunks in flight: one uploading, one computing, one downloading
     cudaEvent_t ev_in[MAX_SLOTS]{}, ev_run[MAX_SLOTS]{}, ev_out[MAX_SLOTS]{};
+    cudaEvent_t ev_grp[MAX_SLOTS][MAX_OUT_GROUPS]{};   // a group's PCM is complete (copy-out of the group may start)
     int wide_min_utt = 0;         // batches at least this large use the batch-throughput waveguide mapping
 };
 
@@ -229,7 +235,7 @@ struct trm_cuda_resident {
 
 namespace {
 
-int plan_chunk(const trm_cuda_utterance *desc, int u0, int u1, const trm::KernelInfo &ki, ChunkPlan &p)
+int plan_chunk(const trm_cuda_utterance *desc, int u0, int u1, const trm::KernelInfo &ki, ChunkPlan &p, int want_groups = 1)
 {
     const int n = u1 - u0;
     // The faster up-sampling shape needs every utterance of the chunk to up-sample with a work-item window that fits it.
@@ -281,44 +287,69 @@ int plan_chunk(const trm_cuda_utterance *desc, int u0, int u1, const trm::Kernel
     {
         // resampler tiles: utterances that share (time-register increment, pad, direction, phase increment,
         // ratio) share every filter coefficient; longest first so the rows of a tile finish together
-        std::vector<int> idx(n);
-        std::iota(idx.begin(), idx.end(), 0);
         auto key = [&](int a) {
             const auto &d = p.desc[a];
             unsigned long long rb;
             memcpy(&rb, &d.sampleRateRatio, sizeof rb);
             return std::make_tuple(d.tri, d.padSize, d.upsample, d.phaseIncrement, rb);
         };
-        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
-            const auto ka = key(a), kb = key(b);
-            if (ka != kb) return ka < kb;
-            return p.desc[a].n_out > p.desc[b].n_out;
-        });
+        // group boundaries: contiguous index ranges with about equal shares of the output samples
+        long long out_sum = 0;
+        for (const auto &d : p.desc) out_sum += d.n_out;
+        const int n_groups = std::max(1, std::min(want_groups, n / std::max(1, tile_width)));
+        p.groups.clear();
         p.tile_utt.clear(); p.tile_nt.clear(); p.tile_max_out.clear(); p.tile_first_out.clear(); p.item_base.assign(1, 0);
-        for (int at = 0; at < n;) {
-            int end = at;
-            while (end < n && end - at < tile_width && key(idx[end]) == key(idx[at])) ++end;
-            const auto &d0 = p.desc[idx[at]];
-            if (d0.n_out > 0) {
-                const int reach = d0.padSize + 1;
-                // outputs per work item: the input window must fit SRC_ROWS, every warp of the CTA gets the same
-                // whole number of SRC_CHUNK-sized runs
-                const long long unit = d0.upsample ? (long long)trm::SRC_CHUNK * (sh.threads / 32) : (long long)trm::SRC_CHUNK;
-                long long nt = (long long)((double)(sh.rows - 3 - 2 * reach) * 65536.0 / (double)d0.tri);
-                // (libtrm refuses such rate pairs when it derives the descriptor; this guards the C-ABI itself)
-                if (nt < unit) return fail_msg("resampler: the input window of one work item does not fit the staged rows (rate ratio too small)");
-                nt = std::min<long long>(nt, sh.nt_max);
-                nt = nt / unit * unit;
-                long long first = d0.n_out;                  // streaming: the tile starts at its earliest missing output
-                for (int r = at; r < end; ++r) first = std::min<long long>(first, p.desc[idx[r]].out_start);
-                first = first / nt * nt;
-                for (int r = 0; r < tile_width; ++r) p.tile_utt.push_back(at + r < end ? idx[at + r] : -1);
-                p.tile_nt.push_back((int)nt);
-                p.tile_max_out.push_back(d0.n_out);
-                p.tile_first_out.push_back(first);
-                p.item_base.push_back(p.item_base.back() + (d0.n_out - first + nt - 1) / nt);
+        int g_at = 0;
+        long long acc = 0;
+        for (int g = 0; g < n_groups; ++g) {
+            int g_end = g_at;
+            if (g == n_groups - 1) g_end = n;
+            else
+                while (g_end < n - (n_groups - 1 - g) && (g_end == g_at || acc + p.desc[g_end].n_out <= out_sum * (g + 1) / n_groups)) acc += p.desc[g_end++].n_out;
+            ChunkPlan::Group grp{g_at, g_end, p.item_base.back(), 0, 0, INT64_MAX, 0};
+            std::vector<int> idx(g_end - g_at);
+            std::iota(idx.begin(), idx.end(), g_at);
+            std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
+                const auto ka = key(a), kb = key(b);
+                if (ka != kb) return ka < kb;
+                return p.desc[a].n_out > p.desc[b].n_out;
+            });
+            const int m = (int)idx.size();
+            for (int at = 0; at < m;) {
+                int end = at;
+                while (end < m && end - at < tile_width && key(idx[end]) == key(idx[at])) ++end;
+                const auto &d0 = p.desc[idx[at]];
+                if (d0.n_out > 0) {
+                    const int reach = d0.padSize + 1;
+                    // outputs per work item: the input window must fit the staged rows, every warp of the CTA gets the
+                    // same whole number of SRC_CHUNK-sized runs
+                    const long long unit = d0.upsample ? (long long)trm::SRC_CHUNK * (sh.threads / 32) : (long long)trm::SRC_CHUNK;
+                    long long nt = (long long)((double)(sh.rows - 3 - 2 * reach) * 65536.0 / (double)d0.tri);
+                    // (libtrm refuses such rate pairs when it derives the descriptor; this guards the C-ABI itself)
+                    if (nt < unit) return fail_msg("resampler: the input window of one work item does not fit the staged rows (rate ratio too small)");
+                    nt = std::min<long long>(nt, sh.nt_max);
+                    nt = nt / unit * unit;
+                    long long first = d0.n_out;              // streaming: the tile starts at its earliest missing output
+                    for (int r = at; r < end; ++r) first = std::min<long long>(first, p.desc[idx[r]].out_start);
+                    first = first / nt * nt;
+                    for (int r = 0; r < tile_width; ++r) p.tile_utt.push_back(at + r < end ? idx[at + r] : -1);
+                    p.tile_nt.push_back((int)nt);
+                    p.tile_max_out.push_back(d0.n_out);
+                    p.tile_first_out.push_back(first);
+                    p.item_base.push_back(p.item_base.back() + (d0.n_out - first + nt - 1) / nt);
+                }
+                at = end;
             }
-            at = end;
+            grp.item_end = p.item_base.back();
+            for (int u = g_at; u < g_end; ++u) {
+                const auto &d = p.desc[u];
+                grp.max_n_out = std::max<long long>(grp.max_n_out, d.n_out);
+                grp.pcm_lo = std::min<long long>(grp.pcm_lo, d.pcm_offset);
+                grp.pcm_hi = std::max<long long>(grp.pcm_hi, d.pcm_offset + d.n_out * d.channels);
+            }
+            if (grp.pcm_lo > grp.pcm_hi) grp.pcm_lo = grp.pcm_hi = 0;
+            p.groups.push_back(grp);
+            g_at = g_end;
         }
         p.total_items = p.item_base.back();
     }
@@ -416,7 +447,7 @@ int wide_groups(const trm_cuda_ctx *ctx, const trm::KernelInfo &ki, int n)
     return waves * sm;
 }
 
-int launch_stage(trm_cuda_ctx *ctx, int precision, int stage, const DeviceChunk &dc, cudaStream_t s)
+int launch_stage(trm_cuda_ctx *ctx, int precision, int stage, const DeviceChunk &dc, cudaStream_t s, const ChunkPlan::Group *grp = nullptr)
 {
     const bool f64 = precision == 0;
     int rc = 0;
@@ -429,7 +460,8 @@ int launch_stage(trm_cuda_ctx *ctx, int precision, int stage, const DeviceChunk 
         if (groups > 0) rc = f64 ? trm_k_tube_wide_f64(&a, groups, s) : trm_k_tube_wide_f32(&a, groups, s);
         else rc = f64 ? trm_k_tube_f64(&a, s) : trm_k_tube_f32(&a, s);
     } else if (stage == TRM_STAGE_SRC) {
-        CK(cudaMemsetAsync(dc.maxbits, 0, (size_t)dc.n * sizeof(unsigned long long), s));
+        // (the running maxima are cleared once per chunk: by the ungrouped launch, or by the first group's)
+        if (!grp || grp->u_begin == 0) CK(cudaMemsetAsync(dc.maxbits, 0, (size_t)dc.n * sizeof(unsigned long long), s));
         trm::SrcArgs a{};
         a.desc = dc.desc; a.n_utt = dc.n; a.tube = dc.tube; a.out = dc.out; a.maxbits = dc.maxbits;
         a.table = f64 ? ctx->d_tab_f64 : ctx->d_tab_f32;
@@ -437,14 +469,17 @@ int launch_stage(trm_cuda_ctx *ctx, int precision, int stage, const DeviceChunk 
         a.tile_utt = dc.tile_utt; a.tile_nt = dc.tile_nt; a.tile_max_out = dc.tile_max_out; a.tile_first_out = dc.tile_first_out;
         a.item_base = dc.item_base;
         a.n_tiles = dc.n_tiles; a.total_items = dc.total_items;
+        if (grp) { a.item_begin = grp->item_begin; a.item_end = grp->item_end; if (a.item_end <= a.item_begin) return 0; }
         const trm::KernelInfo &ki = f64 ? ctx->info64 : ctx->info32;
         const int grid = ctx->sm_count * std::max(1, ki.src[dc.src_shape].ctas_per_sm);
         rc = f64 ? trm_k_src_f64(&a, grid, dc.src_shape, s) : trm_k_src_f32(&a, grid, dc.src_shape, s);
     } else if (stage == TRM_STAGE_PCM) {
         if (!dc.pcm) return 0;
         trm::PcmArgs a{};
-        a.desc = dc.desc; a.n_utt = dc.n; a.out = dc.out; a.maxbits = dc.maxbits; a.pcm = dc.pcm;
-        rc = f64 ? trm_k_pcm_f64(&a, dc.max_n_out, s) : trm_k_pcm_f32(&a, dc.max_n_out, s);
+        a.desc = dc.desc; a.n_utt = grp ? grp->u_end : dc.n; a.u_begin = grp ? grp->u_begin : 0;
+        a.out = dc.out; a.maxbits = dc.maxbits; a.pcm = dc.pcm;
+        const long long longest = grp ? grp->max_n_out : dc.max_n_out;
+        rc = f64 ? trm_k_pcm_f64(&a, longest, s) : trm_k_pcm_f32(&a, longest, s);
     }
     if (rc != 0) return fail("kernel launch", (cudaError_t)rc);
     return 0;
@@ -608,6 +643,7 @@ int trm_cuda_ctx_create(int device, const trm_cuda_tables *t, trm_cuda_ctx **out
             CK(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&c->ev_run[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
+            for (int g = 0; g < MAX_OUT_GROUPS; ++g) CK(cudaEventCreateWithFlags(&c->ev_grp[i][g], cudaEventDisableTiming));
         }
     }
     *out = c;
@@ -645,6 +681,7 @@ void trm_cuda_ctx_destroy(trm_cuda_ctx *c)
         if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
         if (c->ev_run[i]) cudaEventDestroy(c->ev_run[i]);
         if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
+        for (int g = 0; g < MAX_OUT_GROUPS; ++g) if (c->ev_grp[i][g]) cudaEventDestroy(c->ev_grp[i][g]);
     }
     for (auto &a : c->arenas) a.release();
     c->gen.release();
@@ -728,7 +765,12 @@ int trm_cuda_synthesize_host_ex(trm_cuda_ctx *ctx, int precision, int n, const t
         if (slot_chunk[slot] >= 0 && (rc = finish_slot(slot)) != 0) return rc;
         ChunkPlan &p = plans[slot];
         const int u0 = ci * per_chunk, u1 = std::min(n, u0 + per_chunk);
-        if ((rc = plan_chunk(desc, u0, u1, precision == 0 ? ctx->info64 : ctx->info32, p)) != 0) return rc;
+        // large chunks with PCM output are resampled and scaled in up to MAX_OUT_GROUPS output groups
+        long long chunk_out = 0;
+        for (int u = u0; u < u1; ++u) chunk_out += desc[u].n_out;
+        const int want_groups = (want_pcm && !getenv("TRM_NO_OUT_GROUPS")) ? (int)std::min<long long>(MAX_OUT_GROUPS, chunk_out / (64ll << 20)) : 1;
+        if ((rc = plan_chunk(desc, u0, u1, precision == 0 ? ctx->info64 : ctx->info32, p, want_groups)) != 0) return rc;
+        const bool grouped = p.groups.size() > 1;
         if ((rc = ctx->arenas[slot].reserve(p.arena_bytes(esz, want_pcm))) != 0) return rc;
         if ((rc = ctx->stages[slot].reserve(p.stage_bytes())) != 0) return rc;
         DeviceChunk dc;
@@ -746,17 +788,42 @@ int trm_cuda_synthesize_host_ex(trm_cuda_ctx *ctx, int precision, int n, const t
         {
             std::lock_guard<std::mutex> lk(g_run_mu[ctx->device]);
             CK(cudaStreamWaitEvent(s_run, ctx->ev_in[slot], 0));
-            for (int st = 0; st < TRM_STAGE_COUNT; ++st) {
-                if (st == TRM_STAGE_PCM && !want_pcm) { mark(s_run); continue; }
-                if ((rc = launch_stage(ctx, precision, st, dc, s_run)) != 0) return rc;
+            if (!grouped) {
+                for (int st = 0; st < TRM_STAGE_COUNT; ++st) {
+                    if (st == TRM_STAGE_PCM && !want_pcm) { mark(s_run); continue; }
+                    if ((rc = launch_stage(ctx, precision, st, dc, s_run)) != 0) return rc;
+                    mark(s_run);
+                    ++n_launch;
+                }
+            } else {
+                // one waveguide launch (it needs the whole chunk to fill the device), then resampling + scaling group by
+                // group: group g's PCM crosses PCIe while group g+1 is resampled
+                if ((rc = launch_stage(ctx, precision, TRM_STAGE_TUBE, dc, s_run)) != 0) return rc;
                 mark(s_run);
                 ++n_launch;
+                for (size_t g = 0; g < p.groups.size(); ++g) {
+                    if ((rc = launch_stage(ctx, precision, TRM_STAGE_SRC, dc, s_run, &p.groups[g])) != 0) return rc;
+                    if (g + 1 == p.groups.size()) mark(s_run);
+                    if ((rc = launch_stage(ctx, precision, TRM_STAGE_PCM, dc, s_run, &p.groups[g])) != 0) return rc;
+                    CK(cudaEventRecord(ctx->ev_grp[slot][g], s_run));
+                    n_launch += 2;
+                }
+                mark(s_run);
             }
             CK(cudaEventRecord(ctx->ev_run[slot], s_run));
         }
         // ---- copy-out ----------------------------------------------------------------------------------------
+        if (grouped) {
+            for (size_t g = 0; g < p.groups.size(); ++g) {
+                const ChunkPlan::Group &grp = p.groups[g];
+                CK(cudaStreamWaitEvent(s_out, ctx->ev_grp[slot][g], 0));
+                if (grp.pcm_hi > grp.pcm_lo)
+                    CK(cudaMemcpyAsync(pcm_host + p.pcm_lo + grp.pcm_lo, dc.pcm + grp.pcm_lo, (size_t)(grp.pcm_hi - grp.pcm_lo) * sizeof(int16_t),
+                                       cudaMemcpyDeviceToHost, s_out));
+            }
+        }
         CK(cudaStreamWaitEvent(s_out, ctx->ev_run[slot], 0));
-        if (want_pcm && p.pcm_elems) {
+        if (!grouped && want_pcm && p.pcm_elems) {
             long long c_hi = 0;
             for (const auto &d : p.desc) c_hi = std::max<long long>(c_hi, d.pcm_offset + d.n_out * d.channels);
             CK(cudaMemcpyAsync(pcm_host + p.pcm_lo, dc.pcm, (size_t)c_hi * sizeof(int16_t), cudaMemcpyDeviceToHost, s_out));
