@@ -140,6 +140,9 @@ struct DeviceChunk {
     long long total_items = 0, max_n_out = 0;
     int n_tiles = 0;
     int src_shape = 0;                      // resampler shape the tiles were built for (KernelInfo::src[])
+    // time split (ChunkPlan::split_frame > 0): descriptors of the two waveguide launches and the state carried between them
+    trm_cuda_utterance *desc_t[2] = {nullptr, nullptr};
+    void *state = nullptr;
     size_t tube_elems = 0, out_elems = 0, pcm_elems = 0, frame_rows = 0;
 };
 
@@ -160,6 +163,11 @@ struct ChunkPlan {
     // Output groups: contiguous utterance ranges whose resampling + scaling is launched separately, so that the PCM of
     // one group can leave for the host while the next group is still being resampled (tiles never span groups).
     struct Group { int u_begin, u_end; long long item_begin, item_end, max_n_out, pcm_lo, pcm_hi; };
+    // Time split: when every utterance of the chunk has the same number of frames, the waveguide runs as two launches
+    // (tube samples before / from control frame `split_frame`, recurrence state carried in `state` exactly as
+    // trm_cuda_stream_push does), so that the upload of the later frames overlaps the first launch.  0 = one launch.
+    int split_frame = 0, uniform_frames = 0;
+    std::vector<trm_cuda_utterance> desc_t[2];
     std::vector<Group> groups;
     long long total_items = 0, max_n_out = 0;
     size_t n_tiles() const { return tile_nt.size(); }
@@ -179,6 +187,7 @@ struct ChunkPlan {
         add(tube_elems * esz);
         add(out_elems * esz);
         if (want_pcm) add(pcm_elems * sizeof(int16_t));
+        if (split_frame > 0) { add(n * sizeof(trm_cuda_utterance)); add(n * sizeof(trm_cuda_utterance)); add(n * trm::tube_state_bytes(esz)); }
         return b + 256;
     }
     size_t stage_bytes() const
@@ -188,7 +197,8 @@ struct ChunkPlan {
                align_up(tile_utt.size() * sizeof(int), 256) + align_up(tile_nt.size() * sizeof(int), 256) +
                align_up(tile_max_out.size() * sizeof(long long), 256) + align_up(tile_first_out.size() * sizeof(long long), 256) +
                align_up(item_base.size() * sizeof(long long), 256) +
-               align_up(n * sizeof(unsigned long long), 256);
+               (split_frame > 0 ? 2 * align_up(n * sizeof(trm_cuda_utterance), 256) + align_up(n * trm::tube_state_bytes(8), 256) : 0) +
+               align_up(n * sizeof(unsigned long long), 256);     // (last: the maxima come back here)
     }
 };
 
@@ -221,6 +231,7 @@ struct trm_cuda_ctx {
     HostStage stages[MAX_SLOTS];
     int n_slots = 3;              // chunks in flight: one uploading, one computing, one downloading
     cudaEvent_t ev_in[MAX_SLOTS]{}, ev_run[MAX_SLOTS]{}, ev_out[MAX_SLOTS]{};
+    cudaEvent_t ev_in2[MAX_SLOTS]{};                    // time split: the later frames are on the device
     cudaEvent_t ev_grp[MAX_SLOTS][MAX_OUT_GROUPS]{};   // a group's PCM is complete (copy-out of the group may start)
     int wide_min_utt = 0;         // batches at least this large use the batch-throughput waveguide mapping
 };
@@ -359,7 +370,45 @@ int plan_chunk(const trm_cuda_utterance *desc, int u0, int u1, const trm::Kernel
     std::iota(p.order.begin(), p.order.end(), 0);
     std::stable_sort(p.order.begin(), p.order.end(),
                      [&](int a, int b) { return p.desc[a].n_tube > p.desc[b].n_tube; });
+    // time split candidates: dense frames, the same frame count everywhere (so that a frame range is one strided copy) and
+    // one control period (so that every utterance of a CTA reaches the split after the same number of 16-sample blocks:
+    // the kernels save an utterance's state when its CTA's loop ends)
+    p.split_frame = 0;
+    p.uniform_frames = 0;
+    if (n > 0 && p.frames_dense) {
+        const int nf = p.desc[0].n_frames;
+        bool uniform = nf > 0;
+        for (int i = 0; i < n && uniform; ++i)
+            uniform = p.desc[i].n_frames == nf && p.desc[i].frame_offset == (long long)i * nf && p.desc[i].jc0 == 0 && p.desc[i].n_tube > 0 &&
+                      p.desc[i].controlPeriod == p.desc[0].controlPeriod;
+        if (uniform) p.uniform_frames = nf;
+    }
     return 0;
+}
+
+// Arms the time split of a planned chunk: launch 0 covers the tube samples before control frame f1 (rounded down to a
+// whole 16-sample block per utterance), launch 1 the rest, continuing from the saved state in the middle of a control
+// interval (jc0) exactly like a streaming push.
+void arm_time_split(ChunkPlan &p, int f1)
+{
+    const size_t n = p.desc.size();
+    p.split_frame = f1;
+    p.desc_t[0].assign(p.desc.begin(), p.desc.end());
+    p.desc_t[1].assign(p.desc.begin(), p.desc.end());
+    for (size_t u = 0; u < n; ++u) {
+        const trm_cuda_utterance &d = p.desc[u];
+        const long long cp = d.controlPeriod;
+        const long long t1 = ((long long)f1 * cp) / 16 * 16;          // first tube sample of launch 1
+        const long long f0 = t1 / cp;                                 // control interval it lies in
+        trm_cuda_utterance &a = p.desc_t[0][u], &b = p.desc_t[1][u];
+        a.n_tube = t1;
+        a.n_frames = f1 + 1;
+        b.frame_offset = d.frame_offset + f0;
+        b.n_frames = d.n_frames - (int)f0;
+        b.jc0 = (int)(t1 - f0 * cp);
+        b.tube_offset = d.tube_offset + t1;
+        b.n_tube = d.n_tube - t1;
+    }
 }
 
 void carve(Arena &a, const ChunkPlan &p, size_t esz, bool want_pcm, DeviceChunk &dc)
@@ -379,6 +428,14 @@ void carve(Arena &a, const ChunkPlan &p, size_t esz, bool want_pcm, DeviceChunk 
     dc.tube = a.take(p.tube_elems * esz);
     dc.out = a.take(p.out_elems * esz);
     dc.pcm = want_pcm ? (int16_t *)a.take(p.pcm_elems * sizeof(int16_t)) : nullptr;
+    if (p.split_frame > 0) {
+        dc.desc_t[0] = (trm_cuda_utterance *)a.take(n * sizeof(trm_cuda_utterance));
+        dc.desc_t[1] = (trm_cuda_utterance *)a.take(n * sizeof(trm_cuda_utterance));
+        dc.state = a.take(n * trm::tube_state_bytes(esz));
+    } else {
+        dc.desc_t[0] = dc.desc_t[1] = nullptr;
+        dc.state = nullptr;
+    }
     dc.total_items = p.total_items;
     dc.n_tiles = (int)p.n_tiles();
     dc.src_shape = p.src_shape;
@@ -387,7 +444,7 @@ void carve(Arena &a, const ChunkPlan &p, size_t esz, bool want_pcm, DeviceChunk 
 }
 
 // small tables (descriptors, order, tile prefix) -> device, through pinned staging when given
-int upload_plan(const ChunkPlan &p, const DeviceChunk &dc, unsigned char *stage, cudaStream_t s)
+int upload_plan(const ChunkPlan &p, const DeviceChunk &dc, unsigned char *stage, cudaStream_t s, size_t esz = 8, unsigned long long noise_k0 = 0)
 {
     const size_t n = p.desc.size();
     if (n == 0) return 0;
@@ -411,6 +468,19 @@ int upload_plan(const ChunkPlan &p, const DeviceChunk &dc, unsigned char *stage,
     if ((rc = put(dc.tile_max_out, p.tile_max_out.data(), p.tile_max_out.size() * sizeof(long long))) != 0) return rc;
     if ((rc = put(dc.tile_first_out, p.tile_first_out.data(), p.tile_first_out.size() * sizeof(long long))) != 0) return rc;
     if ((rc = put(dc.item_base, p.item_base.data(), p.item_base.size() * sizeof(long long))) != 0) return rc;
+    if (p.split_frame > 0 && dc.state) {
+        if ((rc = put(dc.desc_t[0], p.desc_t[0].data(), n * sizeof(trm_cuda_utterance))) != 0) return rc;
+        if ((rc = put(dc.desc_t[1], p.desc_t[1].data(), n * sizeof(trm_cuda_utterance))) != 0) return rc;
+        // fresh recurrence state: everything zero, noise generator at its start, "no sample yet" flag set
+        const size_t sb = trm::tube_state_bytes(esz);
+        std::vector<unsigned char> init(n * sb, 0);
+        for (size_t u = 0; u < n; ++u) {
+            unsigned long long *h = (unsigned long long *)(init.data() + u * sb);
+            h[2] = noise_k0;
+            h[3] = 1ull;
+        }
+        if ((rc = put(dc.state, init.data(), init.size())) != 0) return rc;
+    }
     return 0;
 }
 
@@ -447,7 +517,8 @@ int wide_groups(const trm_cuda_ctx *ctx, const trm::KernelInfo &ki, int n)
     return waves * sm;
 }
 
-int launch_stage(trm_cuda_ctx *ctx, int precision, int stage, const DeviceChunk &dc, cudaStream_t s, const ChunkPlan::Group *grp = nullptr)
+int launch_stage(trm_cuda_ctx *ctx, int precision, int stage, const DeviceChunk &dc, cudaStream_t s, const ChunkPlan::Group *grp = nullptr,
+                 int time_part = -1)
 {
     const bool f64 = precision == 0;
     int rc = 0;
@@ -455,8 +526,10 @@ int launch_stage(trm_cuda_ctx *ctx, int precision, int stage, const DeviceChunk 
         trm::TubeArgs a{};
         a.desc = dc.desc; a.order = dc.order; a.n_utt = dc.n; a.frames = dc.frames; a.tube = dc.tube;
         a.wavetables = ctx->d_wavetables; a.noise_k0 = ctx->noise_k0;
+        if (time_part >= 0) { a.desc = dc.desc_t[time_part]; a.state = dc.state; }     // (lane-per-utterance mapping only)
         const trm::KernelInfo &ki = f64 ? ctx->info64 : ctx->info32;
         const int groups = wide_groups(ctx, ki, dc.n);
+        if (time_part >= 0 && groups <= 0) return fail_msg("time split needs the lane-per-utterance waveguide mapping");
         if (groups > 0) rc = f64 ? trm_k_tube_wide_f64(&a, groups, s) : trm_k_tube_wide_f32(&a, groups, s);
         else rc = f64 ? trm_k_tube_f64(&a, s) : trm_k_tube_f32(&a, s);
     } else if (stage == TRM_STAGE_SRC) {
@@ -643,6 +716,7 @@ int trm_cuda_ctx_create(int device, const trm_cuda_tables *t, trm_cuda_ctx **out
             CK(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&c->ev_run[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&c->ev_in2[i], cudaEventDisableTiming));
             for (int g = 0; g < MAX_OUT_GROUPS; ++g) CK(cudaEventCreateWithFlags(&c->ev_grp[i][g], cudaEventDisableTiming));
         }
     }
@@ -681,6 +755,7 @@ void trm_cuda_ctx_destroy(trm_cuda_ctx *c)
         if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
         if (c->ev_run[i]) cudaEventDestroy(c->ev_run[i]);
         if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
+        if (c->ev_in2[i]) cudaEventDestroy(c->ev_in2[i]);
         for (int g = 0; g < MAX_OUT_GROUPS; ++g) if (c->ev_grp[i][g]) cudaEventDestroy(c->ev_grp[i][g]);
     }
     for (auto &a : c->arenas) a.release();
@@ -771,6 +846,11 @@ int trm_cuda_synthesize_host_ex(trm_cuda_ctx *ctx, int precision, int n, const t
         const int want_groups = (want_pcm && !getenv("TRM_NO_OUT_GROUPS")) ? (int)std::min<long long>(MAX_OUT_GROUPS, chunk_out / (64ll << 20)) : 1;
         if ((rc = plan_chunk(desc, u0, u1, precision == 0 ? ctx->info64 : ctx->info32, p, want_groups)) != 0) return rc;
         const bool grouped = p.groups.size() > 1;
+        // long uniform chunks: the waveguide as two launches in time, the later frames uploaded behind the first
+        if (p.uniform_frames >= 512 && !getenv("TRM_NO_TIME_SPLIT") &&
+            wide_groups(ctx, precision == 0 ? ctx->info64 : ctx->info32, u1 - u0) > 0)
+            arm_time_split(p, std::max(64, (int)(0.28 * p.uniform_frames)));
+        const bool split = p.split_frame > 0;
         if ((rc = ctx->arenas[slot].reserve(p.arena_bytes(esz, want_pcm))) != 0) return rc;
         if ((rc = ctx->stages[slot].reserve(p.stage_bytes())) != 0) return rc;
         DeviceChunk dc;
@@ -779,28 +859,47 @@ int trm_cuda_synthesize_host_ex(trm_cuda_ctx *ctx, int precision, int n, const t
         {
             std::lock_guard<std::mutex> lk(g_in_mu[ctx->device]);
             mark(s_in);
-            if ((rc = upload_plan(p, dc, ctx->stages[slot].base, s_in)) != 0) return rc;
-            if ((rc = upload_frames(p, dc, desc, frames_host, s_in)) != 0) return rc;
-            CK(cudaEventRecord(ctx->ev_in[slot], s_in));
+            if ((rc = upload_plan(p, dc, ctx->stages[slot].base, s_in, esz, ctx->noise_k0)) != 0) return rc;
+            if (!split) {
+                if ((rc = upload_frames(p, dc, desc, frames_host, s_in)) != 0) return rc;
+                CK(cudaEventRecord(ctx->ev_in[slot], s_in));
+            } else {
+                // frames [0, f1] of every utterance, then the rest: two strided copies
+                const size_t pitch = (size_t)p.uniform_frames * 128, first = (size_t)(p.split_frame + 1) * 128;
+                const unsigned char *src = (const unsigned char *)(frames_host + (size_t)p.frames_lo * 16);
+                CK(cudaMemcpy2DAsync(dc.frames, pitch, src, pitch, first, (size_t)(u1 - u0), cudaMemcpyDefault, s_in));
+                CK(cudaEventRecord(ctx->ev_in[slot], s_in));
+                CK(cudaMemcpy2DAsync((unsigned char *)dc.frames + first, pitch, src + first, pitch, pitch - first, (size_t)(u1 - u0),
+                                     cudaMemcpyDefault, s_in));
+                CK(cudaEventRecord(ctx->ev_in2[slot], s_in));
+            }
             mark(s_in);
         }
         // ---- kernels -----------------------------------------------------------------------------------------
         {
             std::lock_guard<std::mutex> lk(g_run_mu[ctx->device]);
             CK(cudaStreamWaitEvent(s_run, ctx->ev_in[slot], 0));
+            auto waveguide = [&]() -> int {
+                if (!split) { ++n_launch; return launch_stage(ctx, precision, TRM_STAGE_TUBE, dc, s_run); }
+                int r = launch_stage(ctx, precision, TRM_STAGE_TUBE, dc, s_run, nullptr, 0);
+                if (r != 0) return r;
+                CK(cudaStreamWaitEvent(s_run, ctx->ev_in2[slot], 0));
+                n_launch += 2;
+                return launch_stage(ctx, precision, TRM_STAGE_TUBE, dc, s_run, nullptr, 1);
+            };
             if (!grouped) {
                 for (int st = 0; st < TRM_STAGE_COUNT; ++st) {
                     if (st == TRM_STAGE_PCM && !want_pcm) { mark(s_run); continue; }
-                    if ((rc = launch_stage(ctx, precision, st, dc, s_run)) != 0) return rc;
+                    if (st == TRM_STAGE_TUBE) rc = waveguide();
+                    else { rc = launch_stage(ctx, precision, st, dc, s_run); ++n_launch; }
+                    if (rc != 0) return rc;
                     mark(s_run);
-                    ++n_launch;
                 }
             } else {
-                // one waveguide launch (it needs the whole chunk to fill the device), then resampling + scaling group by
-                // group: group g's PCM crosses PCIe while group g+1 is resampled
-                if ((rc = launch_stage(ctx, precision, TRM_STAGE_TUBE, dc, s_run)) != 0) return rc;
+                // the waveguide over the whole chunk (it needs all of it to fill the device), then resampling + scaling
+                // group by group: group g's PCM crosses PCIe while group g+1 is resampled
+                if ((rc = waveguide()) != 0) return rc;
                 mark(s_run);
-                ++n_launch;
                 for (size_t g = 0; g < p.groups.size(); ++g) {
                     if ((rc = launch_stage(ctx, precision, TRM_STAGE_SRC, dc, s_run, &p.groups[g])) != 0) return rc;
                     if (g + 1 == p.groups.size()) mark(s_run);

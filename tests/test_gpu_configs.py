@@ -391,3 +391,39 @@ def test_config4_full_size_mixed_lengths():
         assert ns[u] == want, u
         assert np.abs(pcm[po[u]:po[u] + ns[u]]).max() == 32767, u
     _spot_check(b, pcm, ips, frames, n_frames, g.TRM_PRECISION_FP32, [7, 200, 64, 129])
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_time_split_waveguide_is_bit_identical(precision, monkeypatch):
+    """Long chunks whose utterances have equal frame counts run the waveguide as two launches in time (the later frames
+    are uploaded behind the first launch; recurrence state carried like a streaming push, restart inside a control
+    interval).  Mixed voices give every utterance its own split point and restart phase.  The result must equal the
+    single-launch result bit for bit in both precision modes, and the oracle within tolerance."""
+    g = _g()
+    from gnuspeech_b200 import workloads as W
+    import os
+    if os.environ.get("TRM_TUBE_MAPPING", "").startswith("s"):
+        pytest.skip("the time split belongs to the lane-per-utterance mapping")
+    # one tube length (one control period: every utterance reaches the split after the same number of blocks), otherwise mixed
+    voices = [dict(), dict(waveform=1), dict(usesModulation=0, breathiness=3.0), dict(channels=2, balance=0.3), dict(lossFactor=1.2)]
+    n, nf = 37, 600
+    ips = [g.TRMInputParameters(44100.0 if u % 4 else 22050.0, **voices[u % len(voices)]) for u in range(n)]
+    frames = W.random_walk(n, nf, seed=41)
+    monkeypatch.delenv("TRM_NO_TIME_SPLIT", raising=False)
+    b1, pcm1, smp1, _ = _run(ips, frames, [nf] * n, precision)
+    assert b1.kernelLaunches == 4                      # two waveguide launches + resampler + PCM
+    monkeypatch.setenv("TRM_NO_TIME_SPLIT", "1")
+    b0, pcm0, smp0, _ = _run(ips, frames, [nf] * n, precision)
+    assert b0.kernelLaunches == 3
+    for u in range(n):
+        o, k = b0.outOffsets[u], b0.numberSamples[u]
+        assert np.array_equal(smp1[o:o + k], smp0[o:o + k]), u
+        ch = ips[u].channels
+        assert np.array_equal(pcm1[b0.pcmOffsets[u]:b0.pcmOffsets[u] + k * ch], pcm0[b0.pcmOffsets[u]:b0.pcmOffsets[u] + k * ch]), u
+    assert np.array_equal(b1.maximumSampleValues, b0.maximumSampleValues)
+    print("time split worst", _check(b1, pcm1, smp1, ips, frames, [nf] * n, precision, idx=[0, 1, 2, 36]))
+    # different tube lengths in one chunk: no split
+    monkeypatch.delenv("TRM_NO_TIME_SPLIT", raising=False)
+    ips[5] = g.TRMInputParameters(44100.0, length=15.0)
+    b2, _, _, _ = _run(ips, frames, [nf] * n, precision)
+    assert b2.kernelLaunches == 3
