@@ -320,6 +320,7 @@ def main():
                    "h2d_bytes_per_step": int(lay.total_frames) * 128 * world,
                    "d2h_bytes_per_step": int(lay.out_samples) * 2 * world,
                    "ms_per_step": 1e3 * dt / args.steps,
+                   "gpu_launches_per_step": int(batches[0].kernelLaunches),
                    "api": "TRMBatchSynthesizeAsync / TRMBatchWait (include/trm.h), %d calls in flight, pinned host frames in, "
                           "pinned host PCM16 out; every step's copies and kernels finish inside the timed region" % depth,
                    "blocking": {"value": audio_all / (dt_block / args.steps), "ms_per_step": 1e3 * dt_block / args.steps,
