@@ -427,3 +427,33 @@ def test_time_split_waveguide_is_bit_identical(precision, monkeypatch):
     ips[5] = g.TRMInputParameters(44100.0, length=15.0)
     b2, _, _, _ = _run(ips, frames, [nf] * n, precision)
     assert b2.kernelLaunches == 3
+
+
+def test_output_groups_equal_single_pass(monkeypatch):
+    """Chunks with more than 128 M output samples are resampled and scaled in up to four output groups whose PCM leaves
+    while the next group is resampled.  Ragged lengths, two output rates and three tube lengths, so the groups cut
+    through converter signatures: PCM and maxima must equal the single-pass result exactly."""
+    g = _g()
+    from gnuspeech_b200 import workloads as W
+    n = 4000
+    rng = np.random.default_rng(77)
+    n_frames = [int(v) for v in rng.integers(150, 600, n)]
+    voices = [dict(), dict(length=15.0), dict(length=10.0, temperature=32.0)]
+    ips = [g.TRMInputParameters(44100.0 if u % 3 else 22050.0, **voices[(u // 7) % 3]) for u in range(n)]
+    frames = np.concatenate([W.random_walk(1, nf, seed=1000 + u) for u, nf in enumerate(n_frames)])
+    res = []
+    for off in (False, True):
+        if off:
+            monkeypatch.setenv("TRM_NO_OUT_GROUPS", "1")
+        else:
+            monkeypatch.delenv("TRM_NO_OUT_GROUPS", raising=False)
+        b = g.TRMBatch(ips, n_frames, precision=g.TRM_PRECISION_FP64)      # (FP64: the whole batch is one chunk)
+        pcm = np.zeros(b.layout.total_pcm_samples, np.int16)
+        b.synthesize(frames, pcm_out=pcm, devices=[0])
+        res.append((b, pcm))
+    (b1, p1), (b0, p0) = res
+    assert b0.kernelLaunches == 3 and b1.kernelLaunches in (5, 7, 9)        # waveguide + (resampler + PCM) per group
+    assert np.array_equal(b1.maximumSampleValues, b0.maximumSampleValues)
+    po, ns = b0.pcmOffsets, b0.numberSamples
+    for u in range(n):
+        assert np.array_equal(p1[po[u]:po[u] + ns[u]], p0[po[u]:po[u] + ns[u]]), u
