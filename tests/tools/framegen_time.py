@@ -1,7 +1,7 @@
 """Times the control-frame generator and the events -> PCM path on configs[1]-sized input (4096 x 10 s)."""
 import os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle_lib as O
 import gnuspeech_b200 as g
