@@ -45,6 +45,27 @@ FLOP_PER_OUT_SAMPLE = 110.0      # up-sampling converter, per output sample
 TRAFFIC_PER_UNIT = {"fp64": {"tube": 8.95, "src": 12.08, "pcm": 9.96}, "fp32": {"tube": 5.04, "src": 5.85, "pcm": 5.85}}
 
 
+def bind_to_gpu_numa_node(torch, local_rank, world):
+    """Several ranks share the host: keep this rank's threads (and with them the pinned buffers it allocates and the
+    staging copies libtrm makes) on the CPUs next to its GPU, so that every GPU's PCIe traffic stays on its own socket.
+    Only under torchrun; silently skipped when sysfs does not tell."""
+    if world <= 1 or os.environ.get("TRM_NO_NUMA_BIND"):
+        return
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            print("[bench] rank %d: bound to %d CPUs local to GPU %d" % (local_rank, len(cpus), local_rank), file=sys.stderr)
+    except (OSError, ValueError, AttributeError):
+        pass
+
+
 def host_cores():
     try:
         return max(1, len(os.sched_getaffinity(0)))
@@ -193,6 +214,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the TRM path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    bind_to_gpu_numa_node(torch, local_rank, world)
     dist = None
     if world > 1:
         import torch.distributed as dist
