@@ -4,14 +4,15 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_DIR = os.path.join(_HERE, "lib")
+# TRM_LIB_DIR selects a profiling variant built by `python -m gnuspeech_b200.build --variant <tag> ...` (tools/ only)
+LIB_DIR = os.environ.get("TRM_LIB_DIR") or os.path.join(_HERE, "lib")
 LIBTRM_PATH = os.path.join(LIB_DIR, "libtrm.so")
 LIBTRM_CUDA_PATH = os.path.join(LIB_DIR, "libtrm_cuda.so")
 
 TRM_OK = 0
 TRM_ERR_TUBE_LENGTH, TRM_ERR_FIR, TRM_ERR_NOMEM, TRM_ERR_PARAM = -1, -2, -3, -4
 TRM_ERR_CUDA, TRM_ERR_IO, TRM_ERR_STATE, TRM_ERR_SILENT = -5, -6, -7, -8
-TRM_PRECISION_FP64, TRM_PRECISION_FP32 = 0, 1
+TRM_PRECISION_FP64, TRM_PRECISION_FP32, TRM_PRECISION_FP64_STRICT = 0, 1, 2
 TRM_STAGE_TUBE, TRM_STAGE_SRC, TRM_STAGE_PCM = 0, 1, 2
 
 

@@ -376,7 +376,7 @@ class TRMBatch(object):
             raise TRMError(err.value, "TRMBatchCreate")
         self.layout = N.TRMBatchLayoutStruct()
         N.lib().TRMBatchGetLayout(self._h, C.byref(self.layout))
-        self.sample_dtype = np.float64 if precision == N.TRM_PRECISION_FP64 else np.float32
+        self.sample_dtype = np.float64 if precision != N.TRM_PRECISION_FP32 else np.float32
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -488,7 +488,7 @@ class TRMStream(object):
         err = C.c_int(0)
         self._ip = ip
         self.n = n_streams
-        self.dtype = np.float64 if precision == N.TRM_PRECISION_FP64 else np.float32
+        self.dtype = np.float64 if precision != N.TRM_PRECISION_FP32 else np.float32
         self._h = N.lib().TRMStreamCreate(n_streams, C.byref(ip), precision, max_frames_per_push, device, C.byref(err))
         if not self._h:
             check(err.value or N.TRM_ERR_CUDA, "TRMStreamCreate")

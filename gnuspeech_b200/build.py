@@ -3,8 +3,8 @@
   libtrm_cuda.so  -- sm_100a kernels + C-ABI shim (nvcc; cross-compiles without a GPU)
   libtrm.so       -- C host library behind include/trm.h (gcc), linked against libtrm_cuda.so
 
-The FP64 conformance kernels are compiled with -fmad=false (the reference build has no FMA
-contraction); the FP32 fast-mode kernels with the default contraction.
+The FP64 strict kernels (kernels_f64s.cu) are compiled with -fmad=false (the reference build has no FMA
+contraction); the FP64 conformance and FP32 fast-mode kernels with the default contraction.
 """
 import os
 import shutil
@@ -40,19 +40,25 @@ def _run(cmd, verbose):
         print(r.stdout)
 
 
-def build(verbose=False, force=False):
+def build(verbose=False, force=False, defines=(), tag=None):
+    """Builds the libraries.  `defines` (e.g. ["-DTRM_PROFILE_SKIP=1"]) with a `tag` builds a profiling variant into
+    gnuspeech_b200/lib_<tag>/ (selected at import time with TRM_LIB_DIR); the shipped library is built without either."""
+    global LIB, OBJ
+    if tag:
+        LIB = os.path.join(ROOT, "gnuspeech_b200", "lib_" + tag)
+        OBJ = os.path.join(ROOT, "build", "obj_" + tag)
     os.makedirs(LIB, exist_ok=True)
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, h) for h in ("tube_kernel.cuh", "tube_wide.cuh", "src_kernel.cuh", "framegen_kernel.cuh",
                                                "launch.cuh", "kernel_args.h")]
     headers += [os.path.join(INC, h) for h in ("trm.h", "trm_cuda.h", "trm_workload.h")]
-    cu = [("kernels_f64", ["-fmad=false"]), ("kernels_f32", []), ("kernels_aux", ["-fmad=false"]), ("trm_cuda", [])]
+    cu = [("kernels_f64s", ["-fmad=false"]), ("kernels_f64", []), ("kernels_f32", []), ("kernels_aux", ["-fmad=false"]), ("trm_cuda", [])]
     objs = []
     for name, extra in cu:
         src = os.path.join(CSRC, name + ".cu")
         obj = os.path.join(OBJ, name + ".o")
         if force or _newer(obj, [src] + headers):
-            _run([NVCC] + NVCC_COMMON + extra + ["-c", src, "-o", obj], verbose)
+            _run([NVCC] + NVCC_COMMON + list(defines) + extra + ["-c", src, "-o", obj], verbose)
         objs.append(obj)
     cuda_so = os.path.join(LIB, "libtrm_cuda.so")
     if force or _newer(cuda_so, objs):
@@ -60,7 +66,7 @@ def build(verbose=False, force=False):
     host_src = [os.path.join(CSRC, f) for f in ("trm_host.c", "trm_workload.c")]
     host_so = os.path.join(LIB, "libtrm.so")
     if force or _newer(host_so, host_src + headers + [cuda_so]):
-        _run(["gcc", "-O2", "-std=gnu99", "-Wall", "-fPIC", "-shared", "-I" + INC, "-o", host_so] + host_src +
+        _run(["gcc", "-O2", "-ffp-contract=off", "-fno-fast-math", "-std=gnu99", "-Wall", "-fPIC", "-shared", "-I" + INC, "-o", host_so] + host_src +
              ["-L" + LIB, "-ltrm_cuda", "-Wl,-rpath,$ORIGIN", "-lm", "-lpthread"], verbose)
     return host_so, cuda_so
 
@@ -71,5 +77,9 @@ def build_oracle(verbose=False):
 
 
 if __name__ == "__main__":
-    build(verbose=True, force="--force" in sys.argv)
-    build_oracle(verbose=True)
+    if "--variant" in sys.argv:       # python -m gnuspeech_b200.build --variant <tag> -DX=1 ...
+        i = sys.argv.index("--variant")
+        build(verbose=True, force=True, defines=[a for a in sys.argv[i + 2:] if a.startswith("-D")], tag=sys.argv[i + 1])
+    else:
+        build(verbose=True, force="--force" in sys.argv)
+        build_oracle(verbose=True)

@@ -5,6 +5,16 @@
 
 #include "trm_cuda.h"
 
+// Every kernels_*.cu translation unit instantiates the kernel templates under its own compiler flags (FMA contraction
+// on / off), so each one puts them into its own namespace: identical template instantiations from two TUs would otherwise
+// be merged by the linker.  TRM_STRICT = 1 selects the reference-order FP64 arithmetic (tube_wide.cuh).
+#ifndef TRM_KERNEL_NS
+#define TRM_KERNEL_NS trm_kernels
+#endif
+#ifndef TRM_STRICT
+#define TRM_STRICT 0
+#endif
+
 namespace trm {
 
 constexpr int TB = 16;           // samples per block == lanes per utterance

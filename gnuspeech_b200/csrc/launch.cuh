@@ -9,7 +9,8 @@
 #include "tube_kernel.cuh"
 #include "tube_wide.cuh"
 
-namespace trm {
+namespace TRM_KERNEL_NS {
+using namespace trm;
 
 template <typename R, int SHAPE> constexpr int src_smem_bytes()
 {
@@ -101,8 +102,7 @@ template <typename R> static int launch_tube_wide(const TubeArgs &a, int n_group
 {
     if (a.n_utt <= 0 || n_groups <= 0) return 0;
     if ((a.n_utt + n_groups - 1) / n_groups > 2 * Wide<R>::MAX_PAIRS) return (int)cudaErrorInvalidConfiguration;
-    const char *dbg = getenv("TRM_WIDE_DEBUG");
-    WideArgs w{a, n_groups, dbg ? atoi(dbg) : 0};
+    WideArgs w{a, n_groups};
     tube_wide_kernel<R><<<n_groups, Wide<R>::THREADS, sizeof(WideSmem<R>), s>>>(w);
     return (int)cudaGetLastError();
 }
@@ -140,28 +140,28 @@ template <typename R> static int launch_pcm(const PcmArgs &a, long long max_n_ou
     return (int)cudaGetLastError();
 }
 
-}  // namespace trm
+}  // namespace TRM_KERNEL_NS
 
 #define TRM_DEFINE_LAUNCHERS(R, SUF)                                                                              \
-    extern "C" int trm_k_configure_##SUF(trm::KernelInfo *info) { return trm::configure_kernels<R>(info); }      \
+    extern "C" int trm_k_configure_##SUF(trm::KernelInfo *info) { return TRM_KERNEL_NS::configure_kernels<R>(info); }      \
     extern "C" int trm_k_upload_##SUF(const double *fir, int taps, const unsigned long long *np)                 \
     {                                                                                                             \
-        return trm::upload_constants(fir, taps, np);                                                              \
+        return TRM_KERNEL_NS::upload_constants(fir, taps, np);                                                              \
     }                                                                                                             \
-    extern "C" int trm_k_tube_##SUF(const trm::TubeArgs *a, cudaStream_t s) { return trm::launch_tube<R>(*a, s); } \
+    extern "C" int trm_k_tube_##SUF(const trm::TubeArgs *a, cudaStream_t s) { return TRM_KERNEL_NS::launch_tube<R>(*a, s); } \
     extern "C" int trm_k_tube_wide_##SUF(const trm::TubeArgs *a, int n_groups, cudaStream_t s)                    \
     {                                                                                                             \
-        return trm::launch_tube_wide<R>(*a, n_groups, s);                                                         \
+        return TRM_KERNEL_NS::launch_tube_wide<R>(*a, n_groups, s);                                                         \
     }                                                                                                             \
     extern "C" int trm_k_src_##SUF(const trm::SrcArgs *a, int grid, int shape, cudaStream_t s)                    \
     {                                                                                                             \
-        return trm::launch_src<R>(*a, grid, shape, s);                                                            \
+        return TRM_KERNEL_NS::launch_src<R>(*a, grid, shape, s);                                                            \
     }                                                                                                             \
     extern "C" int trm_k_src_ctab_##SUF(const void *tab, void *ctab, cudaStream_t s)                              \
     {                                                                                                             \
-        return trm::launch_src_ctab<R>(tab, ctab, s);                                                             \
+        return TRM_KERNEL_NS::launch_src_ctab<R>(tab, ctab, s);                                                             \
     }                                                                                                             \
     extern "C" int trm_k_pcm_##SUF(const trm::PcmArgs *a, long long max_n_out, cudaStream_t s)                    \
     {                                                                                                             \
-        return trm::launch_pcm<R>(*a, max_n_out, s);                                                              \
+        return TRM_KERNEL_NS::launch_pcm<R>(*a, max_n_out, s);                                                              \
     }

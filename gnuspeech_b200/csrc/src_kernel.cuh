@@ -28,7 +28,8 @@
 #include "trm_cuda.h"
 #include "tube_kernel.cuh"   // mbarrier / TMA bulk-copy helpers
 
-namespace trm {
+namespace TRM_KERNEL_NS {
+using namespace trm;
 
 // 16 bytes of R through the native vector type (keeps the elements in registers)
 template <typename R> struct Vec16;
@@ -561,4 +562,4 @@ __global__ void __launch_bounds__(PCM_THREADS) pcm_kernel(PcmArgs args)
   }
 }
 
-}  // namespace trm
+}  // namespace TRM_KERNEL_NS

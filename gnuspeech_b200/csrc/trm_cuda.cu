@@ -16,23 +16,36 @@
 #include "kernel_args.h"
 #include "trm_cuda.h"
 
+// launchers of the three kernel translation units (launch.cuh): FP64 conformance, FP32 fast, FP64 strict
+#define TRM_DECLARE_LAUNCHERS(SUF)                                              \
+    int trm_k_configure_##SUF(trm::KernelInfo *);                               \
+    int trm_k_upload_##SUF(const double *, int, const unsigned long long *);    \
+    int trm_k_tube_##SUF(const trm::TubeArgs *, cudaStream_t);                  \
+    int trm_k_tube_wide_##SUF(const trm::TubeArgs *, int, cudaStream_t);        \
+    int trm_k_src_##SUF(const trm::SrcArgs *, int, int, cudaStream_t);          \
+    int trm_k_src_ctab_##SUF(const void *, void *, cudaStream_t);               \
+    int trm_k_pcm_##SUF(const trm::PcmArgs *, long long, cudaStream_t);
 extern "C" {
-int trm_k_configure_f64(trm::KernelInfo *);
-int trm_k_configure_f32(trm::KernelInfo *);
-int trm_k_upload_f64(const double *, int, const unsigned long long *);
-int trm_k_upload_f32(const double *, int, const unsigned long long *);
-int trm_k_tube_f64(const trm::TubeArgs *, cudaStream_t);
-int trm_k_tube_f32(const trm::TubeArgs *, cudaStream_t);
-int trm_k_tube_wide_f64(const trm::TubeArgs *, int, cudaStream_t);
-int trm_k_tube_wide_f32(const trm::TubeArgs *, int, cudaStream_t);
-int trm_k_src_f64(const trm::SrcArgs *, int, int, cudaStream_t);
-int trm_k_src_f32(const trm::SrcArgs *, int, int, cudaStream_t);
-int trm_k_src_ctab_f64(const void *, void *, cudaStream_t);
-int trm_k_src_ctab_f32(const void *, void *, cudaStream_t);
-int trm_k_pcm_f64(const trm::PcmArgs *, long long, cudaStream_t);
-int trm_k_pcm_f32(const trm::PcmArgs *, long long, cudaStream_t);
+TRM_DECLARE_LAUNCHERS(f64)
+TRM_DECLARE_LAUNCHERS(f32)
+TRM_DECLARE_LAUNCHERS(f64s)
 int trm_k_framegen(const trm::FrameGenArgs *, cudaStream_t);
 }
+
+// precision codes of include/trm.h: 0 = FP64 conformance, 1 = FP32 fast, 2 = FP64 strict
+static inline bool prec_is_f64(int precision) { return precision != 1; }
+static inline size_t prec_esz(int precision) { return precision != 1 ? sizeof(double) : sizeof(float); }
+struct KernelSet {
+    int (*tube)(const trm::TubeArgs *, cudaStream_t);
+    int (*tube_wide)(const trm::TubeArgs *, int, cudaStream_t);
+    int (*src)(const trm::SrcArgs *, int, int, cudaStream_t);
+    int (*pcm)(const trm::PcmArgs *, long long, cudaStream_t);
+};
+static const KernelSet g_kernels[3] = {
+    {trm_k_tube_f64, trm_k_tube_wide_f64, trm_k_src_f64, trm_k_pcm_f64},
+    {trm_k_tube_f32, trm_k_tube_wide_f32, trm_k_src_f32, trm_k_pcm_f32},
+    {trm_k_tube_f64s, trm_k_tube_wide_f64s, trm_k_src_f64s, trm_k_pcm_f64s},
+};
 
 // FMA-chain kernels used to MEASURE the FP32 / FP64 CUDA-core peak of the device the bench runs on
 // (MEASURED_PEAKS.json only carries HBM and bf16 tensor numbers; the waveguide kernel is bound by neither).
@@ -225,7 +238,8 @@ struct trm_cuda_ctx {
     void *d_tab_f64 = nullptr, *d_tab_f32 = nullptr;
     void *d_ctab_f64 = nullptr, *d_ctab_f32 = nullptr;   // interpolated converter coefficients per time-register fraction
     uint64_t noise_k0 = 0;
-    trm::KernelInfo info64{}, info32{};
+    trm::KernelInfo info[3]{};        // by precision code
+    const trm::KernelInfo &ki(int precision) const { return info[precision]; }
     cudaStream_t streams[MAX_SLOTS]{};
     Arena arenas[MAX_SLOTS];
     HostStage stages[MAX_SLOTS];
@@ -520,18 +534,19 @@ int wide_groups(const trm_cuda_ctx *ctx, const trm::KernelInfo &ki, int n)
 int launch_stage(trm_cuda_ctx *ctx, int precision, int stage, const DeviceChunk &dc, cudaStream_t s, const ChunkPlan::Group *grp = nullptr,
                  int time_part = -1)
 {
-    const bool f64 = precision == 0;
+    const bool f64 = prec_is_f64(precision);
+    const KernelSet &K = g_kernels[precision];
     int rc = 0;
     if (stage == TRM_STAGE_TUBE) {
         trm::TubeArgs a{};
         a.desc = dc.desc; a.order = dc.order; a.n_utt = dc.n; a.frames = dc.frames; a.tube = dc.tube;
         a.wavetables = ctx->d_wavetables; a.noise_k0 = ctx->noise_k0;
         if (time_part >= 0) { a.desc = dc.desc_t[time_part]; a.state = dc.state; }     // (lane-per-utterance mapping only)
-        const trm::KernelInfo &ki = f64 ? ctx->info64 : ctx->info32;
+        const trm::KernelInfo &ki = ctx->ki(precision);
         const int groups = wide_groups(ctx, ki, dc.n);
         if (time_part >= 0 && groups <= 0) return fail_msg("time split needs the lane-per-utterance waveguide mapping");
-        if (groups > 0) rc = f64 ? trm_k_tube_wide_f64(&a, groups, s) : trm_k_tube_wide_f32(&a, groups, s);
-        else rc = f64 ? trm_k_tube_f64(&a, s) : trm_k_tube_f32(&a, s);
+        if (groups > 0) rc = K.tube_wide(&a, groups, s);
+        else rc = K.tube(&a, s);
     } else if (stage == TRM_STAGE_SRC) {
         // (the running maxima are cleared once per chunk: by the ungrouped launch, or by the first group's)
         if (!grp || grp->u_begin == 0) CK(cudaMemsetAsync(dc.maxbits, 0, (size_t)dc.n * sizeof(unsigned long long), s));
@@ -543,16 +558,16 @@ int launch_stage(trm_cuda_ctx *ctx, int precision, int stage, const DeviceChunk 
         a.item_base = dc.item_base;
         a.n_tiles = dc.n_tiles; a.total_items = dc.total_items;
         if (grp) { a.item_begin = grp->item_begin; a.item_end = grp->item_end; if (a.item_end <= a.item_begin) return 0; }
-        const trm::KernelInfo &ki = f64 ? ctx->info64 : ctx->info32;
+        const trm::KernelInfo &ki = ctx->ki(precision);
         const int grid = ctx->sm_count * std::max(1, ki.src[dc.src_shape].ctas_per_sm);
-        rc = f64 ? trm_k_src_f64(&a, grid, dc.src_shape, s) : trm_k_src_f32(&a, grid, dc.src_shape, s);
+        rc = K.src(&a, grid, dc.src_shape, s);
     } else if (stage == TRM_STAGE_PCM) {
         if (!dc.pcm) return 0;
         trm::PcmArgs a{};
         a.desc = dc.desc; a.n_utt = grp ? grp->u_end : dc.n; a.u_begin = grp ? grp->u_begin : 0;
         a.out = dc.out; a.maxbits = dc.maxbits; a.pcm = dc.pcm;
         const long long longest = grp ? grp->max_n_out : dc.max_n_out;
-        rc = f64 ? trm_k_pcm_f64(&a, longest, s) : trm_k_pcm_f32(&a, longest, s);
+        rc = K.pcm(&a, longest, s);
     }
     if (rc != 0) return fail("kernel launch", (cudaError_t)rc);
     return 0;
@@ -574,12 +589,12 @@ int chunk_utterances(const trm_cuda_ctx *ctx, int precision, int n, const trm_cu
     per_utt = per_utt / std::max(probe, 1) + 1;
     const size_t budget = (size_t)32 << 30;                     // per in-flight chunk (three lanes per device)
     const long long by_mem = std::max<long long>(1, (long long)(budget / per_utt));
-    const trm::KernelInfo &ki = precision == 0 ? ctx->info64 : ctx->info32;
+    const trm::KernelInfo &ki = ctx->ki(precision);
     const long long lo = (long long)ctx->sm_count * (ki.wide_max_utt / 2), hi = (long long)ctx->sm_count * ki.wide_max_utt;
     // FP64: a launch below ~28 utterances per SM is bound by the latency of its feed-forward warps, so halving a batch
     // costs more kernel time than the overlapped copy-out saves -> one chunk up to the device's capacity.  FP32: the
     // kernels are short next to the PCIe time of their PCM -> two chunks, the first one's PCM hides behind the second.
-    long long want = precision == 0 ? hi : std::min<long long>(hi, std::max<long long>(lo, (n + 1) / 2));
+    long long want = prec_is_f64(precision) ? hi : std::min<long long>(hi, std::max<long long>(lo, (n + 1) / 2));
     long long c = std::max<long long>(1, std::min<long long>(std::min<long long>(want, by_mem), n));
     const long long n_chunks = (n + c - 1) / c;                 // balance the chunks
     return (int)((n + n_chunks - 1) / n_chunks);
@@ -623,7 +638,7 @@ int trm_cuda_fp_peak(int device, int precision, int reps, double *tflops)
     CK(cudaSetDevice(device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
-    const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = precision == 0 ? 1 << 14 : 1 << 16;
+    const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = precision != 1 ? 1 << 14 : 1 << 16;
     void *buf = nullptr;
     CK(cudaMalloc(&buf, (size_t)threads * blocks * sizeof(double)));
     cudaEvent_t e0, e1;
@@ -632,7 +647,7 @@ int trm_cuda_fp_peak(int device, int precision, int reps, double *tflops)
     double best = 0;
     for (int r = 0; r < reps + 1; ++r) {
         CK(cudaEventRecord(e0, 0));
-        if (precision == 0) fp_peak_kernel<double><<<blocks, threads>>>((double *)buf, iters);
+        if (precision != 1) fp_peak_kernel<double><<<blocks, threads>>>((double *)buf, iters);
         else fp_peak_kernel<float><<<blocks, threads>>>((float *)buf, iters);
         CK(cudaEventRecord(e1, 0));
         CK(cudaEventSynchronize(e1));
@@ -668,11 +683,13 @@ int trm_cuda_ctx_create(int device, const trm_cuda_tables *t, trm_cuda_ctx **out
     c->wide_min_utt = 1;     // measured: the batch-throughput mapping is the faster one at every batch size (profiles/README.md)
     int rc;
     if ((rc = trm_k_upload_f64(t->fir_coef, t->fir_taps, (const unsigned long long *)t->noise_pow)) != 0 ||
-        (rc = trm_k_upload_f32(t->fir_coef, t->fir_taps, (const unsigned long long *)t->noise_pow)) != 0) {
+        (rc = trm_k_upload_f32(t->fir_coef, t->fir_taps, (const unsigned long long *)t->noise_pow)) != 0 ||
+        (rc = trm_k_upload_f64s(t->fir_coef, t->fir_taps, (const unsigned long long *)t->noise_pow)) != 0) {
         delete c;
         return rc < 0 ? fail_msg("FIR design is not the 49-tap filter the kernels are built for") : fail("constant upload", (cudaError_t)rc);
     }
-    if ((rc = trm_k_configure_f64(&c->info64)) != 0 || (rc = trm_k_configure_f32(&c->info32)) != 0) {
+    if ((rc = trm_k_configure_f64(&c->info[0])) != 0 || (rc = trm_k_configure_f32(&c->info[1])) != 0 ||
+        (rc = trm_k_configure_f64s(&c->info[2])) != 0) {
         delete c;
         return fail("kernel configuration", (cudaError_t)rc);
     }
@@ -692,7 +709,7 @@ int trm_cuda_ctx_create(int device, const trm_cuda_tables *t, trm_cuda_ctx **out
         CK(cudaMemcpy(c->d_tab_f32, tf.data(), tf.size() * sizeof(tf[0]), cudaMemcpyHostToDevice));
         CK(cudaMalloc(&c->d_ctab_f64, (size_t)65536 * trm::SRC_CLD * sizeof(double)));
         CK(cudaMalloc(&c->d_ctab_f32, (size_t)65536 * trm::SRC_CLD * sizeof(float)));
-        if ((rc = trm_k_src_ctab_f64(c->d_tab_f64, c->d_ctab_f64, 0)) != 0 || (rc = trm_k_src_ctab_f32(c->d_tab_f32, c->d_ctab_f32, 0)) != 0) {
+        if ((rc = trm_k_src_ctab_f64s(c->d_tab_f64, c->d_ctab_f64, 0)) != 0 || (rc = trm_k_src_ctab_f32(c->d_tab_f32, c->d_ctab_f32, 0)) != 0) {
             delete c;
             return fail("converter coefficient table", (cudaError_t)rc);
         }
@@ -784,7 +801,8 @@ int trm_cuda_synthesize_host_ex(trm_cuda_ctx *ctx, int precision, int n, const t
     if (launches) *launches = 0;
     if (n <= 0) return 0;
     CK(cudaSetDevice(ctx->device));
-    const size_t esz = precision == 0 ? sizeof(double) : sizeof(float);
+    if (precision < 0 || precision > 2) return fail_msg("unknown precision code");
+    const size_t esz = prec_esz(precision);
     const bool want_pcm = pcm_host != nullptr;
     const int per_chunk = chunk_utterances(ctx, precision, n, desc, esz);
     const int n_chunks = (n + per_chunk - 1) / per_chunk;
@@ -844,11 +862,11 @@ int trm_cuda_synthesize_host_ex(trm_cuda_ctx *ctx, int precision, int n, const t
         long long chunk_out = 0;
         for (int u = u0; u < u1; ++u) chunk_out += desc[u].n_out;
         const int want_groups = (want_pcm && !getenv("TRM_NO_OUT_GROUPS")) ? (int)std::min<long long>(MAX_OUT_GROUPS, chunk_out / (64ll << 20)) : 1;
-        if ((rc = plan_chunk(desc, u0, u1, precision == 0 ? ctx->info64 : ctx->info32, p, want_groups)) != 0) return rc;
+        if ((rc = plan_chunk(desc, u0, u1, ctx->ki(precision), p, want_groups)) != 0) return rc;
         const bool grouped = p.groups.size() > 1;
         // long uniform chunks: the waveguide as two launches in time, the later frames uploaded behind the first
         if (p.uniform_frames >= 512 && !getenv("TRM_NO_TIME_SPLIT") &&
-            wide_groups(ctx, precision == 0 ? ctx->info64 : ctx->info32, u1 - u0) > 0)
+            wide_groups(ctx, ctx->ki(precision), u1 - u0) > 0)
             arm_time_split(p, std::max(64, (int)(0.28 * p.uniform_frames)));
         const bool split = p.split_frame > 0;
         if ((rc = ctx->arenas[slot].reserve(p.arena_bytes(esz, want_pcm))) != 0) return rc;
@@ -1053,7 +1071,8 @@ int trm_cuda_stream_create(trm_cuda_ctx *ctx, int precision, int n_streams, cons
     CK(cudaSetDevice(ctx->device));
     trm_cuda_stream *s = new trm_cuda_stream();
     s->ctx = ctx; s->precision = precision; s->n = n_streams; s->max_m = max_frames_per_push;
-    s->esz = precision == 0 ? sizeof(double) : sizeof(float);
+    if (precision < 0 || precision > 2) return fail_msg("unknown precision code");
+    s->esz = prec_esz(precision);
     s->voice = *voice;
     s->cp = voice->controlPeriod;
     const long long max_new = (long long)(max_frames_per_push + 1) * s->cp + 32;
@@ -1127,8 +1146,9 @@ int trm_cuda_stream_push(trm_cuda_stream *s, const double *frames_host, int m, i
     if (flush && s->frames_seen < 1) { s->flushed = true; return 0; }
     if (n_new <= 0 && !(flush && out_total > s->out_done)) { if (flush) s->flushed = true; return 0; }
     cudaStream_t st = s->st;
-    const bool f64 = s->precision == 0;
-    const trm::KernelInfo &ki = f64 ? ctx->info64 : ctx->info32;
+    const bool f64 = prec_is_f64(s->precision);
+    const KernelSet &K = g_kernels[s->precision];
+    const trm::KernelInfo &ki = ctx->ki(s->precision);
     // ---- waveguide: samples [s_done, target) -----------------------------------------------------------------
     const long long f0 = s->s_done / cp;                          // control interval the call starts in
     const int jc0 = (int)(s->s_done % cp);
@@ -1207,7 +1227,7 @@ int trm_cuda_stream_push(trm_cuda_stream *s, const double *frames_host, int m, i
         const int gmax = ki.wide_max_utt;
         const int groups = std::max(1, std::min(ctx->sm_count, (n + 1) / 2));
         const int g2 = (n + groups - 1) / groups > gmax ? (n + gmax - 1) / gmax : groups;
-        rc = f64 ? trm_k_tube_wide_f64(&a, g2, st) : trm_k_tube_wide_f32(&a, g2, st);
+        rc = K.tube_wide(&a, g2, st);
         if (rc != 0) return fail("stream waveguide launch", (cudaError_t)rc);
     }
     // ---- resampler: outputs [out_done, out_total) ------------------------------------------------------------
@@ -1220,7 +1240,7 @@ int trm_cuda_stream_push(trm_cuda_stream *s, const double *frames_host, int m, i
         a.tile_utt = dc.tile_utt; a.tile_nt = dc.tile_nt; a.tile_max_out = dc.tile_max_out; a.tile_first_out = dc.tile_first_out;
         a.item_base = dc.item_base; a.n_tiles = dc.n_tiles; a.total_items = dc.total_items;
         const int grid = ctx->sm_count * std::max(1, ki.src[dc.src_shape].ctas_per_sm);
-        rc = f64 ? trm_k_src_f64(&a, grid, dc.src_shape, st) : trm_k_src_f32(&a, grid, dc.src_shape, st);
+        rc = K.src(&a, grid, dc.src_shape, st);
         if (rc != 0) return fail("stream resampler launch", (cudaError_t)rc);
         if (samples_host)
             CK(cudaMemcpy2DAsync(samples_host, (size_t)s->cap_out * s->esz, s->d_out + (size_t)(s->out_done % 4) * s->esz,
@@ -1266,12 +1286,13 @@ int trm_cuda_resident_create(trm_cuda_ctx *ctx, int precision, int n, const trm_
 {
     *out = nullptr;
     CK(cudaSetDevice(ctx->device));
-    const size_t esz = precision == 0 ? sizeof(double) : sizeof(float);
+    if (precision < 0 || precision > 2) return fail_msg("unknown precision code");
+    const size_t esz = prec_esz(precision);
     trm_cuda_resident *r = new trm_cuda_resident();
     r->ctx = ctx;
     r->precision = precision;
     int rc;
-    if ((rc = plan_chunk(desc, 0, n, precision == 0 ? ctx->info64 : ctx->info32, r->plan)) != 0) { delete r; return rc; }
+    if ((rc = plan_chunk(desc, 0, n, ctx->ki(precision), r->plan)) != 0) { delete r; return rc; }
     if ((rc = r->arena.reserve(r->plan.arena_bytes(esz, true))) != 0) { delete r; return rc; }
     carve(r->arena, r->plan, esz, true, r->dc);
     if ((rc = upload_plan(r->plan, r->dc, nullptr, 0)) != 0 || (rc = upload_frames(r->plan, r->dc, desc, frames_host, 0)) != 0) {
@@ -1313,7 +1334,7 @@ int trm_cuda_resident_fetch(trm_cuda_resident *r, int16_t *pcm_host, void *sampl
 {
     CK(cudaSetDevice(r->ctx->device));
     CK(cudaDeviceSynchronize());
-    const size_t esz = r->precision == 0 ? sizeof(double) : sizeof(float);
+    const size_t esz = prec_esz(r->precision);
     const ChunkPlan &p = r->plan;
     long long c_hi = 0, o_hi = 0, t_hi = 0;
     for (const auto &d : p.desc) {

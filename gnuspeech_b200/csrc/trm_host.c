@@ -725,6 +725,7 @@ struct TRMBatch {
     int64_t launches;
 };
 
+static int precision_ok(int p) { return p == TRM_PRECISION_FP64 || p == TRM_PRECISION_FP32 || p == TRM_PRECISION_FP64_STRICT; }
 static int64_t round_up_elems(int64_t v) { return (v + TRM_ALIGN_ELEMS - 1) / TRM_ALIGN_ELEMS * TRM_ALIGN_ELEMS; }
 
 void TRMBatchFree(TRMBatch *b)
@@ -740,7 +741,7 @@ TRMBatch *TRMBatchCreate(int n, const TRMInputParameters *ip, int shared, const 
 {
     int dummy;
     if (!err) err = &dummy;
-    if (n < 0 || (precision != TRM_PRECISION_FP64 && precision != TRM_PRECISION_FP32)) {
+    if (n < 0 || !precision_ok(precision)) {
         *err = set_err(TRM_ERR_PARAM, "bad batch size or precision%s", "");
         return NULL;
     }
@@ -1024,8 +1025,7 @@ TRMStream *TRMStreamCreate(int n_streams, const TRMInputParameters *voice, int p
 {
     int dummy;
     if (!err) err = &dummy;
-    if (n_streams <= 0 || max_frames_per_push <= 0 || !voice ||
-        (precision != TRM_PRECISION_FP64 && precision != TRM_PRECISION_FP32)) {
+    if (n_streams <= 0 || max_frames_per_push <= 0 || !voice || !precision_ok(precision)) {
         *err = set_err(TRM_ERR_PARAM, "bad stream arguments%s", "");
         return NULL;
     }
@@ -1238,7 +1238,7 @@ void TRMTubeModelFree(TRMTubeModel *m)
 
 int TRMTubeModelSetPrecision(TRMTubeModel *m, int precision)
 {
-    if (precision != TRM_PRECISION_FP64 && precision != TRM_PRECISION_FP32) return set_err(TRM_ERR_PARAM, "bad precision%s", "");
+    if (!precision_ok(precision)) return set_err(TRM_ERR_PARAM, "bad precision%s", "");
     m->precision = precision;
     return TRM_OK;
 }
@@ -1257,7 +1257,7 @@ int TRMTubeModelSynthesize(TRMTubeModel *m)
     if (!b) return err;
     const size_t n_out = (size_t)b->layout.total_out_samples, n_pcm = (size_t)b->layout.total_pcm_samples;
     const size_t n_tube = (size_t)b->total_tube_elems;
-    const size_t esz = m->precision == TRM_PRECISION_FP64 ? sizeof(double) : sizeof(float);
+    const size_t esz = m->precision != TRM_PRECISION_FP32 ? sizeof(double) : sizeof(float);
     void *samples = malloc((n_out ? n_out : 1) * esz), *tube = malloc((n_tube ? n_tube : 1) * esz);
     m->pcm = malloc((n_pcm ? n_pcm : 1) * sizeof(int16_t));
     m->resampled = malloc((n_out ? n_out : 1) * sizeof(double));
@@ -1270,7 +1270,7 @@ int TRMTubeModelSynthesize(TRMTubeModel *m)
     if (err == TRM_OK) {
         m->numberSamples = b->numberSamples[0];
         m->maximum = b->maxima[0];
-        if (m->precision == TRM_PRECISION_FP64) {
+        if (m->precision != TRM_PRECISION_FP32) {
             memcpy(m->resampled, samples, (size_t)m->numberSamples * sizeof(double));
             memcpy(m->tube, tube, (size_t)b->desc[0].n_tube * sizeof(double));
         } else {

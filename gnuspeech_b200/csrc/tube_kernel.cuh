@@ -40,7 +40,8 @@
 #include "kernel_args.h"
 #include "trm_cuda.h"
 
-namespace trm {
+namespace TRM_KERNEL_NS {
+using namespace trm;
 
 constexpr double TWO_M44 = 5.684341886080801486968994140625e-14;   // 2^-44 exactly
 
@@ -153,6 +154,73 @@ __device__ __forceinline__ double amplitude_db(double dB)
     if (x >= 0.0) return 1.0;
     return exp10(div_known(x, 20.0, 1.0 / 20.0));
 }
+// ---- helpers of the FP64 conformance mode's cheaper forms (tolerance 1e-9, BASELINE.json; none of them is used when
+// TRM_STRICT = 1) -----------------------------------------------------------------------------------------------------
+// 1 / s: hardware seed (MUFU.RCP64H, >= 16 good bits) refined by one cubic Newton step, x (1 + e + e^2) with
+// e = 1 - s x: relative error <= 2^-48 in the worst case the seed allows, 5e-19 for its typical 2^-22.  No special
+// cases: s = 0 gives inf * 0 = NaN in the correction, which is what the reference's 0 / 0 between two closed sections
+// produces (TRMTubeModel.m:716-718) and must propagate.
+__device__ __forceinline__ double rcp_fast(double s)
+{
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(s));
+    const double e = fma(-s, x, 1.0);
+    const double e2 = fma(e, e, e);
+    return fma(x, e2, x);
+}
+
+// 2^x for |x| <= 1000: x = n + f, |f| <= 1/2, 2^f = exp(f ln 2) by its Taylor series to degree 13 (|f ln 2| <= 0.347:
+// truncation 4e-18), exponent added as an integer.  Straight-line code; ~1 ulp.
+__device__ __forceinline__ double exp2_inline(double x)
+{
+    x = fmin(fmax(x, -1000.0), 1000.0);
+    const double n = rint(x);
+    const double g = (x - n) * 0.693147180559945309417;
+    double p = 1.6059043836821613e-10;                 // 1/13!
+    p = fma(p, g, 2.08767569878681e-09);               // 1/12!
+    p = fma(p, g, 2.505210838544172e-08);              // 1/11!
+    p = fma(p, g, 2.755731922398589e-07);              // 1/10!
+    p = fma(p, g, 2.7557319223985893e-06);             // 1/9!
+    p = fma(p, g, 2.48015873015873e-05);               // 1/8!
+    p = fma(p, g, 0.0001984126984126984);              // 1/7!
+    p = fma(p, g, 0.001388888888888889);               // 1/6!
+    p = fma(p, g, 0.008333333333333333);               // 1/5!
+    p = fma(p, g, 0.041666666666666664);               // 1/4!
+    p = fma(p, g, 0.16666666666666666);                // 1/3!
+    p = fma(p, g, 0.5);
+    p = fma(p, g, 1.0);
+    p = fma(p, g, 1.0);
+    return __hiloint2double(__double2hiint(p) + ((int)n << 20), __double2loint(p));
+}
+
+// sin and cos for |x| <= ~100 (the arguments here are below 2 pi): Cody-Waite reduction by pi/2 in two parts with
+// fused multiply-adds, then the minimax kernels of fdlibm (k_sin.c / k_cos.c coefficients) on |r| <= pi/4; ~1 ulp.
+__device__ __forceinline__ void sincos_inline(double x, double *sn, double *cs)
+{
+    const double n = rint(x * 0.63661977236758134308);
+    double r = fma(-n, 1.5707963267948966, x);
+    r = fma(-n, 6.123233995736766e-17, r);
+    const int q = (int)n;
+    const double z = r * r;
+    double ps = 1.58969099521155010221e-10;
+    ps = fma(ps, z, -2.50507602534068634195e-08);
+    ps = fma(ps, z, 2.75573137070700676789e-06);
+    ps = fma(ps, z, -1.98412698298579493134e-04);
+    ps = fma(ps, z, 8.33333333332248946124e-03);
+    ps = fma(ps, z, -1.66666666666666324348e-01);
+    const double sr = fma(r * z, ps, r);
+    double pc = -1.13596475577881948265e-11;
+    pc = fma(pc, z, 2.08757232129817482790e-09);
+    pc = fma(pc, z, -2.75573143513906633035e-07);
+    pc = fma(pc, z, 2.48015872894767294178e-05);
+    pc = fma(pc, z, -1.38888888888741095749e-03);
+    pc = fma(pc, z, 4.16666666666666019037e-02);
+    const double cr = fma(z * z, pc, fma(-0.5, z, 1.0));
+    const double s0 = (q & 1) ? cr : sr, c0 = (q & 1) ? sr : cr;
+    *sn = (q & 2) ? -s0 : s0;
+    *cs = ((q + 1) & 2) ? -c0 : c0;
+}
+
 // Bit-wise select (one LOP3 per 32 bits): m = all ones -> x, m = 0 -> y.  Used instead of ?: in the junction
 // loop so that the per-lane roles stay straight-line code (the compiler turns lane-dependent ternaries into
 // divergent branch regions with reconvergence barriers and a divergence check before every shuffle).
@@ -744,4 +812,4 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) tube_kernel(TubeArgs ar
     }
 }
 
-}  // namespace trm
+}  // namespace TRM_KERNEL_NS

@@ -26,9 +26,31 @@
 // (TRM_TUBE_MAPPING=sections|utterances overrides).  Both are checked against the same oracle.
 #pragma once
 
+#include <stdio.h>
+
 #include "tube_kernel.cuh"
 
-namespace trm {
+namespace TRM_KERNEL_NS {
+using namespace trm;
+
+// Arithmetic of this translation unit's double instantiation (kernel_args.h):
+//   STRICT (kernels_f64s.cu, -fmad=false): the reference's operations in the reference's order -- sequential oscillator
+//       chain, IEEE divisions, library exp2 / exp10 / tan / cos every sample, one-chain FIR sum, ladder as written in
+//       TRMTubeModel.m:778-853.
+//   conformance (kernels_f64.cu): the same values to <= 1e-9 (measured ~1e-12) from cheaper forms --
+//       * every transcendental on the path is a function of a parameter that is LINEAR inside a control interval, so
+//         2^(a + j b), 10^(a + j b), cos / sin(a + j b) are geometric sequences: the parameter lanes seed a complex value
+//         and its per-sample ratio at each control frame (two exp2 or two sincos per frame, not per sample) and step it
+//         with one complex multiplication per sample next to the interpolation add;
+//       * oscillator phase in 64-bit fixed point with a warp scan (as the FP32 mode) instead of a 32-step dependent chain
+//         walked by every lane;
+//       * reflection coefficients from a Newton-refined hardware reciprocal; damping folded into them (k d), so that a
+//         two-port junction of the ladder is 4 operations (e = a - b, x = kd e, fma(a, d, x), fma(b, d, x)) instead of 7;
+//       * FIR as four partial sums of fused multiply-adds.
+//     The discontinuous decisions of the path (glottal closure point rint(ax tnDelta), amplitude() clamps, frication
+//     tap position, table indices) are taken on exactly interpolated parameters; the closure point is re-evaluated with
+//     a directly computed amplitude whenever the product comes within 1e-6 of a rounding boundary.
+constexpr bool STRICT = TRM_STRICT != 0;
 
 template <typename R> struct Wide;
 template <> struct Wide<float> {
@@ -38,14 +60,26 @@ template <> struct Wide<float> {
     static constexpr int UP = 2 * MAX_PAIRS + 1;     // padded utterance dimension: odd -> conflict-free writers
     static constexpr int THREADS = 32 * (2 + MAX_PAIRS);   // recurrence warp + feed-forward warps + one idle warp
     static constexpr int OUT_LD = 20;                // 16-byte aligned rows of the output transpose tile
+    static constexpr int REGS_HI = 0, REGS_DONOR = 0;   // no register redistribution
 };
 template <> struct Wide<double> {
     using Unit = double2;
     static constexpr int MAX_PAIRS = 14;
     static constexpr int NF = 12;
     static constexpr int UP = 2 * MAX_PAIRS + 1;
-    static constexpr int THREADS = 32 * (2 + MAX_PAIRS);
     static constexpr int OUT_LD = 18;
+    // Register redistribution (conformance mode): the CTA is launched with one extra warpgroup, which caps every thread
+    // at 65536 / 640 -> 96 registers; the extra warpgroup gives its registers back at once (setmaxnreg.dec 24) and
+    // exits, and warpgroup 0 -- the recurrence warp, which carries 41 FP64 state values per lane and needs its per-sample
+    // record in flight to cover load and FP64 latencies -- takes them (setmaxnreg.inc): 96 + 72 = 168.
+#ifndef TRM_DONOR_WARPS
+#define TRM_DONOR_WARPS 4
+#endif
+    static constexpr int DONORS = STRICT ? 0 : TRM_DONOR_WARPS;
+    static constexpr int THREADS = 32 * (2 + MAX_PAIRS) + 32 * DONORS;
+    static constexpr int REGS_BASE = (65536 / THREADS) / 8 * 8;                      // what __launch_bounds__ gives every thread
+    static constexpr int REGS_DONOR = 24;
+    static constexpr int REGS_HI = DONORS ? (REGS_BASE + (DONORS * 32 * (REGS_BASE - REGS_DONOR) / 128) / 8 * 8) : 0;
 };
 constexpr int WIDE_SLOTS = 2;
 // Warp w is scheduled by SM sub-partition w % 4, and the recurrence warp (warp 0) alone keeps its partition's FP64
@@ -80,8 +114,21 @@ struct WideSmem {
     long long n_cta;
 };
 
-// try_wait with a suspend-time hint: the waiting warp sleeps in hardware until the phase completes instead of
-// spinning through issue slots the working warps need
+// Waiting on a ring barrier.  try_wait returns after a short hardware-defined time whether or not the phase completed,
+// so a bare loop around it spins: measured (ncu, round 2), the 14 feed-forward warps of a CTA waiting for the recurrence
+// warp issued 47 % of ALL warp instructions of the kernel in this loop, through the very issue slots and shared-memory
+// port the recurrence warp needs.  BACKOFF_NS > 0 parks the warp between polls (the feed-forward warps have two blocks
+// of slack); the recurrence warp, which is the critical path, polls without a pause.
+#ifndef TRM_PROFILE_PHASES
+#define TRM_PROFILE_PHASES 0
+#endif
+#ifndef TRM_WAIT_NS
+#define TRM_WAIT_NS 400
+#endif
+#ifndef TRM_WAIT_FULL_NS
+#define TRM_WAIT_FULL_NS 100
+#endif
+template <int BACKOFF_NS>
 __device__ __forceinline__ void mbar_wait_sleep(void *bar, uint32_t parity)
 {
     uint32_t ok = 0;
@@ -93,8 +140,18 @@ __device__ __forceinline__ void mbar_wait_sleep(void *bar, uint32_t parity)
             : "=r"(ok)
             : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
             : "memory");
-        if (spin > (1u << 20)) __trap();
+        if (!ok) {
+            if (BACKOFF_NS > 0) __nanosleep(BACKOFF_NS);
+            if (spin > (1u << 22)) __trap();
+        }
     }
+}
+
+// predicated shared-memory store as ONE instruction (@p STS): written as a C++ `if`, three of them per interpolation
+// step became a divergent branch region with a reconvergence barrier -- per step -- in the parameter phase
+__device__ __forceinline__ void sts_f64_if(bool pred, double *p, double v)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.shared.f64 [%0], %1;\n\t}" ::"r"(smem_u32(p)), "d"(v), "r"((unsigned)pred) : "memory");
 }
 
 __device__ __forceinline__ void mbar_arrive(void *bar)
@@ -115,8 +172,12 @@ template <typename R> __device__ __forceinline__ R *state_vals(void *state, int 
 struct WideArgs {
     TubeArgs t;
     int n_groups;      // CTAs; group g holds utterances order[start(g) .. start(g+1))
-    int debug;         // profiling aid (TRM_WIDE_DEBUG): 1 = feed-forward warps skip their work, 2 = recurrence warp skips its work
 };
+// Profiling builds only (never in the shipped library): -DTRM_PROFILE_SKIP=1 makes the feed-forward warps skip their
+// work, =2 the recurrence warp, to time the two halves of the kernel separately.
+#ifndef TRM_PROFILE_SKIP
+#define TRM_PROFILE_SKIP 0
+#endif
 
 __device__ __forceinline__ void wide_group(int n, int n_groups, int g, int &start, int &count)
 {
@@ -125,50 +186,16 @@ __device__ __forceinline__ void wide_group(int n, int n_groups, int g, int &star
     count = base + (g < rem ? 1 : 0);
 }
 
+// =========================================================================================================
+// recurrence warp (warp 0 of the CTA): lane = utterance
+// =========================================================================================================
 template <typename R>
-__global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs wargs)
+__device__ __forceinline__ void wide_recurrence_warp(WideSmem<R> &W, const WideArgs &wargs, int g_start, int g_count, int n_blocks, int lane)
 {
-    constexpr bool FAST = sizeof(R) == 4;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    WideSmem<R> &W = *reinterpret_cast<WideSmem<R> *>(smem_raw);
+    constexpr bool FAST = sizeof(R) == 4;                  // FP32 fast mode
+    constexpr bool F64C = !FAST && !STRICT;                // FP64 conformance mode (cheaper forms, see the top of the file)
+    (void)F64C;
     const TubeArgs &args = wargs.t;
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int g_start, g_count;
-    wide_group(args.n_utt, wargs.n_groups, blockIdx.x, g_start, g_count);
-    const int n_pairs = (g_count + 1) >> 1;
-
-    // ---- CTA init: zero the ring and histories, barriers, per-utterance pointers ---------------------------
-    {
-        uint32_t *w = reinterpret_cast<uint32_t *>(&W.ring[0][0][0][0]);
-        constexpr int NW = (int)(sizeof(W.ring) / 4);
-        for (int i = threadIdx.x; i < NW; i += blockDim.x) w[i] = 0u;
-        for (int h = warp; h < 2 * Wide<R>::MAX_PAIRS; h += blockDim.x >> 5) {
-            for (int i = lane; i < FIR_HIST + TB; i += 32) { W.ff[h].HE[i] = (R)0; W.ff[h].HO[i] = (R)0; }
-            if (lane < TB) W.ff[h].INC[lane] = 0.0;
-        }
-        if (threadIdx.x == 0) {
-            W.n_cta = 0;
-            for (int s = 0; s < WIDE_SLOTS; ++s) { mbar_init(&W.full[s], (uint32_t)n_pairs); mbar_init(&W.empty[s], 1); }
-            mbar_fence_init();
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        const bool has = lane < g_count;
-        const int u = args.order ? args.order[g_start + (has ? lane : 0)] : g_start + (has ? lane : 0);
-        const trm_cuda_utterance *D = args.desc + u;
-        W.n_tube[lane] = has ? D->n_tube : 0;
-        W.out_ptr[lane] = reinterpret_cast<R *>(args.tube) + D->tube_offset;
-        if (has) atomicMax((unsigned long long *)&W.n_cta, (unsigned long long)D->n_tube);
-    }
-    __syncthreads();
-    const int64_t n_cta = W.n_cta;
-    const int pair = warp - 1 - (warp > WIDE_IDLE_WARP ? 1 : 0);
-    if (n_cta <= 0 || warp == WIDE_IDLE_WARP || pair >= n_pairs) return;
-    const int n_blocks = (int)((n_cta + TB - 1) / TB);
-
-    if (warp == 0) {
         // =====================================================================================================
         // recurrence warp
         // =====================================================================================================
@@ -214,9 +241,9 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
 
             for (int blk = 0; blk < n_blocks; ++blk) {
                 const int slot = blk & 1;
-                mbar_wait_sleep(&W.full[slot], (uint32_t)((blk >> 1) & 1));
+                mbar_wait_sleep<TRM_WAIT_FULL_NS>(&W.full[slot], (uint32_t)((blk >> 1) & 1));
 #pragma unroll 1
-                for (int s0 = 0; s0 < ((wargs.debug & 2) ? 0 : TB); s0 += 4) {
+                for (int s0 = 0; s0 < ((TRM_PROFILE_SKIP & 2) ? 0 : TB); s0 += 4) {
                   float yo[4];
 #pragma unroll
                   for (int si = 0; si < 4; ++si) {
@@ -319,8 +346,8 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
                 sv[32] = m_ry; sv[33] = m_rx; sv[34] = m_rY; sv[35] = n_ry; sv[36] = n_rx; sv[37] = n_rY;
                 sv[38] = y1; sv[39] = y2; sv[40] = thy;
             }
-        } else {
-            // ---- conformance mode: the reference's operations in the reference's order ---------------------------
+        } else if constexpr (STRICT) {
+            // ---- strict mode: the reference's operations in the reference's order -------------------------------
             // The 16 junctions of one sample are independent; the code is written stage by stage ACROSS the junctions
             // (all differences, then all k-products, ...) so that consecutive instructions are independent and the
             // FP64 pipe never waits on its own result.  Per-utterance constants other than the damping factor are read
@@ -356,9 +383,9 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
 
             for (int blk = 0; blk < n_blocks; ++blk) {
                 const int slot = blk & 1;
-                mbar_wait_sleep(&W.full[slot], (uint32_t)((blk >> 1) & 1));
+                mbar_wait_sleep<TRM_WAIT_FULL_NS>(&W.full[slot], (uint32_t)((blk >> 1) & 1));
 #pragma unroll 1
-                for (int s0 = 0; s0 < ((wargs.debug & 2) ? 0 : TB); s0 += 2) {
+                for (int s0 = 0; s0 < ((TRM_PROFILE_SKIP & 2) ? 0 : TB); s0 += 2) {
                     double yo[2];
 #pragma unroll
                     for (int si = 0; si < 2; ++si) {
@@ -457,14 +484,175 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
                 sv[32] = m_ry; sv[33] = m_rx; sv[34] = m_rY; sv[35] = n_ry; sv[36] = n_rx; sv[37] = n_rY;
                 sv[38] = y1; sv[39] = y2; sv[40] = thy;
             }
-        }
-        return;
-    }
+        } else {
+            // ---- FP64 conformance mode: damping folded into the reflection coefficients, fused multiply-adds ----------
+            // A two-port junction with incident waves a (from the left) and b (from the right), k d = kd:
+            //     e = a - b;  x = kd e;  right-going = fma(a, d, x) (+ tap fr);  left-going = fma(b, d, x)
+            // which is (a + k e) d and (b + k e) d of TRMTubeModel.m:796-829 with one rounding placed differently.
+            // Record of one sample (feed-forward warps, below):
+            //   {kd0,kd1} {kd2,aL d} {kd4,kd6} {kd7,kd8} {k9,kd10} {aU d,FC1} {FC2,FC3} {FC4,FC5} {FC6,FC7} {FC8,2g} {2b,in} {ff,thr}
+            enum { K_TB1, K_GAIN, K_MA10, K_MB11, K_MA20, K_MA21, K_MB21, K_NA10, K_NB11, K_NA20, K_NA21, K_NB21,
+                   K_NK0, K_NK1, K_NK2, K_NK3, K_NK4 };
+            {
+                double (*kc)[32] = W.kc;
+                kc[K_TB1][lane] = D->tb1; kc[K_GAIN][lane] = D->throatGain;
+                kc[K_MA10][lane] = D->mouth[0]; kc[K_MB11][lane] = D->mouth[1]; kc[K_MA20][lane] = D->mouth[2];
+                kc[K_MA21][lane] = D->mouth[3]; kc[K_MB21][lane] = D->mouth[4];
+                kc[K_NA10][lane] = D->nose[0]; kc[K_NB11][lane] = D->nose[1]; kc[K_NA20][lane] = D->nose[2];
+                kc[K_NA21][lane] = D->nose[3]; kc[K_NB21][lane] = D->nose[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) kc[K_NK0 + q][lane] = D->nasal_coeff[q] * D->dampingFactor;   // constant junctions: kd
+                kc[K_NK4][lane] = D->nasal_coeff[4];
+            }
+            __syncwarp(FULL);
+#define KC(i) (W.kc[i][lane])
+            double t[10], bt[10], nt[6], nb[6];
+#pragma unroll
+            for (int q = 0; q < 10; ++q) { t[q] = 0.0; bt[q] = 0.0; }
+#pragma unroll
+            for (int q = 0; q < 6; ++q) { nt[q] = 0.0; nb[q] = 0.0; }
+            double m_ry = 0.0, m_rx = 0.0, m_rY = 0.0, n_ry = 0.0, n_rx = 0.0, n_rY = 0.0;
+            double y1 = 0.0, y2 = 0.0, thy = 0.0;
+            double *const sv = (args.state && has) ? state_vals<double>(args.state, u) + STATE_SER : nullptr;
+            if (sv) {                                      // streaming: continue where the previous call stopped
+#pragma unroll
+                for (int q = 0; q < 10; ++q) { t[q] = sv[q]; bt[q] = sv[10 + q]; }
+#pragma unroll
+                for (int q = 0; q < 6; ++q) { nt[q] = sv[20 + q]; nb[q] = sv[26 + q]; }
+                m_ry = sv[32]; m_rx = sv[33]; m_rY = sv[34]; n_ry = sv[35]; n_rx = sv[36]; n_rY = sv[37];
+                y1 = sv[38]; y2 = sv[39]; thy = sv[40];
+            }
 
-    // =========================================================================================================
-    // feed-forward warp: utterances 2*pair and 2*pair+1 of the group, lane = sample of a 16-sample block
-    // (phases S0 / A1 / S1 / A2 of tube_kernel.cuh; the results go to the ring instead of the ladder's tables)
-    // =========================================================================================================
+            for (int blk = 0; blk < n_blocks; ++blk) {
+                const int slot = blk & 1;
+                mbar_wait_sleep<TRM_WAIT_FULL_NS>(&W.full[slot], (uint32_t)((blk >> 1) & 1));
+                // The record of sample s+1 is requested while sample s is computed: every unit is re-loaded, into the same
+                // registers, right after its last use, so that a load has most of a sample time (~200 cycles) to arrive --
+                // the warp's shared-memory loads queue behind those of 14 feed-forward warps.
+                double2 q0 = W.ring[slot][0][0][lane], q1 = W.ring[slot][1][0][lane], q2 = W.ring[slot][2][0][lane], q3 = W.ring[slot][3][0][lane];
+                double2 q4 = W.ring[slot][4][0][lane], q5 = W.ring[slot][5][0][lane], q6 = W.ring[slot][6][0][lane], q7 = W.ring[slot][7][0][lane];
+                double2 q8 = W.ring[slot][8][0][lane], q9 = W.ring[slot][9][0][lane], q10 = W.ring[slot][10][0][lane], q11 = W.ring[slot][11][0][lane];
+#pragma unroll 1
+                for (int s0 = 0; s0 < ((TRM_PROFILE_SKIP & 2) ? 0 : TB); s0 += 2) {
+                    double yo[2];
+#pragma unroll
+                    for (int si = 0; si < 2; ++si) {
+                        const int sn = (s0 + si + 1) & (TB - 1);     // (the last sample of a block re-reads sample 0: harmless, reloaded after the wait)
+                        // Written stage by stage ACROSS the junctions: the operations of one stage are mutually independent,
+                        // so the FP64 pipe (one warp instruction per ~2.25 cycles, 8-cycle latency) always has a ready one.
+                        const double c_tb1 = KC(K_TB1), c_mb11 = KC(K_MB11), c_nb11 = KC(K_NB11), c_nk4 = KC(K_NK4);
+                        const double c_nk0 = KC(K_NK0), c_nk1 = KC(K_NK1), c_nk2 = KC(K_NK2), c_nk3 = KC(K_NK3);
+                        // ---- stage 1: differences, first products ----
+                        const double fr1 = fma(q9.y, y1, q11.x);                      // band-pass (TRMFilters.m:19-29, factor 2 folded in)
+                        const double th = fma(c_tb1, thy, q11.y);                     // throat low-pass (TRMFilters.m:72-77)
+                        const double e0 = t[0] - bt[1], e1 = t[1] - bt[2], e2 = t[2] - bt[3], e4 = t[4] - bt[5];
+                        const double e6 = t[6] - bt[7], e7 = t[7] - bt[8], e8 = t[8] - bt[9];
+                        const double en0 = nt[0] - nb[1], en1 = nt[1] - nb[2], en2 = nt[2] - nb[3], en3 = nt[3] - nb[4], en4 = nt[4] - nb[5];
+                        const double pa = q1.y * t[3];                                // velum 3-way junction (m:810-813), d folded in
+                        const double mk = q4.x * t[9], nkk = c_nk4 * nt[5];           // mouth / nose (m:832-835, 846-849)
+                        const double m1 = c_mb11 * m_ry, n1 = c_nb11 * n_ry;
+                        const double g0 = fma(bt[0], d, q10.y);                       // glottis end (m:792)
+                        const double h5 = bt[6] * d;                                  // S6|S7: pure delay (m:821-822)
+                        // ---- stage 2: kd-products ----
+                        const double fr = fma(-q10.x, y2, fr1);
+                        const double x0 = q0.x * e0, x1 = q0.y * e1, x2 = q1.x * e2, x4 = q2.x * e4, x6 = q2.y * e6, x7 = q3.x * e7, x8 = q3.y * e8;
+                        const double xn0 = q4.y * en0, xn1 = c_nk0 * en1, xn2 = c_nk1 * en2, xn3 = c_nk2 * en3, xn4 = c_nk3 * en4;
+                        const double pb = fma(q1.y, bt[4], pa);
+                        const double refl = fma(KC(K_MA10), mk, -m1), refn = fma(KC(K_NA10), nkk, -n1);
+                        const double mx1 = t[9] + mk, nx1 = nt[5] + nkk;
+                        y2 = y1; y1 = fr; thy = th;
+                        const double q5x = q5.x, q5y = q5.y, q7y = q7.y, q9x = q9.x;
+                        q0 = W.ring[slot][0][sn][lane]; q1 = W.ring[slot][1][sn][lane]; q2 = W.ring[slot][2][sn][lane];
+                        q3 = W.ring[slot][3][sn][lane]; q4 = W.ring[slot][4][sn][lane];
+                        q9 = W.ring[slot][9][sn][lane]; q10 = W.ring[slot][10][sn][lane]; q11 = W.ring[slot][11][sn][lane];
+                        // ---- stage 3: waves before injection, radiation filters ----
+                        const double jp = fma(q5x, nb[0], pb);
+                        const double u1 = fma(t[0], d, x0), v0 = fma(bt[1], d, x0);
+                        const double u2 = fma(t[1], d, x1), v1 = fma(bt[2], d, x1);
+                        const double u3 = fma(t[2], d, x2), v2 = fma(bt[3], d, x2);
+                        const double u5 = fma(t[4], d, x4), v4 = fma(bt[5], d, x4);
+                        const double u7 = fma(t[6], d, x6), v6 = fma(bt[7], d, x6);
+                        const double u8 = fma(t[7], d, x7), v7 = fma(bt[8], d, x7);
+                        const double u9 = fma(t[8], d, x8), v8 = fma(bt[9], d, x8);
+                        const double un1 = fma(nt[0], d, xn0), vn0 = fma(nb[1], d, xn0);
+                        const double un2 = fma(nt[1], d, xn1), vn1 = fma(nb[2], d, xn1);
+                        const double un3 = fma(nt[2], d, xn2), vn2 = fma(nb[3], d, xn2);
+                        const double un4 = fma(nt[3], d, xn3), vn3 = fma(nb[4], d, xn3);
+                        const double un5 = fma(nt[4], d, xn4), vn4 = fma(nb[5], d, xn4);
+                        const double f5 = q7y * fr;
+                        const double ra = KC(K_MA20) * mx1, rb = KC(K_NA20) * nx1;
+                        const double b9n = d * refl, nb5n = d * refn;
+                        // ---- stage 4: frication injection (m:803-829), 3-way outputs ----
+                        const double rc = fma(KC(K_MA21), m_rx, ra), rd = fma(KC(K_NA21), n_rx, rb);
+                        const double b3n = fma(-d, t[3], jp), w4 = fma(-d, bt[4], jp), nt0n = fma(-d, nb[0], jp);
+                        const double t6n = fma(t[5], d, f5);
+                        t[0] = g0;
+                        t[1] = u1;                    bt[0] = v0;
+                        t[2] = fma(q5y, fr, u2);      bt[1] = v1;
+                        t[3] = fma(q6.x, fr, u3);     bt[2] = v2;
+                        t[5] = fma(q7.x, fr, u5);     bt[4] = v4;
+                        t[7] = fma(q8.x, fr, u7);     bt[6] = v6;
+                        t[8] = fma(q8.y, fr, u8);     bt[7] = v7;
+                        t[9] = fma(q9x, fr, u9);      bt[8] = v8;
+                        t[4] = fma(q6.y, fr, w4);     bt[3] = b3n;
+                        q5 = W.ring[slot][5][sn][lane]; q6 = W.ring[slot][6][sn][lane]; q7 = W.ring[slot][7][sn][lane];
+                        q8 = W.ring[slot][8][sn][lane];
+                        t[6] = t6n;                   bt[5] = h5;
+                        bt[9] = b9n;
+                        nt[0] = nt0n;
+                        nt[1] = un1; nb[0] = vn0; nt[2] = un2; nb[1] = vn1; nt[3] = un3; nb[2] = vn2;
+                        nt[4] = un4; nb[3] = vn3; nt[5] = un5; nb[4] = vn4; nb[5] = nb5n;
+                        const double radm = fma(-KC(K_MB21), m_rY, rc), radn = fma(-KC(K_NB21), n_rY, rd);
+                        m_ry = refl; m_rx = mx1; m_rY = radm;
+                        n_ry = refn; n_rx = nx1; n_rY = radn;
+                        yo[si] = fma(th, KC(K_GAIN), radm + radn);
+                    }
+                    *reinterpret_cast<double2 *>(&orow[s0]) = make_double2(yo[0], yo[1]);
+                }
+#undef KC
+                __syncwarp(FULL);
+                if (lane == 0) mbar_arrive(&W.empty[slot]);
+                {
+                    const int64_t n0 = (int64_t)blk * TB;
+#pragma unroll 1
+                    for (int v0 = 0; v0 < g_count; v0 += 4) {
+                        const int v = v0 + (lane >> 3), part = lane & 7;
+                        if (v < g_count) {
+                            const int64_t left = W.n_tube[v] - n0;
+                            R *dst = W.out_ptr[v] + n0;
+                            if (left >= TB) {
+                                reinterpret_cast<float4 *>(dst)[part] = *reinterpret_cast<const float4 *>(&W.outb[v][2 * part]);
+                            } else {
+                                for (int i = 2 * part; i < 2 * part + 2; ++i)
+                                    if (i < left) dst[i] = W.outb[v][i];
+                            }
+                        }
+                    }
+                }
+                __syncwarp(FULL);
+            }
+            if (sv) {
+#pragma unroll
+                for (int q = 0; q < 10; ++q) { sv[q] = t[q]; sv[10 + q] = bt[q]; }
+#pragma unroll
+                for (int q = 0; q < 6; ++q) { sv[20 + q] = nt[q]; sv[26 + q] = nb[q]; }
+                sv[32] = m_ry; sv[33] = m_rx; sv[34] = m_rY; sv[35] = n_ry; sv[36] = n_rx; sv[37] = n_rY;
+                sv[38] = y1; sv[39] = y2; sv[40] = thy;
+            }
+        }
+}
+
+// =========================================================================================================
+// feed-forward warp: utterances 2*pair and 2*pair+1 of the group, lane = sample of a 16-sample block
+// (phases S0 / A1 / S1 / A2 of tube_kernel.cuh; the results go to the ring instead of the ladder's tables)
+// =========================================================================================================
+template <typename R>
+__device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const WideArgs &wargs, int g_start, int g_count, int n_blocks, int pair, int lane)
+{
+    constexpr bool FAST = sizeof(R) == 4;                  // FP32 fast mode
+    constexpr bool F64C = !FAST && !STRICT;                // FP64 conformance mode (cheaper forms, see the top of the file)
+    (void)F64C;
+    const TubeArgs &args = wargs.t;
     const int half = lane >> 4, hl = lane & 15;
     const int ucol = 2 * pair + half;                     // column of this half's utterance in the ring
     FFHalf<R> &S = W.ff[ucol];
@@ -526,69 +714,172 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
         xm1 = st_v[STATE_XM]; xm2 = st_v[STATE_XM + 1];
         for (int i = hl; i < FIR_HIST; i += TB) { S.HE[i] = st_v[STATE_HE + i]; S.HO[i] = st_v[STATE_HO + i]; }
     }
+    // FP64 conformance mode: parameter lane p also carries function p of its parameter as a complex number (rc, rs) that
+    // is multiplied by (dc, ds) every sample -- geometric for the exponentials (rs = ds = 0), a rotation for the angles:
+    //   0 pitch    -> oscillator increment (220 * 2^((p+3)/12) / 2) * basicIncrement   (TRMUtility.m:44-47, TRMWavetable.m:165)
+    //   1..3 dB    -> 10^((p-60)/20), unclamped (the clamps of amplitude() are applied per sample on the exact parameter)
+    //   5 centre f -> cos(2 pi p / sr)        6 bandwidth -> cos, sin(pi p / sr)        (TRMFilters.m:9-17)
+    double rc = 0.0, rs = 0.0, dc = 0.0, ds = 0.0;
+    const bool fn_exp = hl < 4, fn_rot = (hl == 5) | (hl == 6);
+    const double fn_w = F64C ? (hl == 0 ? (1.0 / 12.0) : (hl < 4 ? 0.16609640474436813 : (hl == 5 ? 6.28318530717958647692 : 3.14159265358979323846) / D->sampleRate)) : 0.0;
+    const double fn_off = hl == 0 ? 3.0 : -60.0, fn_scale = hl == 0 ? 110.0 * D->basicIncrement : 1.0;
+    auto seed_functions = [&](double pc0, double pd0, double &c, double &sn, double &cd, double &sd) {
+        // for a control interval that starts at pc0 and moves by pd0 per sample: two exp2 or two sincos per interval
+        if (fn_exp) {
+            c = fn_scale * exp2_inline((pc0 + fn_off) * fn_w);
+            cd = exp2_inline(pd0 * fn_w);
+            sn = 0.0; sd = 0.0;
+        } else if (fn_rot) {
+            sincos_inline(pc0 * fn_w, &sn, &c);
+            sincos_inline(pd0 * fn_w, &sd, &cd);
+        }
+    };
+    auto step_functions = [&]() {
+        const double c2 = fma(-rs, ds, rc * dc);
+        rs = fma(rc, ds, rs * dc);
+        rc = c2;
+    };
     if (feeds && D->jc0 > 0 && n_frames > 1) {
         // the call starts inside a control interval: redo its jc0 interpolation adds (exactly the reference's sequence)
         const double nxt = S.FR[0][1][hl];
         p_cur = p_next;
         p_delta = (nxt - p_cur) / (double)cp;
         p_next = nxt;
-        for (int i = 0; i < D->jc0; ++i) p_cur += p_delta;
+        if constexpr (F64C) seed_functions(p_cur, p_delta, rc, rs, dc, ds);
+        for (int i = 0; i < D->jc0; ++i) {
+            p_cur += p_delta;
+            if constexpr (F64C) step_functions();
+        }
         jc = D->jc0;
     }
+    // conformance-mode staging: where this parameter lane puts its value / its function inside the ring slot.  Unit
+    // u (16 bytes) of sample t sits at ring[slot][u][(t + u) & 15][ucol]; the reader (lane = sample) takes units 0..9:
+    //   {p1,p2} {p3,p4} {r1,r2} {r3,r4} {r5,r6} {r7,r8} {velum,inc} {c1,c2} {c3,cos5} {cos6,sin6}
+    const int uA = F64C ? (hl >= 7 ? (hl - 3) >> 1 : (hl - 1) >> 1) : pf, cA = F64C ? (hl >= 7 ? (hl - 3) & 1 : (hl - 1) & 1) : pc;
+    const bool wantA = !F64C || !(hl == 0 || hl == 5 || hl == 6);
+    const int uB = hl == 0 ? 6 : (hl <= 2 ? 7 : (hl == 3 || hl == 5 ? 8 : 9)), cB = (hl == 0 || hl == 2 || hl == 5) ? 1 : 0;
+    const bool wantB = F64C && (fn_exp || fn_rot), wantC = F64C && hl == 6;
     __syncwarp(FULL);
 
+#if TRM_PROFILE_PHASES
+    __shared__ unsigned tph[12];
+    unsigned tph_t = (unsigned)clock();
+    const bool tph_on = blockIdx.x == 0 && pair == 0 && lane == 0;
+    if (tph_on) for (int i = 0; i < 12; ++i) tph[i] = 0u;
+#define TPH(i) do { if (tph_on) { const unsigned _t = (unsigned)clock(); tph[i] += _t - tph_t; tph_t = _t; } } while (0)
+    unsigned tphx_t = 0;      // sub-timers inside a phase: TPHX(0) starts, TPHX(i) adds the time since the previous TPHX to tph[i]
+#define TPHX(i) do { if (tph_on) { const unsigned _t = (unsigned)clock(); if (i) tph[i] += _t - tphx_t; tphx_t = _t; } } while (0)
+#else
+#define TPH(i) do { } while (0)
+#define TPHX(i) do { } while (0)
+#endif
     for (int blk = 0; blk < n_blocks; ++blk) {
         const int slot = blk & 1;
         const int64_t n0 = (int64_t)blk * TB;
         const int64_t left = n_tube - n0;
         const int nb = left >= TB ? TB : (left > 0 ? (int)left : 0);
         const bool active = hl < nb;
-        if (blk >= WIDE_SLOTS) mbar_wait_sleep(&W.empty[slot], (uint32_t)(((blk >> 1) - 1) & 1));
-        if (wargs.debug & 1) {
+        if (blk >= WIDE_SLOTS) mbar_wait_sleep<TRM_WAIT_NS>(&W.empty[slot], (uint32_t)(((blk >> 1) - 1) & 1));
+        if (TRM_PROFILE_SKIP & 1) {
             __syncwarp(FULL);
             if (lane == 0) mbar_arrive(&W.full[slot]);
             continue;
         }
 
+        TPH(0);
         // ---- S0: parameter interpolation, lane = parameter (m:611-688).  The 16 x 16 interpolated values are
         //      staged INSIDE this utterance's part of the ring slot (fields 0..7, sample position rotated by the
         //      field so that the stores of the 16 parameter lanes fall into different banks); phase A1 reads
         //      them back into registers before it writes any record.
         int refill = -1;
-        for (int s = 0; s < TB;) {
-            if (jc == 0 && f_idx + 1 < n_frames && feeds) {
-                const int fn = f_idx + 1;
+        constexpr int RS = (int)(Wide<R>::UP * sizeof(typename Wide<R>::Unit) / sizeof(double));   // doubles per sample row
+        const int ib = (jc == 0) ? 0 : cp - jc;             // step of this block at which the next control interval starts
+        if (ib + cp >= TB) {
+            // At most one interval starts inside the block (always, for the reference's control periods >= 17): 16 straight-line
+            // steps with constant store offsets.  The values of the new interval are prepared before the loop and swapped in
+            // at step ib -- same operations on the same values as the reference's loop (m:611-688), no data-dependent loop.
+            const int fb = f_idx + (jc == 0 ? 0 : 1);       // index of the interval that starts at step ib
+            const bool starts = ib < TB && fb + 1 < n_frames && feeds;
+            double np = p_cur, nd = p_delta, nrc = rc, nrs = rs, ndc = dc, nds = ds;
+            if (starts) {
+                TPHX(0);
+                const int fn = fb + 1;
                 const int ch = fn / FRAME_CHUNK;
                 if ((fn % FRAME_CHUNK) == 0) {
                     refill = ch + 1;
                     mbar_wait(&S.mbar[ch & 1], (uint32_t)((ch >> 1) & 1));
                 }
+                TPHX(9);
                 const double nxt = S.FR[ch & 1][fn % FRAME_CHUNK][hl];
-                p_cur = p_next;
-                p_delta = (nxt - p_cur) / (double)cp;
+                np = p_next;
+                nd = (nxt - np) / (double)cp;
                 p_next = nxt;
+                TPHX(10);
+                if constexpr (F64C) seed_functions(np, nd, nrc, nrs, ndc, nds);
+                TPHX(11);
             }
-            const int run = min(TB - s, cp - jc);
-            if (run == TB) {
-                // the whole block lies inside one control interval (4 blocks out of 5 for the male voice): straight-line
-                // stores with constant offsets, the 16 dependent adds are all that is left on the chain
-                double *const row = reinterpret_cast<double *>(&W.ring[slot][pf][0][ucol]) + pc;
-                constexpr int RS = (int)(Wide<R>::UP * sizeof(typename Wide<R>::Unit) / sizeof(double));   // doubles per sample row
-                double *const r0 = row + pf * RS;                        // row of step 0; steps TB-pf .. wrap to the start
+            double *const a0 = reinterpret_cast<double *>(&W.ring[slot][uA][uA][ucol]) + cA;   // row of step 0; steps TB-u .. wrap
+            double *const b0 = reinterpret_cast<double *>(&W.ring[slot][uB][uB][ucol]) + cB;
+            double *const c0 = reinterpret_cast<double *>(&W.ring[slot][9][9][ucol]) + 1;
+            if (!starts) {
 #pragma unroll
                 for (int i = 0; i < TB; ++i) {
-                    (i + pf < TB ? r0 : r0 - TB * RS)[i * RS] = p_cur;
+                    sts_f64_if(wantA, (i + uA < TB ? a0 : a0 - TB * RS) + i * RS, p_cur);
+                    if constexpr (F64C) {
+                        sts_f64_if(wantB, (i + uB < TB ? b0 : b0 - TB * RS) + i * RS, rc);
+                        sts_f64_if(wantC, (i + 9 < TB ? c0 : c0 - TB * RS) + i * RS, rs);
+                        step_functions();
+                    }
                     p_cur += p_delta;
                 }
             } else {
-                for (int i = 0; i < run; ++i) {
-                    reinterpret_cast<double *>(&W.ring[slot][pf][(s + i + pf) & (TB - 1)][ucol])[pc] = p_cur;
+#pragma unroll
+                for (int i = 0; i < TB; ++i) {
+                    if (i == ib) {
+                        p_cur = np; p_delta = nd;
+                        if constexpr (F64C) { rc = nrc; rs = nrs; dc = ndc; ds = nds; }
+                    }
+                    sts_f64_if(wantA, (i + uA < TB ? a0 : a0 - TB * RS) + i * RS, p_cur);
+                    if constexpr (F64C) {
+                        sts_f64_if(wantB, (i + uB < TB ? b0 : b0 - TB * RS) + i * RS, rc);
+                        sts_f64_if(wantC, (i + 9 < TB ? c0 : c0 - TB * RS) + i * RS, rs);
+                        step_functions();
+                    }
                     p_cur += p_delta;
                 }
             }
-            s += run;
-            jc += run;
-            if (jc == cp) { jc = 0; ++f_idx; }
+            jc += TB;
+            if (jc >= cp) { jc -= cp; ++f_idx; }
+        } else {
+            // control periods below 16 samples (outside the reference's range, accepted down to 8): run by run
+            for (int s = 0; s < TB;) {
+                if (jc == 0 && f_idx + 1 < n_frames && feeds) {
+                    const int fn = f_idx + 1;
+                    const int ch = fn / FRAME_CHUNK;
+                    if ((fn % FRAME_CHUNK) == 0) {
+                        refill = ch + 1;
+                        mbar_wait(&S.mbar[ch & 1], (uint32_t)((ch >> 1) & 1));
+                    }
+                    const double nxt = S.FR[ch & 1][fn % FRAME_CHUNK][hl];
+                    p_cur = p_next;
+                    p_delta = (nxt - p_cur) / (double)cp;
+                    p_next = nxt;
+                    if constexpr (F64C) seed_functions(p_cur, p_delta, rc, rs, dc, ds);
+                }
+                const int run = min(TB - s, cp - jc);
+                for (int i = 0; i < run; ++i) {
+                    sts_f64_if(wantA, reinterpret_cast<double *>(&W.ring[slot][uA][(s + i + uA) & (TB - 1)][ucol]) + cA, p_cur);
+                    if constexpr (F64C) {
+                        sts_f64_if(wantB, reinterpret_cast<double *>(&W.ring[slot][uB][(s + i + uB) & (TB - 1)][ucol]) + cB, rc);
+                        sts_f64_if(wantC, reinterpret_cast<double *>(&W.ring[slot][9][(s + i + 9) & (TB - 1)][ucol]) + 1, rs);
+                        step_functions();
+                    }
+                    p_cur += p_delta;
+                }
+                s += run;
+                jc += run;
+                if (jc == cp) { jc = 0; ++f_idx; }
+            }
         }
         __syncwarp(FULL);
         if (hl == 0 && refill >= 0 && refill < n_chunks) {
@@ -597,16 +888,22 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
             tma_bulk_g2s(&S.FR[refill & 1][0][0], F + (size_t)refill * FRAME_CHUNK * 16, (uint32_t)cnt * 128u, &S.mbar[refill & 1]);
         }
 
+        TPH(1);
         // ---- A1: lane = sample: conversions and coefficients (m:294-300, 712-773; TRMFilters.m:9-17) ---------
-        double prm[16];
+        // (conformance mode stages 10 units -- see the layout above --, the other modes the 16 parameters in 8 units)
+        constexpr int N_STAGED = F64C ? 10 : 8;
+        double prm[2 * N_STAGED];
 #pragma unroll
-        for (int f = 0; f < 8; ++f) {
+        for (int f = 0; f < N_STAGED; ++f) {
             const double2 v = *reinterpret_cast<const double2 *>(&W.ring[slot][f][(hl + f) & (TB - 1)][ucol]);
             prm[2 * f] = v.x; prm[2 * f + 1] = v.y;
         }
         __syncwarp(FULL);                                   // every staged value is in registers: records may be written
+        TPH(2);
         double inc_d;
-        {
+        if constexpr (F64C) {
+            inc_d = prm[13];
+        } else {
             const double f0 = 220.0 * exp2(div_known(prm[0] + 3.0, 12.0, 1.0 / 12.0));
             inc_d = (f0 / 2.0) * S.CST[C_BASICINC];
             if constexpr (!FAST) S.INC[hl] = inc_d;
@@ -614,7 +911,60 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
         double ax_d;
         R ax, ah1;
         R bp_alpha2;
-        if constexpr (FAST) {
+        if constexpr (F64C) {
+            // amplitude() (TRMUtility.m:26-41): clamps decided on the exact parameter, value from the geometric sequence
+            const double p1 = prm[0], p2 = prm[1], p3 = prm[2], fpos = prm[3];
+            ax_d = (p1 <= 0.0) ? 0.0 : ((p1 >= 60.0) ? 1.0 : prm[14]);
+            {
+                // glottal closure point rint(ax * tnDelta) (TRMWavetable.m:122): when the product is within 1e-6 of a
+                // rounding boundary, decide with the amplitude computed directly from the parameter
+                const double tq = ax_d * S.CST[C_TNDELTA];
+                if (fabs(fabs(tq - rint(tq)) - 0.5) < 1e-6 && p1 > 0.0 && p1 < 60.0)
+                    ax_d = exp2_inline((p1 - 60.0) * 0.16609640474436813);
+            }
+            ax = ax_d;
+            ah1 = (p2 <= 0.0) ? 0.0 : ((p2 >= 60.0) ? 1.0 : prm[15]);
+            const double fa = (p3 <= 0.0) ? 0.0 : ((p3 >= 60.0) ? 1.0 : prm[16]);
+            const double dd = S.CST[C_DAMP];
+            double r2[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { const double r = prm[4 + q]; r2[q] = r * r; }
+            // k d of the two-port junctions (m:716-741), reciprocals by Newton refinement
+            auto kd = [&](double a2, double b2) { return ((a2 - b2) * dd) * rcp_fast(a2 + b2); };
+            const double kd0 = kd(r2[0], r2[1]), kd1 = kd(r2[1], r2[2]), kd2 = kd(r2[2], r2[3]), kd4 = kd(r2[3], r2[4]);
+            const double kd6 = kd(r2[4], r2[5]), kd7 = kd(r2[5], r2[6]), kd8 = kd(r2[6], r2[7]);
+            const double ap2 = S.CST[C_APSCALE2];
+            const double k9 = (r2[7] - ap2) * rcp_fast(r2[7] + ap2);
+            const double vel = prm[12];
+            const double v2 = vel * vel;
+            const double sum = (2.0 * dd) * rcp_fast((r2[3] + r2[3]) + v2);
+            const double aLd = sum * r2[3], aUd = sum * v2;
+            const double kd10 = kd(v2, S.CST[C_NR1SQ]);
+            double tap[8];
+            {
+                const int ipos = (int)fpos;
+                const double comp = fpos - (double)ipos;
+                const double t0 = (1.0 - comp) * fa, t1 = comp * fa;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) tap[q] = (q == ipos) ? t0 : ((ipos >= 0 && q == ipos + 1) ? t1 : 0.0);
+            }
+            // band-pass (TRMFilters.m:9-17): beta = (1 - tan u) / (2 (1 + tan u)) = (cos u - sin u) / (2 (cos u + sin u))
+            const double cu = prm[18], su = prm[19], cosv = prm[17];
+            const double beta2 = (cu - su) * rcp_fast(cu + su);
+            const double gamma2 = (1.0 + beta2) * cosv;
+            bp_alpha2 = 0.5 - 0.5 * beta2;
+            W.ring[slot][0][hl][ucol] = make_double2(kd0, kd1);
+            W.ring[slot][1][hl][ucol] = make_double2(kd2, aLd);
+            W.ring[slot][2][hl][ucol] = make_double2(kd4, kd6);
+            W.ring[slot][3][hl][ucol] = make_double2(kd7, kd8);
+            W.ring[slot][4][hl][ucol] = make_double2(k9, kd10);
+            W.ring[slot][5][hl][ucol] = make_double2(aUd, tap[0]);
+            W.ring[slot][6][hl][ucol] = make_double2(tap[1], tap[2]);
+            W.ring[slot][7][hl][ucol] = make_double2(tap[3], tap[4]);
+            W.ring[slot][8][hl][ucol] = make_double2(tap[5], tap[6]);
+            W.ring[slot][9][hl][ucol] = make_double2(tap[7], gamma2);
+            reinterpret_cast<double *>(&W.ring[slot][10][hl][ucol])[0] = beta2;
+        } else if constexpr (FAST) {
             const float axf = amplitude_f((float)prm[1]);
             ax_d = (double)axf;
             {
@@ -729,6 +1079,7 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
             W.ring[slot][9][hl][ucol] = make_double2(tap[7], gamma2);
             reinterpret_cast<double *>(&W.ring[slot][10][hl][ucol])[0] = beta2;
         }
+        TPH(3);
         // noise (TRMUtility.m:71-85 as the MCG mod 2^44) + one-zero low-pass (TRMFilters.m:81-86)
         R lp_noise;
         {
@@ -741,9 +1092,14 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
             kb = (kb * pwB) & MASK44;
         }
 
+        TPH(4);
         // ---- S1: oscillator position (TRMWavetable.m:165-168, 28-34) -------------------------------------------
         double p0, p1;
-        if constexpr (FAST) {
+        if constexpr (FAST || F64C) {
+            // 64-bit fixed point, 2^55 units per table entry: 512 entries are exactly 2^64, so the table wrap is the
+            // integer overflow, addition is associative and the 32 positions of a block come from a 4-step warp scan
+            // instead of a 32-step dependent chain.  (Resolution 2.8e-17 entries; the reference's own double
+            // accumulator rounds to 5.7e-14.)  mod0 quirk: values in (511, 512) are reported as negative.
             const unsigned long long inc_fx = __double2ull_rn(inc_d * 36028797018963968.0);
             unsigned long long incl = inc_fx + inc_fx;
 #pragma unroll
@@ -771,6 +1127,7 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
             }
         }
 
+        TPH(5);
         // ---- A2: table look-ups, FIR, source mixing (TRMWavetable.m:174-195, m:305-337) --------------------------
         {
             if (!active) { p0 = 0.0; p1 = 0.0; }
@@ -791,7 +1148,7 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
                 S.HE[FIR_HIST + hl] = w00 + ((float)(p0 - (double)lo0) * (w01 - w00));
                 S.HO[FIR_HIST + hl] = w10 + ((float)(p1 - (double)lo1) * (w11 - w10));
             } else {
-                const R scale = (R)(1.0 / (Ld * Ld));
+                const R scale = F64C ? (R)rcp_fast(Ld * Ld) : (R)(1.0 / (Ld * Ld));
                 R w0 = table_value<R>(wt_base, lo0, div1, div2, newDiv2, scale, pulse_wave);
                 R w1 = table_value<R>(wt_base, hi0, div1, div2, newDiv2, scale, pulse_wave);
                 S.HE[FIR_HIST + hl] = w0 + ((R)(p0 - (double)lo0) * (w1 - w0));
@@ -801,12 +1158,13 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
             }
         }
         __syncwarp(FULL);
+        TPH(6);
         R sig;
         {
             const R *ho = &S.HO[FIR_HIST + hl], *he = &S.HE[FIR_HIST + hl];
             R pulse0;
-            if constexpr (FAST) {
-                float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+            if constexpr (FAST || F64C) {
+                R s0 = (R)0, s1 = (R)0, s2 = (R)0, s3 = (R)0;
 #pragma unroll
                 for (int q = 0; q < FIR_HIST; q += 2) {
                     s0 += ho[-q] * FirCoef<R>::at(2 * q);
@@ -855,6 +1213,7 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
             }
         }
         __syncwarp(FULL);
+        TPH(7);
         if (lane == 0) mbar_arrive(&W.full[slot]);
         {
             // slide the oscillator history down by one block (rows TB.. -> 0..)
@@ -866,7 +1225,15 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
             if (hl < FIR_HIST - TB) { S.HE[TB + hl] = e1; S.HO[TB + hl] = o1; }
         }
         __syncwarp(FULL);
+        TPH(8);
     }
+#if TRM_PROFILE_PHASES
+    if (tph_on)
+        printf("[phases %s] cycles/block: wait %u S0 %u (of which per block: frame wait %u, delta %u, seeds %u) stage-read %u A1 %u noise %u S1 %u A2-table %u FIR+mix %u tail %u  (blocks %d)\n",
+               FAST ? "f32" : (STRICT ? "f64s" : "f64"), tph[0] / n_blocks, tph[1] / n_blocks, tph[9] / n_blocks, tph[10] / n_blocks, tph[11] / n_blocks,
+               tph[2] / n_blocks, tph[3] / n_blocks, tph[4] / n_blocks,
+               tph[5] / n_blocks, tph[6] / n_blocks, tph[7] / n_blocks, tph[8] / n_blocks, n_blocks);
+#endif
     if (st_h) {
         // streaming calls cover whole 16-sample blocks, so everything here is the state after the last sample
         if (hl == 0) {
@@ -880,4 +1247,66 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
     }
 }
 
-}  // namespace trm
+template <typename R>
+__global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs wargs)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WideSmem<R> &W = *reinterpret_cast<WideSmem<R> *>(smem_raw);
+    const TubeArgs &args = wargs.t;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int g_start, g_count;
+    wide_group(args.n_utt, wargs.n_groups, blockIdx.x, g_start, g_count);
+    const int n_pairs = (g_count + 1) >> 1;
+
+    // ---- CTA init: zero the ring and histories, barriers, per-utterance pointers ---------------------------
+    {
+        uint32_t *w = reinterpret_cast<uint32_t *>(&W.ring[0][0][0][0]);
+        constexpr int NW = (int)(sizeof(W.ring) / 4);
+        for (int i = threadIdx.x; i < NW; i += blockDim.x) w[i] = 0u;
+        for (int h = warp; h < 2 * Wide<R>::MAX_PAIRS; h += blockDim.x >> 5) {
+            for (int i = lane; i < FIR_HIST + TB; i += 32) { W.ff[h].HE[i] = (R)0; W.ff[h].HO[i] = (R)0; }
+            if (lane < TB) W.ff[h].INC[lane] = 0.0;
+        }
+        if (threadIdx.x == 0) {
+            W.n_cta = 0;
+            for (int s = 0; s < WIDE_SLOTS; ++s) { mbar_init(&W.full[s], (uint32_t)n_pairs); mbar_init(&W.empty[s], 1); }
+            mbar_fence_init();
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const bool has = lane < g_count;
+        const int u = args.order ? args.order[g_start + (has ? lane : 0)] : g_start + (has ? lane : 0);
+        const trm_cuda_utterance *D = args.desc + u;
+        W.n_tube[lane] = has ? D->n_tube : 0;
+        W.out_ptr[lane] = reinterpret_cast<R *>(args.tube) + D->tube_offset;
+        if (has) atomicMax((unsigned long long *)&W.n_cta, (unsigned long long)D->n_tube);
+    }
+    __syncthreads();
+    const int64_t n_cta = W.n_cta;
+    const int pair = warp - 1 - (warp > WIDE_IDLE_WARP ? 1 : 0);
+    const int n_blocks = (int)((n_cta + TB - 1) / TB);
+    // Register redistribution (setmaxnreg, warpgroup granularity; see Wide<double>).  Every warp of a warpgroup executes
+    // the instruction, before any of them exits; the donors release before the recurrence warpgroup's request can be met.
+    if constexpr (Wide<R>::REGS_HI > 0) {
+        if (warp >= 16) {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Wide<R>::REGS_DONOR));
+            return;
+        }
+        if (warp < 4) {
+            asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Wide<R>::REGS_HI));
+            if (n_cta <= 0 || pair >= n_pairs) return;
+            if (warp == 0) wide_recurrence_warp<R>(W, wargs, g_start, g_count, n_blocks, lane);
+            else wide_feed_forward_warp<R>(W, wargs, g_start, g_count, n_blocks, pair, lane);
+        } else {
+            if (n_cta <= 0 || warp == WIDE_IDLE_WARP || pair >= n_pairs) return;
+            wide_feed_forward_warp<R>(W, wargs, g_start, g_count, n_blocks, pair, lane);
+        }
+    } else {
+        if (n_cta <= 0 || warp == WIDE_IDLE_WARP || pair >= n_pairs) return;
+        if (warp == 0) wide_recurrence_warp<R>(W, wargs, g_start, g_count, n_blocks, lane);
+        else wide_feed_forward_warp<R>(W, wargs, g_start, g_count, n_blocks, pair, lane);
+    }
+}
+
+}  // namespace TRM_KERNEL_NS

@@ -52,8 +52,10 @@ enum {
 
 /* Arithmetic mode of the GPU path (BASELINE.json north_star). */
 enum {
-    TRM_PRECISION_FP64 = 0,   /* conformance: every value double, no FMA contraction                   */
-    TRM_PRECISION_FP32 = 1    /* fast: FP32 state/signal, FP64 pitch->f0->phase, integer noise         */
+    TRM_PRECISION_FP64 = 0,        /* conformance: every value double, within 1e-9 relative of the reference      */
+    TRM_PRECISION_FP32 = 1,        /* fast: FP32 state/signal, FP64 pitch->f0->phase, integer noise; >= 80 dB SNR  */
+    TRM_PRECISION_FP64_STRICT = 2  /* the reference's operations in the reference's order, no FMA contraction: the
+                                      bit-faithful twin the conformance mode is checked against (about 2x slower)  */
 };
 
 /* TRMInputParameters.h:26-54.  Field order follows the reference declaration. */

@@ -15,7 +15,7 @@ def line_map(tag, kernel):
     d = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "gnuspeech_b200", "lib", "libtrm_cuda.so")], cwd=d,
                    stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-    cub = [f for f in os.listdir(d) if f.startswith(tag) and f.endswith(".cubin")][0]
+    cub = [f for f in os.listdir(d) if f.startswith(tag + ".") and f.endswith(".cubin")][0]
     txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(d, cub)], stdout=subprocess.PIPE, text=True).stdout
     m, cur, on = {}, ("?", 0), False
     for ln in txt.splitlines():
