@@ -1107,9 +1107,44 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
                 const unsigned long long up = __shfl_up_sync(FULL, incl, o, 16);
                 if (hl >= o) incl += up;
             }
-            const unsigned long long ub = pos_fx + incl, ua = ub - inc_fx;
-            pos_fx += __shfl_sync(FULL, incl, (lane & 16) | (TB - 1));
+            unsigned long long ub = pos_fx + incl, ua = ub - inc_fx;
             const unsigned long long top = 511ull << 55;
+            if constexpr (F64C) {
+                // The reference accumulates the position in double: every addition rounds to the grid of the sum's binade
+                // (2^-44 table entries for sums in [256, 512), 2^-43 just before a wrap, ...).  For a varying increment
+                // these roundings average out (measured 8e-13 of peak after 30 s); for a CONSTANT one they are the same
+                // every period and the reference drifts away from the exact phase by 5.6e-11 of peak per second -- past
+                // the 1e-9 contract after 18 s of a static vowel.  So whenever a block's increment is constant, the scan
+                // is repeated with every half-step's increment rounded as the reference's addition rounds it (binades
+                // from the first pass; exact ties, which the reference resolves to even, keep the exact increment).
+                const unsigned half_mask = (lane & 16) ? 0xFFFF0000u : 0x0000FFFFu;
+                const bool same = inc_fx == __shfl_sync(FULL, inc_fx, lane & 16);
+                const unsigned vote = __ballot_sync(FULL, same);
+                const bool constant = (vote & half_mask) == half_mask;
+                if (__any_sync(FULL, constant)) {
+                    auto rounded = [&](unsigned long long before, unsigned long long after) {
+                        // grid of the (unwrapped) sum: after a wrap the sum was in [512, 1024); values in (511, 512) are
+                        // kept as negative numbers by mod0 (TRMWavetable.m:28-34)
+                        const bool wrapped = after < before;
+                        const unsigned long long mag = (after > top) ? (0ull - after) : after;
+                        int sh = wrapped ? 12 : 11 - __clzll((long long)mag);
+                        if (mag == 0ull || sh <= 0) return inc_fx;
+                        const unsigned long long low = inc_fx & ((1ull << sh) - 1ull), halfg = 1ull << (sh - 1);
+                        if (low == halfg) return inc_fx;
+                        return (inc_fx - low) + (low > halfg ? (1ull << sh) : 0ull);
+                    };
+                    const unsigned long long prev = ua - inc_fx;           // position before this lane's first half-step
+                    const unsigned long long ra = rounded(prev, ua), rb = rounded(ua, ub);
+                    unsigned long long incl2 = ra + rb;
+#pragma unroll
+                    for (int o = 1; o < TB; o <<= 1) {
+                        const unsigned long long up = __shfl_up_sync(FULL, incl2, o, 16);
+                        if (hl >= o) incl2 += up;
+                    }
+                    if (constant) { ub = pos_fx + incl2; ua = ub - rb; incl = incl2; }
+                }
+            }
+            pos_fx += __shfl_sync(FULL, incl, (lane & 16) | (TB - 1));
             p0 = (ua > top) ? -((double)(0ull - ua) * 2.77555756156289135e-17) : (double)ua * 2.77555756156289135e-17;
             p1 = (ub > top) ? -((double)(0ull - ub) * 2.77555756156289135e-17) : (double)ub * 2.77555756156289135e-17;
         } else {
