@@ -98,6 +98,10 @@ def lib():
     sig("TRMTubeModelSetDevice", C.c_int, vp, C.c_int)
     sig("TRMTubeModelSynthesize", C.c_int, vp)
     sig("TRMTubeModelNumberSamples", i32, vp)
+    sig("TRMTubeModelChannels", i32, vp)
+    sig("TRMTubeModelHitsReferenceFlushBug", C.c_int, vp)
+    sig("TRMReferenceFlushBug", C.c_int, P(TRMInputParametersStruct), sz)
+    sig("TRMBatchReferenceFlushBugFlags", vp, vp)
     sig("TRMTubeModelMaximumSampleValue", dbl, vp)
     sig("TRMTubeModelResampledData", vp, vp)
     sig("TRMTubeModelTubeSignal", vp, vp, P(i64))

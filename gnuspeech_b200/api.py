@@ -242,8 +242,20 @@ class TRMTubeModel(object):
             return np.zeros(0)
         return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), (cnt.value,)).copy()
 
-    def pcm16(self, file_variant=False, channels=1):
+    @property
+    def channels(self):
+        return int(N.lib().TRMTubeModelChannels(self._h))
+
+    @property
+    def hitsReferenceFlushBug(self):
+        return bool(N.lib().TRMTubeModelHitsReferenceFlushBug(self._h))
+
+    def pcm16(self, file_variant=False, channels=None):
+        """Interleaved PCM16; the buffer is sized from the MODEL's channel count (the C call writes n * channels)."""
         n = self.numberSamples
+        if channels is not None and channels != self.channels:
+            raise ValueError("this model has %d channel(s)" % self.channels)
+        channels = self.channels
         out = np.zeros(max(n, 1) * channels, dtype=np.int16)
         got = N.lib().TRMTubeModelPullPCM16(self._h, out.ctypes.data_as(C.c_void_p), n, int(bool(file_variant)))
         if got < 0:
@@ -415,6 +427,11 @@ class TRMBatch(object):
     @property
     def maximumSampleValues(self):
         return self._arr("TRMBatchMaximumSampleValues", C.c_double, np.float64)
+
+    @property
+    def referenceFlushBugFlags(self):
+        """Per utterance: the reference's streaming converter would append spurious samples here (include/trm.h)."""
+        return self._arr("TRMBatchReferenceFlushBugFlags", C.c_uint8, np.uint8).astype(bool)
 
     @property
     def kernelLaunches(self):

@@ -55,9 +55,11 @@ __global__ void __launch_bounds__(128) framegen_kernel(FrameGenArgs a)
     if (lane < 16) {
         long long j = 1;
         double temp;
-        while (isnan(temp = ev[j].value[lane])) j++;
+        // (bounded: the reference walks past the end of the array when a track has no later value; libtrm refuses such
+        //  lists -- check_event_lists -- and the kernel never reads outside this utterance's events)
+        while (isnan(temp = ev[j].value[lane]) && j < count - 1) j++;
         cv = ev[0].value[lane];
-        cd = ((temp - cv) / (double)ev[j].time) * ms;
+        cd = isnan(temp) ? 0.0 : ((temp - cv) / (double)ev[j].time) * ms;
     }
     // tracks 32..35 (m:932-961)
     double cv32 = 0.0, cd32 = 0.0, cd33 = 0.0, cd34 = 0.0, cd35 = 0.0;

@@ -157,6 +157,7 @@ struct DeviceChunk {
     trm_cuda_utterance *desc_t[2] = {nullptr, nullptr};
     void *state = nullptr;
     size_t tube_elems = 0, out_elems = 0, pcm_elems = 0, frame_rows = 0;
+    const double *wavetables = nullptr;     // own copy of the glottal tables (device-resident batches); null = the context's
 };
 
 // Host-side plan of one chunk: rebased descriptors + where its spans live in the caller's arrays.
@@ -256,6 +257,7 @@ struct trm_cuda_resident {
     ChunkPlan plan;
     Arena arena;
     DeviceChunk dc;
+    double *d_wavetables = nullptr;     // the batch's glottal tables: the context's set may be replaced by later calls
 };
 
 namespace {
@@ -540,7 +542,7 @@ int launch_stage(trm_cuda_ctx *ctx, int precision, int stage, const DeviceChunk 
     if (stage == TRM_STAGE_TUBE) {
         trm::TubeArgs a{};
         a.desc = dc.desc; a.order = dc.order; a.n_utt = dc.n; a.frames = dc.frames; a.tube = dc.tube;
-        a.wavetables = ctx->d_wavetables; a.noise_k0 = ctx->noise_k0;
+        a.wavetables = dc.wavetables ? dc.wavetables : ctx->d_wavetables; a.noise_k0 = ctx->noise_k0;
         if (time_part >= 0) { a.desc = dc.desc_t[time_part]; a.state = dc.state; }     // (lane-per-utterance mapping only)
         const trm::KernelInfo &ki = ctx->ki(precision);
         const int groups = wide_groups(ctx, ki, dc.n);
@@ -581,13 +583,17 @@ int chunk_utterances(const trm_cuda_ctx *ctx, int precision, int n, const trm_cu
     // PCM of one chunk leaves for the host while the next one is computed.  Bounded by scratch memory.
     const char *env = getenv("TRM_CHUNK_UTTERANCES");
     if (env && atoi(env) > 0) return atoi(env);
-    size_t per_utt = 0;
-    const int probe = std::min(n, 64);
-    for (int i = 0; i < probe; ++i)
-        per_utt += (size_t)desc[i].n_frames * 128 + ((size_t)desc[i].n_tube + (size_t)desc[i].n_out) * esz +
-                   (size_t)desc[i].n_out * 2 * desc[i].channels;
-    per_utt = per_utt / std::max(probe, 1) + 1;
-    const size_t budget = (size_t)32 << 30;                     // per in-flight chunk (three lanes per device)
+    // scratch of a chunk = frames + tube-rate + output-rate samples + PCM of its utterances; the bound uses the LARGEST
+    // utterance of the batch (ragged batches: an average over a prefix would let one chunk of long utterances overshoot)
+    // and what the device can actually give three in-flight chunks per context lane
+    size_t per_utt = 1;
+    for (int i = 0; i < n; ++i)
+        per_utt = std::max(per_utt, (size_t)desc[i].n_frames * 128 + ((size_t)desc[i].n_tube + (size_t)desc[i].n_out) * esz +
+                                        (size_t)desc[i].n_out * 2 * desc[i].channels + 1024);
+    size_t free_b = 0, total_b = 0, reserved = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { free_b = (size_t)96 << 30; cudaGetLastError(); }
+    for (int i = 0; i < MAX_SLOTS; ++i) reserved += ctx->arenas[i].cap;          // already ours: reused, not needed again
+    const size_t budget = std::min<size_t>((size_t)32 << 30, (size_t)(0.85 * (double)(free_b + reserved)) / 3);
     const long long by_mem = std::max<long long>(1, (long long)(budget / per_utt));
     const trm::KernelInfo &ki = ctx->ki(precision);
     const long long lo = (long long)ctx->sm_count * (ki.wide_max_utt / 2), hi = (long long)ctx->sm_count * ki.wide_max_utt;
@@ -852,56 +858,72 @@ int trm_cuda_synthesize_host_ex(trm_cuda_ctx *ctx, int precision, int n, const t
         return 0;
     };
 
+    // An error inside the chunk loop must not return while earlier chunks' copies are still landing in the caller's buffers
+    // (the caller may free them as soon as the call fails): drain this call's queues first.
+    auto drain = [&]() {
+        cudaStreamSynchronize(s_in);
+        cudaStreamSynchronize(s_run);
+        cudaStreamSynchronize(s_out);
+    };
+#define CKD(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) { drain(); return fail(#call, _e); }                                \
+    } while (0)
+#define RCD(expr)                                                                                  \
+    do {                                                                                           \
+        if ((rc = (expr)) != 0) { drain(); return rc; }                                            \
+    } while (0)
     for (int ci = 0; ci < n_chunks; ++ci) {
         const int slot = ci % N_SLOTS;
         int rc;
-        if (slot_chunk[slot] >= 0 && (rc = finish_slot(slot)) != 0) return rc;
+        if (slot_chunk[slot] >= 0) RCD(finish_slot(slot));
         ChunkPlan &p = plans[slot];
         const int u0 = ci * per_chunk, u1 = std::min(n, u0 + per_chunk);
         // large chunks with PCM output are resampled and scaled in up to MAX_OUT_GROUPS output groups
         long long chunk_out = 0;
         for (int u = u0; u < u1; ++u) chunk_out += desc[u].n_out;
         const int want_groups = (want_pcm && !getenv("TRM_NO_OUT_GROUPS")) ? (int)std::min<long long>(MAX_OUT_GROUPS, chunk_out / (64ll << 20)) : 1;
-        if ((rc = plan_chunk(desc, u0, u1, ctx->ki(precision), p, want_groups)) != 0) return rc;
+        RCD(plan_chunk(desc, u0, u1, ctx->ki(precision), p, want_groups));
         const bool grouped = p.groups.size() > 1;
         // long uniform chunks: the waveguide as two launches in time, the later frames uploaded behind the first
         if (p.uniform_frames >= 512 && !getenv("TRM_NO_TIME_SPLIT") &&
             wide_groups(ctx, ctx->ki(precision), u1 - u0) > 0)
             arm_time_split(p, std::max(64, (int)(0.28 * p.uniform_frames)));
         const bool split = p.split_frame > 0;
-        if ((rc = ctx->arenas[slot].reserve(p.arena_bytes(esz, want_pcm))) != 0) return rc;
-        if ((rc = ctx->stages[slot].reserve(p.stage_bytes())) != 0) return rc;
+        RCD(ctx->arenas[slot].reserve(p.arena_bytes(esz, want_pcm)));
+        RCD(ctx->stages[slot].reserve(p.stage_bytes()));
         DeviceChunk dc;
         carve(ctx->arenas[slot], p, esz, want_pcm, dc);
         // ---- copy-in -----------------------------------------------------------------------------------------
         {
             std::lock_guard<std::mutex> lk(g_in_mu[ctx->device]);
             mark(s_in);
-            if ((rc = upload_plan(p, dc, ctx->stages[slot].base, s_in, esz, ctx->noise_k0)) != 0) return rc;
+            RCD(upload_plan(p, dc, ctx->stages[slot].base, s_in, esz, ctx->noise_k0));
             if (!split) {
-                if ((rc = upload_frames(p, dc, desc, frames_host, s_in)) != 0) return rc;
-                CK(cudaEventRecord(ctx->ev_in[slot], s_in));
+                RCD(upload_frames(p, dc, desc, frames_host, s_in));
+                CKD(cudaEventRecord(ctx->ev_in[slot], s_in));
             } else {
                 // frames [0, f1] of every utterance, then the rest: two strided copies
                 const size_t pitch = (size_t)p.uniform_frames * 128, first = (size_t)(p.split_frame + 1) * 128;
                 const unsigned char *src = (const unsigned char *)(frames_host + (size_t)p.frames_lo * 16);
-                CK(cudaMemcpy2DAsync(dc.frames, pitch, src, pitch, first, (size_t)(u1 - u0), cudaMemcpyDefault, s_in));
-                CK(cudaEventRecord(ctx->ev_in[slot], s_in));
-                CK(cudaMemcpy2DAsync((unsigned char *)dc.frames + first, pitch, src + first, pitch, pitch - first, (size_t)(u1 - u0),
+                CKD(cudaMemcpy2DAsync(dc.frames, pitch, src, pitch, first, (size_t)(u1 - u0), cudaMemcpyDefault, s_in));
+                CKD(cudaEventRecord(ctx->ev_in[slot], s_in));
+                CKD(cudaMemcpy2DAsync((unsigned char *)dc.frames + first, pitch, src + first, pitch, pitch - first, (size_t)(u1 - u0),
                                      cudaMemcpyDefault, s_in));
-                CK(cudaEventRecord(ctx->ev_in2[slot], s_in));
+                CKD(cudaEventRecord(ctx->ev_in2[slot], s_in));
             }
             mark(s_in);
         }
         // ---- kernels -----------------------------------------------------------------------------------------
         {
             std::lock_guard<std::mutex> lk(g_run_mu[ctx->device]);
-            CK(cudaStreamWaitEvent(s_run, ctx->ev_in[slot], 0));
+            CKD(cudaStreamWaitEvent(s_run, ctx->ev_in[slot], 0));
             auto waveguide = [&]() -> int {
                 if (!split) { ++n_launch; return launch_stage(ctx, precision, TRM_STAGE_TUBE, dc, s_run); }
                 int r = launch_stage(ctx, precision, TRM_STAGE_TUBE, dc, s_run, nullptr, 0);
                 if (r != 0) return r;
-                CK(cudaStreamWaitEvent(s_run, ctx->ev_in2[slot], 0));
+                CKD(cudaStreamWaitEvent(s_run, ctx->ev_in2[slot], 0));
                 n_launch += 2;
                 return launch_stage(ctx, precision, TRM_STAGE_TUBE, dc, s_run, nullptr, 1);
             };
@@ -910,56 +932,56 @@ int trm_cuda_synthesize_host_ex(trm_cuda_ctx *ctx, int precision, int n, const t
                     if (st == TRM_STAGE_PCM && !want_pcm) { mark(s_run); continue; }
                     if (st == TRM_STAGE_TUBE) rc = waveguide();
                     else { rc = launch_stage(ctx, precision, st, dc, s_run); ++n_launch; }
-                    if (rc != 0) return rc;
+                    if (rc != 0) { drain(); return rc; }
                     mark(s_run);
                 }
             } else {
                 // the waveguide over the whole chunk (it needs all of it to fill the device), then resampling + scaling
                 // group by group: group g's PCM crosses PCIe while group g+1 is resampled
-                if ((rc = waveguide()) != 0) return rc;
+                RCD(waveguide());
                 mark(s_run);
                 for (size_t g = 0; g < p.groups.size(); ++g) {
-                    if ((rc = launch_stage(ctx, precision, TRM_STAGE_SRC, dc, s_run, &p.groups[g])) != 0) return rc;
+                    RCD(launch_stage(ctx, precision, TRM_STAGE_SRC, dc, s_run, &p.groups[g]));
                     if (g + 1 == p.groups.size()) mark(s_run);
-                    if ((rc = launch_stage(ctx, precision, TRM_STAGE_PCM, dc, s_run, &p.groups[g])) != 0) return rc;
-                    CK(cudaEventRecord(ctx->ev_grp[slot][g], s_run));
+                    RCD(launch_stage(ctx, precision, TRM_STAGE_PCM, dc, s_run, &p.groups[g]));
+                    CKD(cudaEventRecord(ctx->ev_grp[slot][g], s_run));
                     n_launch += 2;
                 }
                 mark(s_run);
             }
-            CK(cudaEventRecord(ctx->ev_run[slot], s_run));
+            CKD(cudaEventRecord(ctx->ev_run[slot], s_run));
         }
         // ---- copy-out ----------------------------------------------------------------------------------------
         if (grouped) {
             for (size_t g = 0; g < p.groups.size(); ++g) {
                 const ChunkPlan::Group &grp = p.groups[g];
-                CK(cudaStreamWaitEvent(s_out, ctx->ev_grp[slot][g], 0));
+                CKD(cudaStreamWaitEvent(s_out, ctx->ev_grp[slot][g], 0));
                 if (grp.pcm_hi > grp.pcm_lo)
-                    CK(cudaMemcpyAsync(pcm_host + p.pcm_lo + grp.pcm_lo, dc.pcm + grp.pcm_lo, (size_t)(grp.pcm_hi - grp.pcm_lo) * sizeof(int16_t),
+                    CKD(cudaMemcpyAsync(pcm_host + p.pcm_lo + grp.pcm_lo, dc.pcm + grp.pcm_lo, (size_t)(grp.pcm_hi - grp.pcm_lo) * sizeof(int16_t),
                                        cudaMemcpyDeviceToHost, s_out));
             }
         }
-        CK(cudaStreamWaitEvent(s_out, ctx->ev_run[slot], 0));
+        CKD(cudaStreamWaitEvent(s_out, ctx->ev_run[slot], 0));
         if (!grouped && want_pcm && p.pcm_elems) {
             long long c_hi = 0;
             for (const auto &d : p.desc) c_hi = std::max<long long>(c_hi, d.pcm_offset + d.n_out * d.channels);
-            CK(cudaMemcpyAsync(pcm_host + p.pcm_lo, dc.pcm, (size_t)c_hi * sizeof(int16_t), cudaMemcpyDeviceToHost, s_out));
+            CKD(cudaMemcpyAsync(pcm_host + p.pcm_lo, dc.pcm, (size_t)c_hi * sizeof(int16_t), cudaMemcpyDeviceToHost, s_out));
         }
         if (samples_host && p.out_elems) {
             long long o_hi = 0;
             for (const auto &d : p.desc) o_hi = std::max<long long>(o_hi, d.out_offset + d.n_out);
-            CK(cudaMemcpyAsync((unsigned char *)samples_host + (size_t)p.out_lo * esz, dc.out, (size_t)o_hi * esz, cudaMemcpyDeviceToHost, s_out));
+            CKD(cudaMemcpyAsync((unsigned char *)samples_host + (size_t)p.out_lo * esz, dc.out, (size_t)o_hi * esz, cudaMemcpyDeviceToHost, s_out));
         }
         if (tube_host && p.tube_elems) {
             long long t_hi = 0;
             for (const auto &d : p.desc) t_hi = std::max<long long>(t_hi, d.tube_offset + d.n_tube);
-            CK(cudaMemcpyAsync((unsigned char *)tube_host + (size_t)p.tube_lo * esz, dc.tube, (size_t)t_hi * esz, cudaMemcpyDeviceToHost, s_out));
+            CKD(cudaMemcpyAsync((unsigned char *)tube_host + (size_t)p.tube_lo * esz, dc.tube, (size_t)t_hi * esz, cudaMemcpyDeviceToHost, s_out));
         }
         if (max_host) {
             unsigned char *mb = ctx->stages[slot].base + p.stage_bytes() - align_up(p.desc.size() * sizeof(unsigned long long), 256);
-            CK(cudaMemcpyAsync(mb, dc.maxbits, p.desc.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s_out));
+            CKD(cudaMemcpyAsync(mb, dc.maxbits, p.desc.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s_out));
         }
-        CK(cudaEventRecord(ctx->ev_out[slot], s_out));
+        CKD(cudaEventRecord(ctx->ev_out[slot], s_out));
         mark(s_out);
         slot_chunk[slot] = ci;
         if (ci == 0 && enqueued) enqueued(enqueued_arg);
@@ -982,6 +1004,8 @@ int trm_cuda_synthesize_host_ex(trm_cuda_ctx *ctx, int precision, int n, const t
     }
     if (launches) *launches = n_launch;
     return 0;
+#undef CKD
+#undef RCD
 }
 
 int trm_cuda_generate_frames(trm_cuda_ctx *ctx, int n, const trm_cuda_utterance *desc, const trm_cuda_event *events,
@@ -1051,6 +1075,7 @@ struct trm_cuda_stream {
     int cur = 0;
     unsigned char *d_out = nullptr, *d_state = nullptr;
     double *d_frames = nullptr;
+    double *d_wavetables = nullptr;    // own copy: the stream does not hold a context lane between pushes
     Arena scratch;                 // descriptors + resampler plan of a push
     HostStage stage;
     cudaStream_t st = nullptr;
@@ -1085,6 +1110,10 @@ int trm_cuda_stream_create(trm_cuda_ctx *ctx, int precision, int n_streams, cons
     if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_state, (size_t)n_streams * st_bytes);
     if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_frames, (size_t)n_streams * (max_frames_per_push + 3) * 128);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
+    if (e == cudaSuccess && !ctx->wt_host.empty()) {
+        e = cudaMalloc((void **)&s->d_wavetables, ctx->wt_host.size() * sizeof(double));
+        if (e == cudaSuccess) e = cudaMemcpy(s->d_wavetables, ctx->wt_host.data(), ctx->wt_host.size() * sizeof(double), cudaMemcpyHostToDevice);
+    }
     if (e == cudaSuccess) {
         // fresh state: everything zero, "no sample yet" flag set, noise generator at its start
         std::vector<unsigned char> init((size_t)n_streams * st_bytes, 0);
@@ -1111,6 +1140,7 @@ void trm_cuda_stream_destroy(trm_cuda_stream *s)
     if (s->d_out) cudaFree(s->d_out);
     if (s->d_state) cudaFree(s->d_state);
     if (s->d_frames) cudaFree(s->d_frames);
+    if (s->d_wavetables) cudaFree(s->d_wavetables);
     s->scratch.release();
     s->stage.release();
     delete s;
@@ -1223,7 +1253,7 @@ int trm_cuda_stream_push(trm_cuda_stream *s, const double *frames_host, int m, i
     if (n_new > 0) {
         trm::TubeArgs a{};
         a.state = s->d_state; a.desc = d_dt; a.order = nullptr; a.n_utt = n; a.frames = s->d_frames; a.tube = s->d_tube[s->cur];
-        a.wavetables = ctx->d_wavetables; a.noise_k0 = ctx->noise_k0;
+        a.wavetables = s->d_wavetables ? s->d_wavetables : ctx->d_wavetables; a.noise_k0 = ctx->noise_k0;
         const int gmax = ki.wide_max_utt;
         const int groups = std::max(1, std::min(ctx->sm_count, (n + 1) / 2));
         const int g2 = (n + groups - 1) / groups > gmax ? (n + gmax - 1) / gmax : groups;
@@ -1301,6 +1331,16 @@ int trm_cuda_resident_create(trm_cuda_ctx *ctx, int precision, int n, const trm_
         return rc;
     }
     CK(cudaMemset(r->dc.maxbits, 0, (size_t)n * sizeof(unsigned long long)));
+    if (!ctx->wt_host.empty()) {
+        if (cudaMalloc((void **)&r->d_wavetables, ctx->wt_host.size() * sizeof(double)) != cudaSuccess ||
+            cudaMemcpy(r->d_wavetables, ctx->wt_host.data(), ctx->wt_host.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+            if (r->d_wavetables) cudaFree(r->d_wavetables);
+            r->arena.release();
+            delete r;
+            return fail("resident wavetables", cudaGetLastError());
+        }
+        r->dc.wavetables = r->d_wavetables;
+    }
     CK(cudaDeviceSynchronize());
     *out = r;
     return 0;
@@ -1312,6 +1352,7 @@ void trm_cuda_resident_destroy(trm_cuda_resident *r)
     cudaSetDevice(r->ctx->device);
     cudaDeviceSynchronize();
     r->arena.release();
+    if (r->d_wavetables) cudaFree(r->d_wavetables);
     delete r;
 }
 

@@ -267,6 +267,35 @@ static int64_t src_output_count(const rates_t *r, int64_t n_in)
     return (total * 65536 + (int64_t)r->tri - 1) / (int64_t)r->tri;
 }
 
+/* The reference's streaming converter mis-handles its final drain when down-sampling (TRMSampleRateConverter.m:160-168,
+ * TRMRingBuffer.m:55-59,85-93).  Its read pointer advances 1..3 input positions per output, so a
+ * pass over the ring may stop o = 1..2 positions PAST the end pointer.  The next pass repairs "end < read" by adding the
+ * ring size -- correct when the ring wrapped, wrong when the pass simply has fewer than o new inputs: it then runs over a
+ * whole ring of stale data and appends ~1024 x ratio spurious samples.  Passes triggered by the fill counter always bring
+ * fillSize new inputs; only the final pass of -flush can be short.  With total = N_in + 2 pad inputs, K = total / fillSize
+ * counter-triggered passes and r = total % fillSize inputs left for the final one, the last counter-triggered pass ends
+ * after n* = ceil(K fillSize 2^16 / tri) outputs at read position P = (n* tri) >> 16: the bug fires iff K >= 1 and
+ * r < P - K fillSize.  (Checked against the oracle's restatement of the streaming converter over 6 voices x 498 lengths,
+ * tests/test_host.py.)  This implementation computes the converter's defined output (the stateless form) and reports
+ * the condition instead. */
+static int flush_bug(const rates_t *r, int64_t n_in)
+{
+    if (r->upsample) return 0;
+    const int64_t fill = 1024 - 2 * (int64_t)r->padSize, total = n_in + 2 * (int64_t)r->padSize;
+    if (fill <= 0 || total < fill) return 0;
+    const int64_t K = total / fill, rest = total - K * fill, tri = (int64_t)r->tri;
+    const int64_t n_star = (K * fill * 65536 + tri - 1) / tri;
+    const int64_t over = ((n_star * tri) >> 16) - K * fill;
+    return rest < over;
+}
+
+int TRMReferenceFlushBug(const TRMInputParameters *ip, size_t n_frames)
+{
+    rates_t r;
+    if (!ip || n_frames == 0 || derive_rates(ip, &r) != TRM_OK) return 0;
+    return flush_bug(&r, (int64_t)(n_frames - 1) * r.controlPeriod);
+}
+
 int TRMDeriveValues(const TRMInputParameters *ip, size_t n_frames, TRMDerivedValues *out)
 {
     rates_t r;
@@ -433,42 +462,47 @@ static int describe(const TRMInputParameters *ip, int32_t n_frames, voice_set *v
  * in flight on one GPU (TRMBatchSynthesizeAsync): the PCM of call k leaves for the host while call k+1 computes. */
 #define CTX_LANES 3
 static trm_cuda_ctx *g_ctx[MAX_DEVICES][CTX_LANES];
-static pthread_mutex_t g_ctx_mu[MAX_DEVICES][CTX_LANES];
-static pthread_mutex_t g_ctx_table_mu = PTHREAD_MUTEX_INITIALIZER;
-static int g_ctx_mu_init;
+static int g_lane_busy[MAX_DEVICES][CTX_LANES];
+static pthread_mutex_t g_lane_mu = PTHREAD_MUTEX_INITIALIZER;     /* covers g_lane_busy and context creation */
+static pthread_cond_t g_lane_cv = PTHREAD_COND_INITIALIZER;
 
+/* A context lane serves one call at a time.  A caller takes the first free lane of the device and, when all are busy,
+ * waits on the condition variable until ANY of them is released (no lane is special; nothing is ever held across calls:
+ * streams and device-resident batches own copies of what they need from the context). */
 static int acquire_ctx(int device, trm_cuda_ctx **out, int *lane_out)
 {
     int rc;
     const trm_cuda_tables *t = tables(&rc);
     if (rc) return set_err(rc, "FIR design failed%s", "");
     if (device < 0 || device >= MAX_DEVICES) return set_err(TRM_ERR_CUDA, "bad device ordinal%s", "");
-    pthread_mutex_lock(&g_ctx_table_mu);
-    if (!g_ctx_mu_init) {
-        for (int i = 0; i < MAX_DEVICES; i++)
-            for (int l = 0; l < CTX_LANES; l++) pthread_mutex_init(&g_ctx_mu[i][l], NULL);
-        g_ctx_mu_init = 1;
-    }
-    pthread_mutex_unlock(&g_ctx_table_mu);
-    /* a context serves one call at a time: take the first free lane, else queue on lane 0 */
+    pthread_mutex_lock(&g_lane_mu);
     int lane = -1;
-    for (int l = 0; l < CTX_LANES && lane < 0; l++)
-        if (pthread_mutex_trylock(&g_ctx_mu[device][l]) == 0) lane = l;
-    if (lane < 0) { lane = 0; pthread_mutex_lock(&g_ctx_mu[device][0]); }
-    if (!g_ctx[device][lane]) {
-        pthread_mutex_lock(&g_ctx_table_mu);
-        const int failed = trm_cuda_ctx_create(device, t, &g_ctx[device][lane]) != 0;
-        pthread_mutex_unlock(&g_ctx_table_mu);
-        if (failed) {
-            pthread_mutex_unlock(&g_ctx_mu[device][lane]);
-            return cuda_err();
-        }
+    for (;;) {
+        for (int l = 0; l < CTX_LANES && lane < 0; l++)
+            if (!g_lane_busy[device][l]) lane = l;
+        if (lane >= 0) break;
+        pthread_cond_wait(&g_lane_cv, &g_lane_mu);
     }
+    g_lane_busy[device][lane] = 1;
+    int failed = 0;
+    if (!g_ctx[device][lane]) failed = trm_cuda_ctx_create(device, t, &g_ctx[device][lane]) != 0;
+    if (failed) {
+        g_lane_busy[device][lane] = 0;
+        pthread_cond_broadcast(&g_lane_cv);
+    }
+    pthread_mutex_unlock(&g_lane_mu);
+    if (failed) return cuda_err();
     *out = g_ctx[device][lane];
     *lane_out = lane;
     return TRM_OK;
 }
-static void release_ctx(int device, int lane) { pthread_mutex_unlock(&g_ctx_mu[device][lane]); }
+static void release_ctx(int device, int lane)
+{
+    pthread_mutex_lock(&g_lane_mu);
+    g_lane_busy[device][lane] = 0;
+    pthread_cond_broadcast(&g_lane_cv);
+    pthread_mutex_unlock(&g_lane_mu);
+}
 
 void *TRMHostAlloc(size_t bytes)
 {
@@ -720,6 +754,7 @@ struct TRMBatch {
     int32_t *numberSamples;
     int64_t *pcm_offsets, *out_offsets, *tube_offsets;
     double *maxima;
+    uint8_t *flush_bug;            /* per utterance: the reference would hit its converter flush bug (TRMReferenceFlushBug) */
     TRMBatchLayout layout;
     int64_t total_tube_elems;
     int64_t launches;
@@ -731,7 +766,7 @@ static int64_t round_up_elems(int64_t v) { return (v + TRM_ALIGN_ELEMS - 1) / TR
 void TRMBatchFree(TRMBatch *b)
 {
     if (!b) return;
-    free(b->desc); free(b->numberSamples); free(b->pcm_offsets); free(b->out_offsets); free(b->tube_offsets); free(b->maxima);
+    free(b->desc); free(b->numberSamples); free(b->pcm_offsets); free(b->out_offsets); free(b->tube_offsets); free(b->maxima); free(b->flush_bug);
     voice_set_free(&b->voices);
     free(b);
 }
@@ -759,7 +794,8 @@ TRMBatch *TRMBatchCreate(int n, const TRMInputParameters *ip, int shared, const 
     b->out_offsets = calloc(nn, sizeof *b->out_offsets);
     b->tube_offsets = calloc(nn, sizeof *b->tube_offsets);
     b->maxima = calloc(nn, sizeof *b->maxima);
-    if (!b->desc || !b->numberSamples || !b->pcm_offsets || !b->out_offsets || !b->tube_offsets || !b->maxima) {
+    b->flush_bug = calloc(nn, 1);
+    if (!b->flush_bug || !b->numberSamples || !b->pcm_offsets || !b->out_offsets || !b->tube_offsets || !b->maxima) {
         TRMBatchFree(b);
         *err = set_err(TRM_ERR_NOMEM, "out of memory%s", "");
         return NULL;
@@ -791,6 +827,7 @@ TRMBatch *TRMBatchCreate(int n, const TRMInputParameters *ip, int shared, const 
         d->out_offset = out_at;
         d->pcm_offset = pcm_at;
         b->numberSamples[u] = (int32_t)d->n_out;
+        b->flush_bug[u] = n_frames[u] > 0 && flush_bug(&r, d->n_tube);
         b->tube_offsets[u] = tube_at;
         b->out_offsets[u] = out_at;
         b->pcm_offsets[u] = pcm_at;
@@ -819,6 +856,7 @@ const int32_t *TRMBatchNumberSamples(const TRMBatch *b) { return b->numberSample
 const int64_t *TRMBatchPCMOffsets(const TRMBatch *b) { return b->pcm_offsets; }
 const int64_t *TRMBatchOutOffsets(const TRMBatch *b) { return b->out_offsets; }
 const double *TRMBatchMaximumSampleValues(const TRMBatch *b) { return b->maxima; }
+const uint8_t *TRMBatchReferenceFlushBugFlags(const TRMBatch *b) { return b->flush_bug; }
 int64_t TRMBatchTubeElements(const TRMBatch *b) { return b->total_tube_elems; }
 const int64_t *TRMBatchTubeOffsets(const TRMBatch *b) { return b->tube_offsets; }
 int64_t TRMBatchKernelLaunches(const TRMBatch *b) { return b->launches; }
@@ -970,6 +1008,14 @@ static int check_event_lists(const TRMBatch *b, const TRMEvent *events, const in
         const int64_t want = n_events[u] >= 0 ? TRMEventListFrameCount(events + event_offset[u], n_events[u]) : -1;
         if (want != b->desc[u].n_frames)
             return set_err(TRM_ERR_PARAM, "utterance frame count differs from TRMEventListFrameCount of its event list%s", "");
+        /* every TRM parameter track needs a value after the first event: the reference's set-up loop (EventList.m:919-930)
+         * scans forward for one without a bound and reads past the array otherwise */
+        const TRMEvent *ev = events + event_offset[u];
+        for (int j = 0; j < 16 && n_events[u] >= 2; j++) {
+            int found = 0;
+            for (int32_t k = 1; k < n_events[u] && !found; k++) found = !isnan(ev[k].value[j]);
+            if (!found) return set_err(TRM_ERR_PARAM, "event list: a parameter track has no value after the first event%s", "");
+        }
     }
     return TRM_OK;
 }
@@ -1045,8 +1091,9 @@ TRMStream *TRMStreamCreate(int n_streams, const TRMInputParameters *voice, int p
         free(t);
         return NULL;
     }
+    release_ctx(device, t->lane);      /* the stream owns its wavetable copy, streams and scratch: no lane is held */
     *err = TRM_OK;
-    return t;      /* the context lane stays with the stream (its wavetables must not change under it) */
+    return t;
 }
 
 int64_t TRMStreamCapacity(const TRMStream *t) { return t ? trm_cuda_stream_capacity(t->s) : 0; }
@@ -1062,7 +1109,6 @@ void TRMStreamFree(TRMStream *t)
 {
     if (!t) return;
     trm_cuda_stream_destroy(t->s);
-    release_ctx(t->device, t->lane);
     voice_set_free(&t->voices);
     free(t);
 }
@@ -1284,6 +1330,8 @@ int TRMTubeModelSynthesize(TRMTubeModel *m)
 }
 
 int32_t TRMTubeModelNumberSamples(const TRMTubeModel *m) { return m->numberSamples; }
+int32_t TRMTubeModelChannels(const TRMTubeModel *m) { return m->ip.channels == 2 ? 2 : 1; }
+int TRMTubeModelHitsReferenceFlushBug(const TRMTubeModel *m) { return TRMReferenceFlushBug(&m->ip, m->n_frames); }
 double TRMTubeModelMaximumSampleValue(const TRMTubeModel *m) { return m->maximum; }
 const double *TRMTubeModelResampledData(const TRMTubeModel *m) { return m->resampled; }
 const double *TRMTubeModelTubeSignal(const TRMTubeModel *m, int64_t *count)

@@ -112,6 +112,12 @@ typedef struct TRMDerivedValues {
     int32_t  numberSamples;      /* output-rate frames the converter will emit for n_frames frames      */
 } TRMDerivedValues;
 int TRMDeriveValues(const TRMInputParameters *ip, size_t n_frames, TRMDerivedValues *out);
+/* 1 if the REFERENCE would hit its converter flush bug for an utterance of n_frames frames with these parameters
+ * (TRMSampleRateConverter.m:160-168: when down-sampling, a final drain that finds fewer new inputs than the previous pass
+ * overshot by runs over a whole ring of stale data and appends ~1024 x ratio spurious samples; exact rule in trm_host.c).
+ * This implementation produces the converter's defined output; the flag tells a caller that the reference's sample
+ * count and tail differ for that utterance. */
+int TRMReferenceFlushBug(const TRMInputParameters *ip, size_t n_frames);
 
 /* ---------------------------------------------------------------------------------------------
  * TRMDataList  (TRMDataList.h:8-18; TRMSynthesizer.m:98-106 for add/removeAll)
@@ -183,6 +189,8 @@ int           TRMTubeModelSynthesize(TRMTubeModel *model);
 
 /* sampleRateConverter.numberSamples / .maximumSampleValue / .resampledData (TRMSampleRateConverter.h:13-17) */
 int32_t       TRMTubeModelNumberSamples(const TRMTubeModel *model);
+int32_t       TRMTubeModelChannels(const TRMTubeModel *model);          /* 1 or 2: int16 elements per frame of PullPCM16 */
+int           TRMTubeModelHitsReferenceFlushBug(const TRMTubeModel *model);
 double        TRMTubeModelMaximumSampleValue(const TRMTubeModel *model);
 const double *TRMTubeModelResampledData(const TRMTubeModel *model);
 /* tube-rate signal before the converter (what -synthesize hands to dataFill:, TRMTubeModel.m:346) */
@@ -226,6 +234,7 @@ const int32_t *TRMBatchNumberSamples(const TRMBatch *batch);       /* [n] output
 const int64_t *TRMBatchPCMOffsets(const TRMBatch *batch);          /* [n] element offset into pcm_out     */
 const int64_t *TRMBatchOutOffsets(const TRMBatch *batch);          /* [n] element offset into samples_out */
 const double  *TRMBatchMaximumSampleValues(const TRMBatch *batch); /* [n]                                 */
+const uint8_t *TRMBatchReferenceFlushBugFlags(const TRMBatch *batch); /* [n] TRMReferenceFlushBug per utterance  */
 
 /* Synthesizes the whole batch on `n_devices` GPUs (devices[] lists CUDA ordinals; NULL = 0..n-1), host
  * buffers in and out.  frames: TRMParameters array in host memory (pinned memory from TRMHostAlloc makes
@@ -284,7 +293,7 @@ int TRMBatchSynthesizeEvents(TRMBatch *batch, const TRMEvent *events, const int6
  * stream and returns the un-normalised output-rate samples that became computable (what .resampledData holds for a
  * whole utterance; double in FP64 mode, float in FP32 mode).  The state of every recurrence is carried on the device:
  * the pushes, concatenated, are bit-identical to synthesizing the whole utterance at once.
- * A stream object occupies one of its device's three context lanes until it is freed.
+ * A stream owns its device buffers and wavetable copy; it does not hold a context lane between calls.
  * ------------------------------------------------------------------------------------------- */
 typedef struct TRMStream TRMStream;
 TRMStream *TRMStreamCreate(int n_streams, const TRMInputParameters *voice, int precision, int max_frames_per_push,

@@ -95,3 +95,39 @@ def test_down_sampling_voice_streams_too(precision):
         assert y[u].shape == want[u].shape, (u, y[u].shape, want[u].shape)
         assert np.array_equal(y[u], want[u]), "stream %d: %d samples differ, first at %d" % (
             u, int((y[u] != want[u]).sum()), int(np.nonzero(y[u] != want[u])[0][0]))
+
+
+import oracle_lib as O  # noqa: E402
+
+
+@pytest.mark.skipif(not O.have_reference_binary(), reason="oracle/_ref/tube_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("case", ["walk_44k", "walk_short_tube_down"])
+def test_stream_against_the_reference_float_stream(case):
+    """TRAcT's mode of use, checked against the reference itself: oracle/_ref/tube_ref is Applications/TRAcT/tube.c
+    compiled unmodified; its converter (dataFill / dataEmpty, tube.c:2348-2521) emits the un-normalised FLOAT stream TRAcT
+    plays (tube.c:1096-1191).  TRMStream, fed the same frames in small pushes, must return that stream -- to the float
+    precision tube.c emits (2e-7 of peak, as tests/test_oracle.py uses for the same comparison)."""
+    import os
+    g = _g()
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "trm_golden.npz"))
+    oip = O.OracleInputParameters.from_buffer_copy(bytes(z[case + "/ip"]))
+    frames = z[case + "/frames"]
+    ref = O.run_reference(oip, frames)
+    ip = g.TRMInputParameters(float(oip.outputRate))
+    for name, _ in oip._fields_:
+        if hasattr(ip, name):
+            setattr(ip, name, getattr(oip, name))
+    nf = frames.shape[0]
+    st = g.TRMStream(1, ip, precision=g.TRM_PRECISION_FP64, max_frames_per_push=16)
+    parts, at = [], 0
+    for m in ([5, 1, 16, 3] * nf)[:nf]:
+        m = min(m, nf - at)
+        if m <= 0:
+            break
+        parts.append(st.push(frames[None, at:at + m], flush=(at + m >= nf))[0])
+        at += m
+    st.free()
+    y = np.concatenate(parts)
+    assert y.shape[0] == ref["out"].shape[0]
+    peak = float(np.abs(ref["out"]).max())
+    assert np.abs(y.astype(np.float32) - ref["out"]).max() <= 2e-7 * peak

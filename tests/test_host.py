@@ -241,3 +241,27 @@ def test_voice_parameters_defaults_header_and_named_voices(tmp_path):
     assert g.MMSynthesisParameters("Female").tnMin == 32.0 and g.MMSynthesisParameters("Baby").pitch == 7.5
     with pytest.raises(g.TRMError):
         g.MMSynthesisParameters("tenor")
+
+
+def test_reference_flush_bug_is_flagged():
+    """TRMSampleRateConverter.m:160-168: when DOWN-sampling, a final drain that finds fewer new
+    inputs than the previous pass overshot by makes the reference run over a whole ring of stale data and append spurious
+    samples.  The oracle restates the streaming converter and reproduces that; this implementation computes the defined
+    output and FLAGS the condition: flag set <=> the reference's sample count differs from the closed form."""
+    g = _g()
+    from gnuspeech_b200 import _native as N
+    from gnuspeech_b200 import workloads as W
+    seen = 0
+    for kw in (dict(length=7.5805, temperature=32.0), dict(length=10.0, temperature=32.0), dict(length=6.5)):
+        ip = g.TRMInputParameters(22050.0, **kw)
+        lengths = list(range(2, 260, 7)) + [209, 210, 211]
+        b = g.TRMBatch(ip, lengths)
+        flags = b.referenceFlushBugFlags
+        for k, nf in enumerate(lengths):
+            assert bool(N.lib().TRMReferenceFlushBug(C.byref(ip), nf)) == bool(flags[k])
+            ref = O.synthesize(ip, W.static_vowel(nf, 0), want_tube=False)
+            assert (ref.numberSamples != b.numberSamples[k]) == bool(flags[k]), (kw, nf, ref.numberSamples, b.numberSamples[k])
+            seen += int(flags[k])
+    assert seen >= 1                                                         # (7.58 cm tract, 210 frames: +488 samples)
+    up = g.TRMInputParameters(44100.0)                                       # up-sampling is immune
+    assert not any(N.lib().TRMReferenceFlushBug(C.byref(up), nf) for nf in range(2, 400))
