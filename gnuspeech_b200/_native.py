@@ -14,6 +14,7 @@ TRM_ERR_TUBE_LENGTH, TRM_ERR_FIR, TRM_ERR_NOMEM, TRM_ERR_PARAM = -1, -2, -3, -4
 TRM_ERR_CUDA, TRM_ERR_IO, TRM_ERR_STATE, TRM_ERR_SILENT = -5, -6, -7, -8
 TRM_PRECISION_FP64, TRM_PRECISION_FP32, TRM_PRECISION_FP64_STRICT = 0, 1, 2
 TRM_STAGE_TUBE, TRM_STAGE_SRC, TRM_STAGE_PCM = 0, 1, 2
+TRM_FRAMES_F64, TRM_FRAMES_F32 = 0, 1
 
 
 class TRMInputParametersStruct(C.Structure):
@@ -141,12 +142,18 @@ def lib():
     sig("TRMResidentRun", C.c_int, vp, vp)
     sig("TRMResidentFetch", C.c_int, vp, vp, vp, vp, vp)
     sig("TRMResidentFree", None, vp)
+    sig("TRMResidentFetchUtterance", C.c_int, vp, C.c_int, vp, vp, vp)
+    sig("TRMBatchSetFrameFormat", C.c_int, vp, C.c_int)
+    sig("TRMCopyProbe", C.c_int, C.c_int, vp, sz, vp, sz, C.c_int, P(C.c_double))
     sig("TRMHostAlloc", vp, sz)
     sig("TRMHostFree", None, vp)
     sig("TRMWorkloadStaticVowel", None, C.c_int, dbl, sz, vp)
     sig("TRMWorkloadRandomWalk", None, C.c_uint64, C.c_uint64, sz, vp)
     sig("TRMWorkloadRandomWalkBatch", None, C.c_uint64, C.c_uint64, sz, sz, vp, C.c_int)
     sig("TRMWorkloadGridPoint", None, C.c_uint64, sz, vp)
+    sig("TRMWorkloadWalk2", None, C.c_uint64, C.c_uint64, sz, vp)
+    sig("TRMSweepSynthesize", C.c_int, P(TRMInputParametersStruct), i32, C.c_uint64, C.c_uint64, i64, C.c_int, C.c_int, vp, vp, i64, vp,
+        vp, i64, P(i32), P(i64), P(C.c_double))
     _lib = L
     return L
 

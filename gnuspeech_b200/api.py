@@ -495,6 +495,11 @@ class TRMBatch(object):
     def make_resident(self, frames, device=0):
         return TRMResident(self, frames, device)
 
+    def set_frame_format(self, fmt):
+        """N.TRM_FRAMES_F64 (TRMParameters rows, default) or N.TRM_FRAMES_F32 (rows of 16 floats: half the upload,
+        identical results -- Monet's frames are floats)."""
+        check(N.lib().TRMBatchSetFrameFormat(self._h, fmt), "TRMBatchSetFrameFormat")
+
 
 class TRMStream(object):
     """Streaming synthesis of n voices at once (TRMStreamCreate / TRMStreamPush): push control frames as they arrive,
@@ -571,10 +576,52 @@ class TRMResident(object):
         check(N.lib().TRMResidentFetch(self._h, _ptr(pcm_out), _ptr(samples_out), _ptr(maxima), _ptr(tube_out)),
               "TRMResidentFetch")
 
+    def fetch_utterance(self, u):
+        """(samples, pcm, maximum) of utterance u of the resident batch."""
+        b = self.batch
+        n = int(b.numberSamples[u])
+        ch = 2 if (b._ip[u].channels if isinstance(b._ip, C.Array) else b._ip.channels) == 2 else 1
+        smp = np.zeros(max(n, 1), b.sample_dtype)
+        pcm = np.zeros(max(n * ch, 1), np.int16)
+        mx = C.c_double(0.0)
+        check(N.lib().TRMResidentFetchUtterance(self._h, int(u), _ptr(smp), _ptr(pcm), C.byref(mx)), "TRMResidentFetchUtterance")
+        return smp[:n], pcm[:n * ch], float(mx.value)
+
     def free(self):
         if getattr(self, "_h", None):
-            N.lib().TRMResidentFree(self._h)
+            try:
+                N.lib().TRMResidentFree(self._h)
+            except TypeError:   # interpreter shutdown
+                pass
             self._h = None
 
     def __del__(self):
         self.free()
+
+
+def sweep_synthesize(ip, n_frames, n, seed=1, first_index=0, precision=N.TRM_PRECISION_FP64, device=0, probes=()):
+    """TRMSweepSynthesize: n utterances of walk2 tracks generated on the device.  Returns a dict with per-utterance
+    `checksums` (uint64), `maxima`, `numberSamples`, `kernel_ms`, `launches` and, for the utterances in `probes`
+    (indices relative to this call), their PCM as `probe_pcm[k]`."""
+    probes = np.ascontiguousarray(sorted(int(p) for p in probes), dtype=np.int64)
+    ns = C.c_int32(0)
+    check(N.lib().TRMSweepSynthesize(C.byref(ip), int(n_frames), int(seed), int(first_index), 0, precision, device,
+                                     _ptr(np.zeros(1, np.uint64)), None, 0, None, None, 0, C.byref(ns), None, None), "TRMSweepSynthesize")
+    stride = int(ns.value) * (2 if ip.channels == 2 else 1)
+    sums = np.zeros(max(int(n), 1), np.uint64)
+    mx = np.zeros(max(int(n), 1), np.float64)
+    ppcm = np.zeros((max(len(probes), 1), max(stride, 1)), np.int16)
+    launches, ms = C.c_int64(0), C.c_double(0.0)
+    check(N.lib().TRMSweepSynthesize(C.byref(ip), int(n_frames), int(seed), int(first_index), int(n), precision, device, _ptr(sums),
+                                     _ptr(mx), len(probes), _ptr(probes) if len(probes) else None, _ptr(ppcm), stride, C.byref(ns),
+                                     C.byref(launches), C.byref(ms)), "TRMSweepSynthesize")
+    return dict(checksums=sums[:n], maxima=mx[:n], numberSamples=int(ns.value), kernel_ms=float(ms.value), launches=int(launches.value),
+                probes=probes, probe_pcm=ppcm[:len(probes)])
+
+
+def pcm_checksum(pcm):
+    """The sweep's per-utterance checksum of a PCM16 array: sum(pcm[i] * (2 i + 1)) mod 2^64."""
+    p = np.asarray(pcm).astype(np.int64).astype(np.uint64)
+    w = (2 * np.arange(p.shape[0], dtype=np.uint64) + np.uint64(1))
+    with np.errstate(over="ignore"):
+        return np.uint64((p * w).sum(dtype=np.uint64))

@@ -30,6 +30,9 @@ TRM_DECLARE_LAUNCHERS(f64)
 TRM_DECLARE_LAUNCHERS(f32)
 TRM_DECLARE_LAUNCHERS(f64s)
 int trm_k_framegen(const trm::FrameGenArgs *, cudaStream_t);
+int trm_k_widen_frames(const float *, double *, long long, long long, long long, long long, cudaStream_t);
+int trm_k_workload_walk2(unsigned long long, unsigned long long, long long, int, double *, cudaStream_t);
+int trm_k_pcm_checksum(const trm_cuda_utterance *, int, const int16_t *, unsigned long long *, cudaStream_t);
 }
 
 // precision codes of include/trm.h: 0 = FP64 conformance, 1 = FP32 fast, 2 = FP64 strict
@@ -148,6 +151,7 @@ struct DeviceChunk {
     long long *tile_max_out = nullptr, *tile_first_out = nullptr, *item_base = nullptr;
     unsigned long long *maxbits = nullptr;
     double *frames = nullptr;
+    float *frames32 = nullptr;              // float32 frames as uploaded (frame format 1), widened into `frames` on the device
     void *tube = nullptr, *out = nullptr;
     int16_t *pcm = nullptr;
     long long total_items = 0, max_n_out = 0;
@@ -185,6 +189,7 @@ struct ChunkPlan {
     std::vector<Group> groups;
     long long total_items = 0, max_n_out = 0;
     size_t n_tiles() const { return tile_nt.size(); }
+    bool f32_frames = false;                // the caller's frames are float32 rows (64 bytes)
     size_t arena_bytes(size_t esz, bool want_pcm) const
     {
         size_t n = desc.size(), b = 0;
@@ -198,6 +203,7 @@ struct ChunkPlan {
         add(item_base.size() * sizeof(long long));
         add(n * sizeof(unsigned long long));
         add(frame_rows * 128);
+        if (f32_frames) add(frame_rows * 64);
         add(tube_elems * esz);
         add(out_elems * esz);
         if (want_pcm) add(pcm_elems * sizeof(int16_t));
@@ -441,6 +447,7 @@ void carve(Arena &a, const ChunkPlan &p, size_t esz, bool want_pcm, DeviceChunk 
     dc.item_base = (long long *)a.take(p.item_base.size() * sizeof(long long));
     dc.maxbits = (unsigned long long *)a.take(n * sizeof(unsigned long long));
     dc.frames = (double *)a.take(p.frame_rows * 128);
+    dc.frames32 = p.f32_frames ? (float *)a.take(p.frame_rows * 64) : nullptr;
     dc.tube = a.take(p.tube_elems * esz);
     dc.out = a.take(p.out_elems * esz);
     dc.pcm = want_pcm ? (int16_t *)a.take(p.pcm_elems * sizeof(int16_t)) : nullptr;
@@ -501,17 +508,24 @@ int upload_plan(const ChunkPlan &p, const DeviceChunk &dc, unsigned char *stage,
 }
 
 int upload_frames(const ChunkPlan &p, const DeviceChunk &dc, const trm_cuda_utterance *desc_global,
-                  const double *frames_host, cudaStream_t s)
+                  const void *frames_host, cudaStream_t s)
 {
     if (p.frame_rows == 0) return 0;
+    const size_t row = p.f32_frames ? 64 : 128;                     // bytes per frame in the caller's array
+    unsigned char *dst = p.f32_frames ? (unsigned char *)dc.frames32 : (unsigned char *)dc.frames;
+    const unsigned char *src = (const unsigned char *)frames_host;
     if (p.frames_dense) {
-        CK(cudaMemcpyAsync(dc.frames, frames_host + (size_t)p.frames_lo * 16, p.frame_rows * 128, cudaMemcpyDefault, s));
+        CK(cudaMemcpyAsync(dst, src + (size_t)p.frames_lo * row, p.frame_rows * row, cudaMemcpyDefault, s));
     } else {
         for (size_t i = 0; i < p.desc.size(); ++i) {
             const auto &g = desc_global[p.u0 + i];
-            CK(cudaMemcpyAsync(dc.frames + (size_t)p.desc[i].frame_offset * 16, frames_host + (size_t)g.frame_offset * 16,
-                               (size_t)g.n_frames * 128, cudaMemcpyDefault, s));
+            CK(cudaMemcpyAsync(dst + (size_t)p.desc[i].frame_offset * row, src + (size_t)g.frame_offset * row,
+                               (size_t)g.n_frames * row, cudaMemcpyDefault, s));
         }
+    }
+    if (p.f32_frames) {
+        const int rc = trm_k_widen_frames(dc.frames32, dc.frames, 1, (long long)p.frame_rows, 0, (long long)p.frame_rows, s);
+        if (rc != 0) return fail("widen_frames_kernel launch", (cudaError_t)rc);
     }
     return 0;
 }
@@ -804,6 +818,16 @@ int trm_cuda_synthesize_host_ex(trm_cuda_ctx *ctx, int precision, int n, const t
                                 const double *frames_host, int16_t *pcm_host, void *samples_host, double *max_host,
                                 void *tube_host, int64_t *launches, void (*enqueued)(void *), void *enqueued_arg)
 {
+    return trm_cuda_synthesize_host_fmt(ctx, precision, 0, n, desc, frames_host, pcm_host, samples_host, max_host, tube_host, launches,
+                                        enqueued, enqueued_arg);
+}
+
+int trm_cuda_synthesize_host_fmt(trm_cuda_ctx *ctx, int precision, int frame_format, int n, const trm_cuda_utterance *desc,
+                                 const void *frames_host, int16_t *pcm_host, void *samples_host, double *max_host,
+                                 void *tube_host, int64_t *launches, void (*enqueued)(void *), void *enqueued_arg)
+{
+    if (frame_format != 0 && frame_format != 1) return fail_msg("unknown frame format");
+    const bool f32_frames = frame_format == 1;
     if (launches) *launches = 0;
     if (n <= 0) return 0;
     CK(cudaSetDevice(ctx->device));
@@ -885,6 +909,7 @@ int trm_cuda_synthesize_host_ex(trm_cuda_ctx *ctx, int precision, int n, const t
         for (int u = u0; u < u1; ++u) chunk_out += desc[u].n_out;
         const int want_groups = (want_pcm && !getenv("TRM_NO_OUT_GROUPS")) ? (int)std::min<long long>(MAX_OUT_GROUPS, chunk_out / (64ll << 20)) : 1;
         RCD(plan_chunk(desc, u0, u1, ctx->ki(precision), p, want_groups));
+        p.f32_frames = f32_frames;
         const bool grouped = p.groups.size() > 1;
         // long uniform chunks: the waveguide as two launches in time, the later frames uploaded behind the first
         if (p.uniform_frames >= 512 && !getenv("TRM_NO_TIME_SPLIT") &&
@@ -904,13 +929,23 @@ int trm_cuda_synthesize_host_ex(trm_cuda_ctx *ctx, int precision, int n, const t
                 RCD(upload_frames(p, dc, desc, frames_host, s_in));
                 CKD(cudaEventRecord(ctx->ev_in[slot], s_in));
             } else {
-                // frames [0, f1] of every utterance, then the rest: two strided copies
-                const size_t pitch = (size_t)p.uniform_frames * 128, first = (size_t)(p.split_frame + 1) * 128;
-                const unsigned char *src = (const unsigned char *)(frames_host + (size_t)p.frames_lo * 16);
-                CKD(cudaMemcpy2DAsync(dc.frames, pitch, src, pitch, first, (size_t)(u1 - u0), cudaMemcpyDefault, s_in));
+                // frames [0, f1] of every utterance, then the rest: two strided copies (float32 rows are widened on the device)
+                const size_t row = f32_frames ? 64 : 128;
+                const size_t pitch = (size_t)p.uniform_frames * row, first = (size_t)(p.split_frame + 1) * row;
+                const unsigned char *src = (const unsigned char *)frames_host + (size_t)p.frames_lo * row;
+                unsigned char *dst = f32_frames ? (unsigned char *)dc.frames32 : (unsigned char *)dc.frames;
+                CKD(cudaMemcpy2DAsync(dst, pitch, src, pitch, first, (size_t)(u1 - u0), cudaMemcpyDefault, s_in));
+                if (f32_frames && trm_k_widen_frames(dc.frames32, dc.frames, u1 - u0, p.uniform_frames, 0, p.split_frame + 1, s_in) != 0) {
+                    drain();
+                    return fail_msg("widen_frames_kernel launch");
+                }
                 CKD(cudaEventRecord(ctx->ev_in[slot], s_in));
-                CKD(cudaMemcpy2DAsync((unsigned char *)dc.frames + first, pitch, src + first, pitch, pitch - first, (size_t)(u1 - u0),
-                                     cudaMemcpyDefault, s_in));
+                CKD(cudaMemcpy2DAsync(dst + first, pitch, src + first, pitch, pitch - first, (size_t)(u1 - u0), cudaMemcpyDefault, s_in));
+                if (f32_frames && trm_k_widen_frames(dc.frames32, dc.frames, u1 - u0, p.uniform_frames, p.split_frame + 1,
+                                                     p.uniform_frames - p.split_frame - 1, s_in) != 0) {
+                    drain();
+                    return fail_msg("widen_frames_kernel launch");
+                }
                 CKD(cudaEventRecord(ctx->ev_in2[slot], s_in));
             }
             mark(s_in);
@@ -1391,6 +1426,142 @@ int trm_cuda_resident_fetch(trm_cuda_resident *r, int16_t *pcm_host, void *sampl
         CK(cudaMemcpy(mb.data(), r->dc.maxbits, mb.size() * sizeof(mb[0]), cudaMemcpyDeviceToHost));
         for (size_t i = 0; i < mb.size(); ++i) memcpy(&max_host[i], &mb[i], sizeof(double));
     }
+    return 0;
+}
+
+/*
+ * Sweep (BASELINE configs[4]): n utterances of one voice and n_frames frames each, whose control
+ * tracks are the walk2 workload (include/trm_workload.h) generated ON THE DEVICE -- utterance k uses index first_index + k
+ * of stream `seed` -- synthesized chunk by chunk; the audio never leaves the device: 8 bytes of PCM checksum (and the
+ * maximum) per utterance come back.  probe_utt[] (sorted, relative to this call) names utterances whose PCM is copied to
+ * probe_pcm (n_probe rows of probe_stride int16) for oracle spot checks.  One stream, no copies inside the loop.
+ */
+int trm_cuda_sweep(trm_cuda_ctx *ctx, int precision, const trm_cuda_utterance *voice, int32_t n_frames, uint64_t seed,
+                   uint64_t first_index, int64_t n, uint64_t *checksums_host, double *max_host, int64_t n_probe,
+                   const int64_t *probe_utt, int16_t *probe_pcm, int64_t probe_stride, int64_t *launches, double *kernel_ms)
+{
+    if (launches) *launches = 0;
+    if (kernel_ms) *kernel_ms = 0.0;
+    if (n <= 0) return 0;
+    if (precision < 0 || precision > 2) return fail_msg("unknown precision code");
+    CK(cudaSetDevice(ctx->device));
+    const size_t esz = prec_esz(precision);
+    const trm::KernelInfo &ki = ctx->ki(precision);
+    const int64_t cap = (int64_t)ctx->sm_count * ki.wide_max_utt;          // one full wave of the waveguide kernel
+    const int C = (int)std::min<int64_t>(n, cap);
+    // one chunk plan, reused: C utterances of the template voice, frames back to back
+    std::vector<trm_cuda_utterance> desc((size_t)C, *voice);
+    long long tube_at = 0, out_at = 0, pcm_at = 0;
+    auto up = [](long long v) { return (v + TRM_ALIGN_ELEMS - 1) / TRM_ALIGN_ELEMS * TRM_ALIGN_ELEMS; };
+    for (int u = 0; u < C; ++u) {
+        trm_cuda_utterance &d = desc[u];
+        d.n_frames = n_frames;
+        d.frame_offset = (long long)u * n_frames;
+        d.tube_offset = tube_at; d.out_offset = out_at; d.pcm_offset = pcm_at;
+        tube_at += up(d.n_tube); out_at += up(d.n_out); pcm_at += up(d.n_out * d.channels);
+    }
+    ChunkPlan plan;
+    int rc;
+    if ((rc = plan_chunk(desc.data(), 0, C, ki, plan)) != 0) return rc;
+    Arena &arena = ctx->arenas[0];
+    if ((rc = arena.reserve(plan.arena_bytes(esz, true) + (size_t)C * sizeof(unsigned long long) + 4096)) != 0) return rc;
+    DeviceChunk dc;
+    carve(arena, plan, esz, true, dc);
+    unsigned long long *d_sums = (unsigned long long *)arena.take((size_t)C * sizeof(unsigned long long));
+    cudaStream_t st = ctx->streams[2];
+    if ((rc = upload_plan(plan, dc, nullptr, st)) != 0) return rc;
+    std::vector<unsigned long long> mb((size_t)C);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    int64_t n_launch = 0, probe_at = 0;
+    double ms_total = 0.0;
+    for (int64_t at = 0; at < n; at += C) {
+        const int m = (int)std::min<int64_t>(C, n - at);
+        // (a short last chunk runs the full plan: the utterances beyond m keep the previous chunk's frames and are ignored)
+        CK(cudaEventRecord(e0, st));
+        if (trm_k_workload_walk2(seed, first_index + (uint64_t)at, m, n_frames, dc.frames, st) != 0) return fail_msg("walk2 launch");
+        for (int stage = 0; stage < TRM_STAGE_COUNT; ++stage)
+            if ((rc = launch_stage(ctx, precision, stage, dc, st)) != 0) return rc;
+        if (trm_k_pcm_checksum(dc.desc, m, dc.pcm, d_sums, st) != 0) return fail_msg("checksum launch");
+        CK(cudaEventRecord(e1, st));
+        n_launch += 5;
+        CK(cudaMemcpyAsync(checksums_host + at, d_sums, (size_t)m * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(mb.data(), dc.maxbits, (size_t)m * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        while (probe_at < n_probe && probe_utt[probe_at] < at + m) {
+            const int64_t k = probe_utt[probe_at] - at;
+            if (k >= 0) {
+                const trm_cuda_utterance &d = plan.desc[(size_t)k];
+                const int64_t cnt = std::min<int64_t>(d.n_out * d.channels, probe_stride);
+                CK(cudaMemcpyAsync(probe_pcm + probe_at * probe_stride, dc.pcm + d.pcm_offset, (size_t)cnt * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+            }
+            ++probe_at;
+        }
+        CK(cudaStreamSynchronize(st));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        ms_total += ms;
+        if (max_host)
+            for (int i = 0; i < m; ++i) memcpy(&max_host[at + i], &mb[(size_t)i], sizeof(double));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (launches) *launches = n_launch;
+    if (kernel_ms) *kernel_ms = ms_total;
+    return 0;
+}
+
+/* Output-rate samples (and PCM) of ONE utterance of a device-resident batch: what bench.py's in-run oracle check reads. */
+int trm_cuda_resident_fetch_utterance(trm_cuda_resident *r, int u, void *samples_host, int16_t *pcm_host, double *max_host)
+{
+    CK(cudaSetDevice(r->ctx->device));
+    CK(cudaDeviceSynchronize());
+    if (u < 0 || u >= (int)r->plan.desc.size()) return fail_msg("trm_cuda_resident_fetch_utterance: no such utterance");
+    const size_t esz = prec_esz(r->precision);
+    const trm_cuda_utterance &d = r->plan.desc[u];
+    if (samples_host && d.n_out) CK(cudaMemcpy(samples_host, (unsigned char *)r->dc.out + (size_t)d.out_offset * esz, (size_t)d.n_out * esz, cudaMemcpyDeviceToHost));
+    if (pcm_host && d.n_out) CK(cudaMemcpy(pcm_host, r->dc.pcm + d.pcm_offset, (size_t)d.n_out * d.channels * sizeof(int16_t), cudaMemcpyDeviceToHost));
+    if (max_host) {
+        unsigned long long mb = 0;
+        CK(cudaMemcpy(&mb, r->dc.maxbits + u, sizeof mb, cudaMemcpyDeviceToHost));
+        memcpy(max_host, &mb, sizeof(double));
+    }
+    return 0;
+}
+
+/* Pure copy traffic of one synthesis step, no kernels: `h2d_bytes` from pinned host memory up and `d2h_bytes` down, at the
+ * same time on two streams, `reps` times; *ms receives the average time of one repetition.  The ceiling the end-to-end
+ * number of a step with these byte counts can reach on this host / PCIe path (tools/pcie_ceiling.py, bench.py e2e.ceiling). */
+int trm_cuda_copy_probe(int device, const void *host_in, size_t h2d_bytes, void *host_out, size_t d2h_bytes, int reps, double *ms)
+{
+    CK(cudaSetDevice(device));
+    void *d_in = nullptr, *d_out = nullptr;
+    cudaStream_t s_up, s_down;
+    cudaEvent_t e0, e1, e2;
+    CK(cudaMalloc(&d_in, h2d_bytes ? h2d_bytes : 1));
+    CK(cudaMalloc(&d_out, d2h_bytes ? d2h_bytes : 1));
+    CK(cudaMemset(d_out, 0, d2h_bytes ? d2h_bytes : 1));
+    CK(cudaStreamCreateWithFlags(&s_up, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&s_down, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0, s_up));
+    CK(cudaStreamWaitEvent(s_down, e0, 0));
+    for (int r = 0; r < reps; ++r) {
+        if (h2d_bytes) CK(cudaMemcpyAsync(d_in, host_in, h2d_bytes, cudaMemcpyHostToDevice, s_up));
+        if (d2h_bytes) CK(cudaMemcpyAsync(host_out, d_out, d2h_bytes, cudaMemcpyDeviceToHost, s_down));
+    }
+    CK(cudaEventRecord(e1, s_up));
+    CK(cudaEventRecord(e2, s_down));
+    CK(cudaStreamSynchronize(s_up));
+    CK(cudaStreamSynchronize(s_down));
+    float a = 0, b = 0;
+    CK(cudaEventElapsedTime(&a, e0, e1));
+    CK(cudaEventElapsedTime(&b, e0, e2));
+    *ms = (double)(a > b ? a : b) / (reps > 0 ? reps : 1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    cudaStreamDestroy(s_up); cudaStreamDestroy(s_down);
+    cudaFree(d_in); cudaFree(d_out);
     return 0;
 }
 

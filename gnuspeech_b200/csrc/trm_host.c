@@ -755,6 +755,7 @@ struct TRMBatch {
     int64_t *pcm_offsets, *out_offsets, *tube_offsets;
     double *maxima;
     uint8_t *flush_bug;            /* per utterance: the reference would hit its converter flush bug (TRMReferenceFlushBug) */
+    int frame_format;              /* TRM_FRAMES_F64 / TRM_FRAMES_F32: how the `frames` argument of the synthesize calls is read */
     TRMBatchLayout layout;
     int64_t total_tube_elems;
     int64_t launches;
@@ -852,6 +853,12 @@ bad:
 }
 
 void TRMBatchGetLayout(const TRMBatch *b, TRMBatchLayout *l) { *l = b->layout; }
+int TRMBatchSetFrameFormat(TRMBatch *b, int format)
+{
+    if (format != TRM_FRAMES_F64 && format != TRM_FRAMES_F32) return set_err(TRM_ERR_PARAM, "unknown frame format%s", "");
+    b->frame_format = format;
+    return TRM_OK;
+}
 const int32_t *TRMBatchNumberSamples(const TRMBatch *b) { return b->numberSamples; }
 const int64_t *TRMBatchPCMOffsets(const TRMBatch *b) { return b->pcm_offsets; }
 const int64_t *TRMBatchOutOffsets(const TRMBatch *b) { return b->out_offsets; }
@@ -881,9 +888,9 @@ static void *shard_main(void *arg)
     j->rc = acquire_ctx(j->device, &ctx, &lane);
     if (j->rc == TRM_OK) {
         if (trm_cuda_set_wavetables(ctx, j->b->voices.tables, j->b->voices.n) != 0 ||
-            trm_cuda_synthesize_host_ex(ctx, j->b->precision, j->u1 - j->u0, j->b->desc + j->u0, (const double *)j->frames,
-                                        j->pcm, j->samples, j->b->maxima + j->u0, j->tube, &j->launches, j->enqueued,
-                                        j->enqueued_arg) != 0)
+            trm_cuda_synthesize_host_fmt(ctx, j->b->precision, j->b->frame_format, j->u1 - j->u0, j->b->desc + j->u0, j->frames,
+                                         j->pcm, j->samples, j->b->maxima + j->u0, j->tube, &j->launches, j->enqueued,
+                                         j->enqueued_arg) != 0)
             j->rc = cuda_err();
         release_ctx(j->device, lane);
     }
@@ -968,6 +975,31 @@ int TRMBatchSynthesize(TRMBatch *b, const TRMParameters *frames, int16_t *pcm_ou
                        const int *devices, int n_devices)
 {
     return batch_run(b, frames, pcm_out, samples_out, NULL, devices, n_devices, NULL);
+}
+
+/* ---- sweeps over device-generated tracks (BASELINE configs[4]) ---- */
+int TRMSweepSynthesize(const TRMInputParameters *ip, int32_t n_frames, uint64_t seed, uint64_t first_index, int64_t n,
+                       int precision, int device, uint64_t *checksums, double *maxima, int64_t n_probe, const int64_t *probe_utt,
+                       int16_t *probe_pcm, int64_t probe_stride, int32_t *numberSamples, int64_t *launches, double *kernel_ms)
+{
+    if (!ip || n < 0 || n_frames < 0 || !precision_ok(precision) || !checksums) return set_err(TRM_ERR_PARAM, "bad sweep arguments%s", "");
+    voice_set vs;
+    memset(&vs, 0, sizeof vs);
+    trm_cuda_utterance d;
+    int rc = describe(ip, n_frames, &vs, &d, NULL);
+    if (rc) { voice_set_free(&vs); return rc; }
+    if (numberSamples) *numberSamples = (int32_t)d.n_out;
+    if (n == 0) { voice_set_free(&vs); return TRM_OK; }
+    trm_cuda_ctx *ctx;
+    int lane = 0;
+    if ((rc = acquire_ctx(device, &ctx, &lane)) != TRM_OK) { voice_set_free(&vs); return rc; }
+    if (trm_cuda_set_wavetables(ctx, vs.tables, vs.n) != 0 ||
+        trm_cuda_sweep(ctx, precision, &d, n_frames, seed, first_index, n, checksums, maxima, n_probe, probe_utt, probe_pcm,
+                       probe_stride, launches, kernel_ms) != 0)
+        rc = cuda_err();
+    release_ctx(device, lane);
+    voice_set_free(&vs);
+    return rc;
 }
 
 /* ---- control frames from event lists (EventList.m:883-1061) ---- */
@@ -1219,6 +1251,14 @@ int TRMResidentRunStage(TRMResident *r, int stage, void *cuda_stream)
     return trm_cuda_resident_stage(r->res, stage, cuda_stream) ? cuda_err() : TRM_OK;
 }
 int TRMResidentRun(TRMResident *r, void *cuda_stream) { return trm_cuda_resident_run(r->res, cuda_stream) ? cuda_err() : TRM_OK; }
+int TRMResidentFetchUtterance(TRMResident *r, int u, void *samples, int16_t *pcm, double *maximum)
+{
+    return trm_cuda_resident_fetch_utterance(r->res, u, samples, pcm, maximum) ? cuda_err() : TRM_OK;
+}
+int TRMCopyProbe(int device, const void *host_in, size_t h2d_bytes, void *host_out, size_t d2h_bytes, int reps, double *ms)
+{
+    return trm_cuda_copy_probe(device, host_in, h2d_bytes, host_out, d2h_bytes, reps, ms) ? cuda_err() : TRM_OK;
+}
 int TRMResidentFetch(TRMResident *r, int16_t *pcm, void *samples, double *maxima, void *tube)
 {
     return trm_cuda_resident_fetch(r->res, pcm, samples, maxima, tube) ? cuda_err() : TRM_OK;

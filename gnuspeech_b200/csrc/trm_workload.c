@@ -68,6 +68,34 @@ void TRMWorkloadRandomWalk(uint64_t seed, uint64_t index, size_t n_frames, TRMPa
     }
 }
 
+/* walk2: see include/trm_workload.h.  Every operation below is one IEEE double operation in a fixed order (this file is
+ * compiled with -ffp-contract=off); workload_walk2_kernel performs the same sequence with __dadd_rn / __dmul_rn. */
+void TRMWorkloadWalk2(uint64_t seed, uint64_t index, size_t n_frames, TRMParameters *out)
+{
+    for (int q = 0; q < 16; q++) {
+        uint64_t s = seed * 0xD1342543DE82EF95ull + index * 0x9E3779B97F4A7C15ull + (uint64_t)q * 0xC2B2AE3D27D4EB4Full + 0x632BE59BD9B4E019ull;
+        splitmix64(&s);
+        const double lo = k_lo[q], hi = k_hi[q], range = hi - lo;
+        const double step = (range * 1.7320508075688772) * 0.02;
+        double x = lo + range * uniform01(&s);
+        for (size_t i = 0; i < n_frames; i++) {
+            if (i > 0 && range > 0) {
+                double g = uniform01(&s);
+                g = g + uniform01(&s);
+                g = g + uniform01(&s);
+                g = g + uniform01(&s);
+                g = g - 2.0;
+                x = x + g * step;
+                for (int it = 0; it < 4 && (x < lo || x > hi); it++) {
+                    if (x < lo) x = 2 * lo - x;
+                    if (x > hi) x = 2 * hi - x;
+                }
+            }
+            ((double *)&out[i])[q] = as_float(x);
+        }
+    }
+}
+
 typedef struct { uint64_t seed, first; size_t n, n_frames, t, nt; TRMParameters *out; } walk_job;
 static void *walk_main(void *arg)
 {

@@ -229,6 +229,12 @@ TRMBatch *TRMBatchCreate(int n_utterances, const TRMInputParameters *ip, int sha
                          const int64_t *frame_offset, const int32_t *n_frames, int precision, int *err);
 void      TRMBatchFree(TRMBatch *batch);
 void      TRMBatchGetLayout(const TRMBatch *batch, TRMBatchLayout *layout);
+/* How the `frames` argument of TRMBatchSynthesize / TRMBatchSynthesizeAsync is read: TRMParameters rows (16 doubles,
+ * the default) or rows of 16 floats in the same order.  Monet's frame generator holds its table in float
+ * (EventList.m:968-1002) and TRMParameters only widens it, so float rows carry the same information in half the
+ * bytes across PCIe; they are widened on the device and the results are bit-identical. */
+enum { TRM_FRAMES_F64 = 0, TRM_FRAMES_F32 = 1 };
+int       TRMBatchSetFrameFormat(TRMBatch *batch, int format);
 /* per-utterance results / placement; valid after TRMBatchCreate (offsets, counts) and after synthesis (max) */
 const int32_t *TRMBatchNumberSamples(const TRMBatch *batch);       /* [n] output frames                   */
 const int64_t *TRMBatchPCMOffsets(const TRMBatch *batch);          /* [n] element offset into pcm_out     */
@@ -305,6 +311,19 @@ int64_t TRMStreamCapacity(const TRMStream *stream);
 int TRMStreamPush(TRMStream *stream, const TRMParameters *frames, int m, int flush, void *samples_out, int64_t *n_samples);
 void TRMStreamFree(TRMStream *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Sweeps (BASELINE configs[4]: 10^6 synthetic 2 s utterances): n utterances of one voice whose control tracks are the walk2
+ * workload of include/trm_workload.h, generated on the device (utterance k = index first_index + k of stream `seed`) --
+ * 64 GB of frames per million utterances never cross PCIe.  The audio stays on the device as well: per utterance an
+ * 8-byte checksum of its PCM16, sum(pcm[i] * (2 i + 1)) mod 2^64, and its maximumSampleValue come back (checksums equal
+ * across any sharding of the index range); the PCM of the utterances listed in probe_utt (sorted, relative to this call)
+ * is copied to probe_pcm (rows of probe_stride int16) for comparison with the reference.  *numberSamples: output frames per
+ * utterance; *kernel_ms: device time of all chunks.
+ * ------------------------------------------------------------------------------------------- */
+int TRMSweepSynthesize(const TRMInputParameters *ip, int32_t n_frames, uint64_t seed, uint64_t first_index, int64_t n,
+                       int precision, int device, uint64_t *checksums, double *maxima, int64_t n_probe, const int64_t *probe_utt,
+                       int16_t *probe_pcm, int64_t probe_stride, int32_t *numberSamples, int64_t *launches, double *kernel_ms);
+
 /* Debug / conformance variant on one device: additionally returns the tube-rate signal (what -synthesize
  * hands to dataFill:, TRMTubeModel.m:346) in the batch's arithmetic type; TRMBatchTubeElements() elements,
  * utterance u at TRMBatchTubeOffsets()[u]. */
@@ -322,7 +341,14 @@ TRMResident *TRMBatchMakeResident(TRMBatch *batch, const TRMParameters *frames, 
 int  TRMResidentRunStage(TRMResident *r, int stage, void *cuda_stream);
 int  TRMResidentRun(TRMResident *r, void *cuda_stream);
 int  TRMResidentFetch(TRMResident *r, int16_t *pcm_out, void *samples_out, double *maxima, void *tube_out);
+/* one utterance of the resident batch: numberSamples output-rate samples, its PCM, its maximum (any may be NULL) */
+int  TRMResidentFetchUtterance(TRMResident *r, int utterance, void *samples_out, int16_t *pcm_out, double *maximum);
 void TRMResidentFree(TRMResident *r);
+
+/* Copy-only probe (measurement aid): h2d_bytes from host_in to the device and d2h_bytes from the device to host_out at the
+ * same time, `reps` times, no kernels; *ms = average time of one repetition.  With a step's byte counts this is the ceiling
+ * the host / PCIe path sets for the end-to-end throughput of that step (bench.py e2e.ceiling, tools/pcie_ceiling.py). */
+int TRMCopyProbe(int device, const void *host_in, size_t h2d_bytes, void *host_out, size_t d2h_bytes, int reps, double *ms);
 
 /* Pinned host memory for the batch buffers. */
 void *TRMHostAlloc(size_t bytes);

@@ -132,6 +132,14 @@ int trm_cuda_synthesize_host_ex(trm_cuda_ctx *ctx, int precision, int n, const t
                                 double *max_host, void *tube_host, int64_t *launches,
                                 void (*enqueued)(void *), void *arg);
 
+/* The same call with the frame format given: 0 = TRMParameters rows of 16 doubles (128 bytes), 1 = rows of 16 floats
+ * (64 bytes; what Monet's generator holds, EventList.m:968-1002) widened to double on the device -- half the upload,
+ * identical results. */
+int trm_cuda_synthesize_host_fmt(trm_cuda_ctx *ctx, int precision, int frame_format, int n, const trm_cuda_utterance *desc,
+                                 const void *frames_host, int16_t *pcm_host, void *samples_host,
+                                 double *max_host, void *tube_host, int64_t *launches,
+                                 void (*enqueued)(void *), void *arg);
+
 /*
  * Device-resident path (bench `value`, roofline timing): inputs uploaded once, stages launched on the
  * caller's stream (a cudaStream_t passed as void*, NULL = the legacy default stream) without any
@@ -144,7 +152,20 @@ int  trm_cuda_resident_stage(trm_cuda_resident *res, int stage, void *stream);  
 int  trm_cuda_resident_run(trm_cuda_resident *res, void *stream);                /* all stages, in order  */
 int  trm_cuda_resident_fetch(trm_cuda_resident *res, int16_t *pcm_host, void *samples_host,
                              double *max_host, void *tube_host);                 /* blocking D2H          */
+int  trm_cuda_resident_fetch_utterance(trm_cuda_resident *res, int u, void *samples_host, int16_t *pcm_host,
+                                       double *max_host);                        /* one utterance, blocking */
 int  trm_cuda_stage_launches(int stage);     /* kernel launches one stage issues */
+/* Sweep (BASELINE configs[4]): n utterances of one voice x n_frames frames, control tracks = the walk2 workload
+ * (include/trm_workload.h) generated on the device (utterance k: index first_index + k of stream seed), synthesized in
+ * chunks of one full wave; per utterance an 8-byte PCM checksum sum(pcm[i] * (2 i + 1)) mod 2^64 and the maximum come back,
+ * plus the PCM of the utterances listed in probe_utt (sorted; rows of probe_stride int16).  kernel_ms: device time of
+ * all chunks (CUDA events around generator + 3 stages + checksum). */
+int  trm_cuda_sweep(trm_cuda_ctx *ctx, int precision, const trm_cuda_utterance *voice, int32_t n_frames, uint64_t seed,
+                    uint64_t first_index, int64_t n, uint64_t *checksums_host, double *max_host, int64_t n_probe,
+                    const int64_t *probe_utt, int16_t *probe_pcm, int64_t probe_stride, int64_t *launches, double *kernel_ms);
+/* Copy-only probe: h2d_bytes up and d2h_bytes down concurrently, `reps` times; *ms = average per repetition. */
+int  trm_cuda_copy_probe(int device, const void *host_in, size_t h2d_bytes, void *host_out, size_t d2h_bytes, int reps,
+                         double *ms);
 
 /*
  * Streaming synthesis (TRAcT-style, Applications/TRAcT/tube.c:1096-1191: output as it is produced, no normalisation):

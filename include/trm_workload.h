@@ -24,6 +24,13 @@ void TRMWorkloadStaticVowel(int posture, double pitch, size_t n_frames, TRMParam
  * fricCF 864..5500, fricBW 500..4500, r1 = 0.8, r2..r8 0.05..2.61, velum 0.1..1.5. */
 void TRMWorkloadRandomWalk(uint64_t seed, uint64_t index, size_t n_frames, TRMParameters *out);
 
+/* Config 5 (10^6 utterances: the tracks cannot cross PCIe, they are generated where they are consumed): the same bounded
+ * reflecting walk with ranges as above, defined so that the host and a GPU kernel produce IDENTICAL bits -- one SplitMix64
+ * stream per (seed, utterance index, parameter), steps = (u1 + u2 + u3 + u4 - 2) * sqrt(3) * range / 50 (Irwin-Hall, unit
+ * variance) instead of Box-Muller: only IEEE additions and multiplications, no libm.  The device twin is
+ * workload_walk2_kernel (kernels_aux.cu, no FMA contraction); tests/test_gpu_sweep.py compares them bit for bit. */
+void TRMWorkloadWalk2(uint64_t seed, uint64_t index, size_t n_frames, TRMParameters *out);
+
 /* n utterances of n_frames frames each, written back to back; uses n_threads host threads. */
 void TRMWorkloadRandomWalkBatch(uint64_t seed, uint64_t first_index, size_t n, size_t n_frames, TRMParameters *out,
                                 int n_threads);
