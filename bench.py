@@ -481,7 +481,7 @@ def main():
             h2d = int(lay.total_frames) * 64
             d2h = int(lay.out_samples) * 2
             e2e = {"unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-                   "frame_format": "float32 rows (TRM_FRAMES_F32), widened on the device; bit-identical to double rows",
+                   "frame_format": "float32 rows (TRM_FRAMES_F32), widened by the waveguide kernel when read; bit-identical to double rows",
                    "gpu_launches_per_step": int(batches[0].kernelLaunches),
                    "blocking": {"value": audio_all / (dt_block / steps), "ms_per_step": 1e3 * dt_block / steps,
                                 "api": "TRMBatchSynthesize, one blocking call per step"}}

@@ -48,7 +48,8 @@ struct TubeArgs {
     const trm_cuda_utterance *desc;
     const int *order;            // slot -> utterance (longest first), may be null
     int n_utt;
-    const double *frames;        // [frame][16]
+    const void *frames;          // [frame][16] doubles, or floats when frames_f32
+    int frames_f32;
     void *tube;                  // Real[...]
     const double *wavetables;    // [voice][512]
     uint64_t noise_k0;

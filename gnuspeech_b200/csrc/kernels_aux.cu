@@ -10,31 +10,6 @@ extern "C" int trm_k_framegen(const trm::FrameGenArgs *a, cudaStream_t s)
     return (int)cudaGetLastError();
 }
 
-// float32 control frames (64 bytes per frame, what Monet's generator produces: EventList.m:968-1002 keeps the table in
-// float) widened to the double rows the waveguide kernel stages: frames f_begin .. f_begin + f_count of n_utt utterances
-// whose rows are pitch frames apart.  Exact (float -> double), so results are bit-identical to uploading doubles.
-__global__ void widen_frames_kernel(const float *__restrict__ src, double *__restrict__ dst, long long n_utt, long long pitch,
-                                    long long f_begin, long long f_count)
-{
-    const long long per = f_count * 16, total = n_utt * per;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long u = i / per, r = i - u * per;
-        const long long at = (u * pitch + f_begin) * 16 + r;
-        dst[at] = (double)src[at];
-    }
-}
-
-extern "C" int trm_k_widen_frames(const float *src, double *dst, long long n_utt, long long pitch, long long f_begin,
-                                  long long f_count, cudaStream_t s)
-{
-    const long long total = n_utt * f_count * 16;
-    if (total <= 0) return 0;
-    const int threads = 256;
-    const long long want = (total + threads - 1) / threads;
-    widen_frames_kernel<<<(unsigned)(want < 148 * 16 ? want : 148 * 16), threads, 0, s>>>(src, dst, n_utt, pitch, f_begin, f_count);
-    return (int)cudaGetLastError();
-}
-
 // ---- config 5: control tracks generated on the device (include/trm_workload.h TRMWorkloadWalk2, bit-identical) -----------
 __device__ __forceinline__ unsigned long long w2_splitmix(unsigned long long &s)
 {

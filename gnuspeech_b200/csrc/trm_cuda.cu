@@ -30,7 +30,6 @@ TRM_DECLARE_LAUNCHERS(f64)
 TRM_DECLARE_LAUNCHERS(f32)
 TRM_DECLARE_LAUNCHERS(f64s)
 int trm_k_framegen(const trm::FrameGenArgs *, cudaStream_t);
-int trm_k_widen_frames(const float *, double *, long long, long long, long long, long long, cudaStream_t);
 int trm_k_workload_walk2(unsigned long long, unsigned long long, long long, int, double *, cudaStream_t);
 int trm_k_pcm_checksum(const trm_cuda_utterance *, int, const int16_t *, unsigned long long *, cudaStream_t);
 }
@@ -150,8 +149,8 @@ struct DeviceChunk {
     int *tile_utt = nullptr, *tile_nt = nullptr;
     long long *tile_max_out = nullptr, *tile_first_out = nullptr, *item_base = nullptr;
     unsigned long long *maxbits = nullptr;
-    double *frames = nullptr;
-    float *frames32 = nullptr;              // float32 frames as uploaded (frame format 1), widened into `frames` on the device
+    double *frames = nullptr;               // (holds float32 rows when the plan says f32_frames: the kernels widen on read)
+    bool f32_frames = false;
     void *tube = nullptr, *out = nullptr;
     int16_t *pcm = nullptr;
     long long total_items = 0, max_n_out = 0;
@@ -203,7 +202,6 @@ struct ChunkPlan {
         add(item_base.size() * sizeof(long long));
         add(n * sizeof(unsigned long long));
         add(frame_rows * 128);
-        if (f32_frames) add(frame_rows * 64);
         add(tube_elems * esz);
         add(out_elems * esz);
         if (want_pcm) add(pcm_elems * sizeof(int16_t));
@@ -447,7 +445,7 @@ void carve(Arena &a, const ChunkPlan &p, size_t esz, bool want_pcm, DeviceChunk 
     dc.item_base = (long long *)a.take(p.item_base.size() * sizeof(long long));
     dc.maxbits = (unsigned long long *)a.take(n * sizeof(unsigned long long));
     dc.frames = (double *)a.take(p.frame_rows * 128);
-    dc.frames32 = p.f32_frames ? (float *)a.take(p.frame_rows * 64) : nullptr;
+    dc.f32_frames = p.f32_frames;
     dc.tube = a.take(p.tube_elems * esz);
     dc.out = a.take(p.out_elems * esz);
     dc.pcm = want_pcm ? (int16_t *)a.take(p.pcm_elems * sizeof(int16_t)) : nullptr;
@@ -511,8 +509,8 @@ int upload_frames(const ChunkPlan &p, const DeviceChunk &dc, const trm_cuda_utte
                   const void *frames_host, cudaStream_t s)
 {
     if (p.frame_rows == 0) return 0;
-    const size_t row = p.f32_frames ? 64 : 128;                     // bytes per frame in the caller's array
-    unsigned char *dst = p.f32_frames ? (unsigned char *)dc.frames32 : (unsigned char *)dc.frames;
+    const size_t row = p.f32_frames ? 64 : 128;                     // bytes per frame in the caller's array and on the device
+    unsigned char *dst = (unsigned char *)dc.frames;
     const unsigned char *src = (const unsigned char *)frames_host;
     if (p.frames_dense) {
         CK(cudaMemcpyAsync(dst, src + (size_t)p.frames_lo * row, p.frame_rows * row, cudaMemcpyDefault, s));
@@ -522,10 +520,6 @@ int upload_frames(const ChunkPlan &p, const DeviceChunk &dc, const trm_cuda_utte
             CK(cudaMemcpyAsync(dst + (size_t)p.desc[i].frame_offset * row, src + (size_t)g.frame_offset * row,
                                (size_t)g.n_frames * row, cudaMemcpyDefault, s));
         }
-    }
-    if (p.f32_frames) {
-        const int rc = trm_k_widen_frames(dc.frames32, dc.frames, 1, (long long)p.frame_rows, 0, (long long)p.frame_rows, s);
-        if (rc != 0) return fail("widen_frames_kernel launch", (cudaError_t)rc);
     }
     return 0;
 }
@@ -555,7 +549,7 @@ int launch_stage(trm_cuda_ctx *ctx, int precision, int stage, const DeviceChunk 
     int rc = 0;
     if (stage == TRM_STAGE_TUBE) {
         trm::TubeArgs a{};
-        a.desc = dc.desc; a.order = dc.order; a.n_utt = dc.n; a.frames = dc.frames; a.tube = dc.tube;
+        a.desc = dc.desc; a.order = dc.order; a.n_utt = dc.n; a.frames = dc.frames; a.frames_f32 = dc.f32_frames ? 1 : 0; a.tube = dc.tube;
         a.wavetables = dc.wavetables ? dc.wavetables : ctx->d_wavetables; a.noise_k0 = ctx->noise_k0;
         if (time_part >= 0) { a.desc = dc.desc_t[time_part]; a.state = dc.state; }     // (lane-per-utterance mapping only)
         const trm::KernelInfo &ki = ctx->ki(precision);
@@ -929,23 +923,14 @@ int trm_cuda_synthesize_host_fmt(trm_cuda_ctx *ctx, int precision, int frame_for
                 RCD(upload_frames(p, dc, desc, frames_host, s_in));
                 CKD(cudaEventRecord(ctx->ev_in[slot], s_in));
             } else {
-                // frames [0, f1] of every utterance, then the rest: two strided copies (float32 rows are widened on the device)
+                // frames [0, f1] of every utterance, then the rest: two strided copies
                 const size_t row = f32_frames ? 64 : 128;
                 const size_t pitch = (size_t)p.uniform_frames * row, first = (size_t)(p.split_frame + 1) * row;
                 const unsigned char *src = (const unsigned char *)frames_host + (size_t)p.frames_lo * row;
-                unsigned char *dst = f32_frames ? (unsigned char *)dc.frames32 : (unsigned char *)dc.frames;
+                unsigned char *dst = (unsigned char *)dc.frames;
                 CKD(cudaMemcpy2DAsync(dst, pitch, src, pitch, first, (size_t)(u1 - u0), cudaMemcpyDefault, s_in));
-                if (f32_frames && trm_k_widen_frames(dc.frames32, dc.frames, u1 - u0, p.uniform_frames, 0, p.split_frame + 1, s_in) != 0) {
-                    drain();
-                    return fail_msg("widen_frames_kernel launch");
-                }
                 CKD(cudaEventRecord(ctx->ev_in[slot], s_in));
                 CKD(cudaMemcpy2DAsync(dst + first, pitch, src + first, pitch, pitch - first, (size_t)(u1 - u0), cudaMemcpyDefault, s_in));
-                if (f32_frames && trm_k_widen_frames(dc.frames32, dc.frames, u1 - u0, p.uniform_frames, p.split_frame + 1,
-                                                     p.uniform_frames - p.split_frame - 1, s_in) != 0) {
-                    drain();
-                    return fail_msg("widen_frames_kernel launch");
-                }
                 CKD(cudaEventRecord(ctx->ev_in2[slot], s_in));
             }
             mark(s_in);

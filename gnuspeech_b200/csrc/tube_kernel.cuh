@@ -299,7 +299,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) tube_kernel(TubeArgs ar
     if (n_warp <= 0) return;
     const int n_frames = D->n_frames;
     const int cp = D->controlPeriod;
-    const double *__restrict__ F = args.frames + D->frame_offset * 16;
+    // control frames: rows of 16 doubles (128 bytes) or, when the caller gave float32 rows, of 16 floats (64 bytes) --
+    // staged as they are and widened when a parameter lane reads its value (exact)
+    const uint32_t frow = args.frames_f32 ? 64u : 128u;
+    const unsigned char *__restrict__ F = reinterpret_cast<const unsigned char *>(args.frames) + (size_t)D->frame_offset * frow;
+    auto staged = [&](int buf, int row) -> double {
+        return args.frames_f32 ? (double)reinterpret_cast<const float *>(&S.FR[buf][0][0])[row * 16 + hl] : S.FR[buf][row][hl];
+    };
     R *__restrict__ out = reinterpret_cast<R *>(args.tube) + D->tube_offset;
     const double *__restrict__ wt_base = args.wavetables + (size_t)D->voice * TRM_TABLE_LENGTH;
 
@@ -363,15 +369,15 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) tube_kernel(TubeArgs ar
     if (hl == 0 && feeds) {
         for (int c = 0; c < 2 && c < n_chunks; ++c) {
             int cnt = min(FRAME_CHUNK, n_frames - c * FRAME_CHUNK);
-            mbar_expect_tx(&S.mbar[c], (uint32_t)cnt * 128u);
-            tma_bulk_g2s(&S.FR[c][0][0], F + (size_t)c * FRAME_CHUNK * 16, (uint32_t)cnt * 128u, &S.mbar[c]);
+            mbar_expect_tx(&S.mbar[c], (uint32_t)cnt * frow);
+            tma_bulk_g2s(&S.FR[c][0][0], F + (size_t)c * FRAME_CHUNK * frow, (uint32_t)cnt * frow, &S.mbar[c]);
         }
     }
     if (feeds) mbar_wait(&S.mbar[0], 0);
 
     // ---- running state ---------------------------------------------------------------------------
     // parameter lane p = hl (TRMTubeModel.m:611-688)
-    double p_cur = 0.0, p_delta = 0.0, p_next = feeds ? S.FR[0][0][hl] : 0.0;
+    double p_cur = 0.0, p_delta = 0.0, p_next = feeds ? staged(0, 0) : 0.0;
     int f_idx = 0, jc = 0;                 // current interval, sample inside it
     // oscillator position (all lanes carry the same value)
     double pos = 0.0;
@@ -404,7 +410,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) tube_kernel(TubeArgs ar
                     refill = ch + 1;
                     mbar_wait(&S.mbar[ch & 1], (uint32_t)((ch >> 1) & 1));
                 }
-                const double nxt = S.FR[ch & 1][fn % FRAME_CHUNK][hl];
+                const double nxt = staged(ch & 1, fn % FRAME_CHUNK);
                 p_cur = p_next;
                 p_delta = (nxt - p_cur) / (double)cp;
                 p_next = nxt;
@@ -422,8 +428,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) tube_kernel(TubeArgs ar
         if (hl == 0 && refill >= 0 && refill < n_chunks) {
             // every lane is past its last read of chunk refill-2, whose buffer is refilled now
             const int cnt = min(FRAME_CHUNK, n_frames - refill * FRAME_CHUNK);
-            mbar_expect_tx(&S.mbar[refill & 1], (uint32_t)cnt * 128u);
-            tma_bulk_g2s(&S.FR[refill & 1][0][0], F + (size_t)refill * FRAME_CHUNK * 16, (uint32_t)cnt * 128u,
+            mbar_expect_tx(&S.mbar[refill & 1], (uint32_t)cnt * frow);
+            tma_bulk_g2s(&S.FR[refill & 1][0][0], F + (size_t)refill * FRAME_CHUNK * frow, (uint32_t)cnt * frow,
                          &S.mbar[refill & 1]);
         }
 

@@ -664,7 +664,13 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
     const int64_t n_tube = D->n_tube;
     const int n_frames = D->n_frames;
     const int cp = D->controlPeriod;
-    const double *__restrict__ F = args.frames + D->frame_offset * 16;
+    // control frames: rows of 16 doubles (128 bytes) or, when the caller gave float32 rows, of 16 floats (64 bytes) --
+    // staged as they are and widened when a parameter lane reads its value (exact)
+    const uint32_t frow = args.frames_f32 ? 64u : 128u;
+    const unsigned char *__restrict__ F = reinterpret_cast<const unsigned char *>(args.frames) + (size_t)D->frame_offset * frow;
+    auto staged = [&](int buf, int row) -> double {
+        return args.frames_f32 ? (double)reinterpret_cast<const float *>(&S.FR[buf][0][0])[row * 16 + hl] : S.FR[buf][row][hl];
+    };
     const double *__restrict__ wt_base = args.wavetables + (size_t)D->voice * TRM_TABLE_LENGTH;
     const bool pulse_wave = D->waveform == 0;
     const bool modulation = D->usesModulation != 0;
@@ -687,13 +693,13 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
     if (hl == 0 && feeds) {
         for (int c = 0; c < 2 && c < n_chunks; ++c) {
             int cnt = min(FRAME_CHUNK, n_frames - c * FRAME_CHUNK);
-            mbar_expect_tx(&S.mbar[c], (uint32_t)cnt * 128u);
-            tma_bulk_g2s(&S.FR[c][0][0], F + (size_t)c * FRAME_CHUNK * 16, (uint32_t)cnt * 128u, &S.mbar[c]);
+            mbar_expect_tx(&S.mbar[c], (uint32_t)cnt * frow);
+            tma_bulk_g2s(&S.FR[c][0][0], F + (size_t)c * FRAME_CHUNK * frow, (uint32_t)cnt * frow, &S.mbar[c]);
         }
     }
     if (feeds) mbar_wait(&S.mbar[0], 0);
 
-    double p_cur = 0.0, p_delta = 0.0, p_next = feeds ? S.FR[0][0][hl] : 0.0;
+    double p_cur = 0.0, p_delta = 0.0, p_next = feeds ? staged(0, 0) : 0.0;
     int f_idx = 0, jc = 0;
     double pos = 0.0;
     unsigned long long pos_fx = 0ull;
@@ -741,7 +747,7 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
     };
     if (feeds && D->jc0 > 0 && n_frames > 1) {
         // the call starts inside a control interval: redo its jc0 interpolation adds (exactly the reference's sequence)
-        const double nxt = S.FR[0][1][hl];
+        const double nxt = staged(0, 1);
         p_cur = p_next;
         p_delta = (nxt - p_cur) / (double)cp;
         p_next = nxt;
@@ -810,7 +816,7 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
                     mbar_wait(&S.mbar[ch & 1], (uint32_t)((ch >> 1) & 1));
                 }
                 TPHX(9);
-                const double nxt = S.FR[ch & 1][fn % FRAME_CHUNK][hl];
+                const double nxt = staged(ch & 1, fn % FRAME_CHUNK);
                 np = p_next;
                 nd = (nxt - np) / (double)cp;
                 p_next = nxt;
@@ -860,7 +866,7 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
                         refill = ch + 1;
                         mbar_wait(&S.mbar[ch & 1], (uint32_t)((ch >> 1) & 1));
                     }
-                    const double nxt = S.FR[ch & 1][fn % FRAME_CHUNK][hl];
+                    const double nxt = staged(ch & 1, fn % FRAME_CHUNK);
                     p_cur = p_next;
                     p_delta = (nxt - p_cur) / (double)cp;
                     p_next = nxt;
@@ -884,8 +890,8 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
         __syncwarp(FULL);
         if (hl == 0 && refill >= 0 && refill < n_chunks) {
             const int cnt = min(FRAME_CHUNK, n_frames - refill * FRAME_CHUNK);
-            mbar_expect_tx(&S.mbar[refill & 1], (uint32_t)cnt * 128u);
-            tma_bulk_g2s(&S.FR[refill & 1][0][0], F + (size_t)refill * FRAME_CHUNK * 16, (uint32_t)cnt * 128u, &S.mbar[refill & 1]);
+            mbar_expect_tx(&S.mbar[refill & 1], (uint32_t)cnt * frow);
+            tma_bulk_g2s(&S.FR[refill & 1][0][0], F + (size_t)refill * FRAME_CHUNK * frow, (uint32_t)cnt * frow, &S.mbar[refill & 1]);
         }
 
         TPH(1);

@@ -232,7 +232,7 @@ void      TRMBatchGetLayout(const TRMBatch *batch, TRMBatchLayout *layout);
 /* How the `frames` argument of TRMBatchSynthesize / TRMBatchSynthesizeAsync is read: TRMParameters rows (16 doubles,
  * the default) or rows of 16 floats in the same order.  Monet's frame generator holds its table in float
  * (EventList.m:968-1002) and TRMParameters only widens it, so float rows carry the same information in half the
- * bytes across PCIe; they are widened on the device and the results are bit-identical. */
+ * bytes across PCIe; the waveguide kernel widens them when it reads them and the results are bit-identical. */
 enum { TRM_FRAMES_F64 = 0, TRM_FRAMES_F32 = 1 };
 int       TRMBatchSetFrameFormat(TRMBatch *batch, int format);
 /* per-utterance results / placement; valid after TRMBatchCreate (offsets, counts) and after synthesis (max) */

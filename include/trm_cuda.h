@@ -133,8 +133,8 @@ int trm_cuda_synthesize_host_ex(trm_cuda_ctx *ctx, int precision, int n, const t
                                 void (*enqueued)(void *), void *arg);
 
 /* The same call with the frame format given: 0 = TRMParameters rows of 16 doubles (128 bytes), 1 = rows of 16 floats
- * (64 bytes; what Monet's generator holds, EventList.m:968-1002) widened to double on the device -- half the upload,
- * identical results. */
+ * (64 bytes; what Monet's generator holds, EventList.m:968-1002), staged as they are and widened by the waveguide kernel
+ * when a parameter lane reads its value -- half the upload, identical results. */
 int trm_cuda_synthesize_host_fmt(trm_cuda_ctx *ctx, int precision, int frame_format, int n, const trm_cuda_utterance *desc,
                                  const void *frames_host, int16_t *pcm_host, void *samples_host,
                                  double *max_host, void *tube_host, int64_t *launches,
