@@ -491,21 +491,14 @@ __device__ __forceinline__ void wide_recurrence_warp(WideSmem<R> &W, const WideA
             // which is (a + k e) d and (b + k e) d of TRMTubeModel.m:796-829 with one rounding placed differently.
             // Record of one sample (feed-forward warps, below):
             //   {kd0,kd1} {kd2,aL d} {kd4,kd6} {kd7,kd8} {k9,kd10} {aU d,FC1} {FC2,FC3} {FC4,FC5} {FC6,FC7} {FC8,2g} {2b,in} {ff,thr}
-            enum { K_TB1, K_GAIN, K_MA10, K_MB11, K_MA20, K_MA21, K_MB21, K_NA10, K_NB11, K_NA20, K_NA21, K_NB21,
-                   K_NK0, K_NK1, K_NK2, K_NK3, K_NK4 };
-            {
-                double (*kc)[32] = W.kc;
-                kc[K_TB1][lane] = D->tb1; kc[K_GAIN][lane] = D->throatGain;
-                kc[K_MA10][lane] = D->mouth[0]; kc[K_MB11][lane] = D->mouth[1]; kc[K_MA20][lane] = D->mouth[2];
-                kc[K_MA21][lane] = D->mouth[3]; kc[K_MB21][lane] = D->mouth[4];
-                kc[K_NA10][lane] = D->nose[0]; kc[K_NB11][lane] = D->nose[1]; kc[K_NA20][lane] = D->nose[2];
-                kc[K_NA21][lane] = D->nose[3]; kc[K_NB21][lane] = D->nose[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) kc[K_NK0 + q][lane] = D->nasal_coeff[q] * D->dampingFactor;   // constant junctions: kd
-                kc[K_NK4][lane] = D->nasal_coeff[4];
-            }
-            __syncwarp(FULL);
-#define KC(i) (W.kc[i][lane])
+            // Per-utterance constants live in registers (the warp has 168 of them): the shared-memory pipe is this kernel's
+            // bottleneck (ncu: 74 % of its wavefront rate), and 17 constant loads per sample were 11 % of the traffic.
+            const double c_tb1 = D->tb1, c_gain = D->throatGain;
+            const double c_ma10 = D->mouth[0], c_mb11 = D->mouth[1], c_ma20 = D->mouth[2];
+            const double c_na10 = D->nose[0], c_nb11 = D->nose[1], c_na20 = D->nose[2];
+            const double c_nk0 = D->nasal_coeff[0] * D->dampingFactor, c_nk1 = D->nasal_coeff[1] * D->dampingFactor;      // constant junctions: kd
+            const double c_nk2 = D->nasal_coeff[2] * D->dampingFactor, c_nk3 = D->nasal_coeff[3] * D->dampingFactor;
+            const double c_nk4 = D->nasal_coeff[4];
             double t[10], bt[10], nt[6], nb[6];
 #pragma unroll
             for (int q = 0; q < 10; ++q) { t[q] = 0.0; bt[q] = 0.0; }
@@ -526,22 +519,18 @@ __device__ __forceinline__ void wide_recurrence_warp(WideSmem<R> &W, const WideA
             for (int blk = 0; blk < n_blocks; ++blk) {
                 const int slot = blk & 1;
                 mbar_wait_sleep<TRM_WAIT_FULL_NS>(&W.full[slot], (uint32_t)((blk >> 1) & 1));
-                // The record of sample s+1 is requested while sample s is computed: every unit is re-loaded, into the same
-                // registers, right after its last use, so that a load has most of a sample time (~200 cycles) to arrive --
-                // the warp's shared-memory loads queue behind those of 14 feed-forward warps.
-                double2 q0 = W.ring[slot][0][0][lane], q1 = W.ring[slot][1][0][lane], q2 = W.ring[slot][2][0][lane], q3 = W.ring[slot][3][0][lane];
-                double2 q4 = W.ring[slot][4][0][lane], q5 = W.ring[slot][5][0][lane], q6 = W.ring[slot][6][0][lane], q7 = W.ring[slot][7][0][lane];
-                double2 q8 = W.ring[slot][8][0][lane], q9 = W.ring[slot][9][0][lane], q10 = W.ring[slot][10][0][lane], q11 = W.ring[slot][11][0][lane];
 #pragma unroll 1
                 for (int s0 = 0; s0 < ((TRM_PROFILE_SKIP & 2) ? 0 : TB); s0 += 2) {
                     double yo[2];
 #pragma unroll
                     for (int si = 0; si < 2; ++si) {
-                        const int sn = (s0 + si + 1) & (TB - 1);     // (the last sample of a block re-reads sample 0: harmless, reloaded after the wait)
+                        const int s = s0 + si;
                         // Written stage by stage ACROSS the junctions: the operations of one stage are mutually independent,
                         // so the FP64 pipe (one warp instruction per ~2.25 cycles, 8-cycle latency) always has a ready one.
-                        const double c_tb1 = KC(K_TB1), c_mb11 = KC(K_MB11), c_nb11 = KC(K_NB11), c_nk4 = KC(K_NK4);
-                        const double c_nk0 = KC(K_NK0), c_nk1 = KC(K_NK1), c_nk2 = KC(K_NK2), c_nk3 = KC(K_NK3);
+                        const double2 q9 = W.ring[slot][9][s][lane], q10 = W.ring[slot][10][s][lane], q11 = W.ring[slot][11][s][lane];
+                        const double2 q0 = W.ring[slot][0][s][lane], q1 = W.ring[slot][1][s][lane], q2 = W.ring[slot][2][s][lane];
+                        const double2 q3 = W.ring[slot][3][s][lane], q4 = W.ring[slot][4][s][lane], q5 = W.ring[slot][5][s][lane];
+                        const double2 q6 = W.ring[slot][6][s][lane], q7 = W.ring[slot][7][s][lane], q8 = W.ring[slot][8][s][lane];
                         // ---- stage 1: differences, first products ----
                         const double fr1 = fma(q9.y, y1, q11.x);                      // band-pass (TRMFilters.m:19-29, factor 2 folded in)
                         const double th = fma(c_tb1, thy, q11.y);                     // throat low-pass (TRMFilters.m:72-77)
@@ -558,13 +547,10 @@ __device__ __forceinline__ void wide_recurrence_warp(WideSmem<R> &W, const WideA
                         const double x0 = q0.x * e0, x1 = q0.y * e1, x2 = q1.x * e2, x4 = q2.x * e4, x6 = q2.y * e6, x7 = q3.x * e7, x8 = q3.y * e8;
                         const double xn0 = q4.y * en0, xn1 = c_nk0 * en1, xn2 = c_nk1 * en2, xn3 = c_nk2 * en3, xn4 = c_nk3 * en4;
                         const double pb = fma(q1.y, bt[4], pa);
-                        const double refl = fma(KC(K_MA10), mk, -m1), refn = fma(KC(K_NA10), nkk, -n1);
+                        const double refl = fma(c_ma10, mk, -m1), refn = fma(c_na10, nkk, -n1);
                         const double mx1 = t[9] + mk, nx1 = nt[5] + nkk;
                         y2 = y1; y1 = fr; thy = th;
                         const double q5x = q5.x, q5y = q5.y, q7y = q7.y, q9x = q9.x;
-                        q0 = W.ring[slot][0][sn][lane]; q1 = W.ring[slot][1][sn][lane]; q2 = W.ring[slot][2][sn][lane];
-                        q3 = W.ring[slot][3][sn][lane]; q4 = W.ring[slot][4][sn][lane];
-                        q9 = W.ring[slot][9][sn][lane]; q10 = W.ring[slot][10][sn][lane]; q11 = W.ring[slot][11][sn][lane];
                         // ---- stage 3: waves before injection, radiation filters ----
                         const double jp = fma(q5x, nb[0], pb);
                         const double u1 = fma(t[0], d, x0), v0 = fma(bt[1], d, x0);
@@ -580,10 +566,12 @@ __device__ __forceinline__ void wide_recurrence_warp(WideSmem<R> &W, const WideA
                         const double un4 = fma(nt[3], d, xn3), vn3 = fma(nb[4], d, xn3);
                         const double un5 = fma(nt[4], d, xn4), vn4 = fma(nb[5], d, xn4);
                         const double f5 = q7y * fr;
-                        const double ra = KC(K_MA20) * mx1, rb = KC(K_NA20) * nx1;
+                        // radiation filter (TRMFilters.m:47-60): a21 = b21 = -a20 by construction (TRMFilters.m:34-45), so
+                        // a20 x + a21 x[n-1] - b21 y[n-1] = a20 ((x - x[n-1]) + y[n-1])
+                        const double ra = mx1 - m_rx, rb = nx1 - n_rx;
                         const double b9n = d * refl, nb5n = d * refn;
                         // ---- stage 4: frication injection (m:803-829), 3-way outputs ----
-                        const double rc = fma(KC(K_MA21), m_rx, ra), rd = fma(KC(K_NA21), n_rx, rb);
+                        const double rc = ra + m_rY, rd = rb + n_rY;
                         const double b3n = fma(-d, t[3], jp), w4 = fma(-d, bt[4], jp), nt0n = fma(-d, nb[0], jp);
                         const double t6n = fma(t[5], d, f5);
                         t[0] = g0;
@@ -595,21 +583,18 @@ __device__ __forceinline__ void wide_recurrence_warp(WideSmem<R> &W, const WideA
                         t[8] = fma(q8.y, fr, u8);     bt[7] = v7;
                         t[9] = fma(q9x, fr, u9);      bt[8] = v8;
                         t[4] = fma(q6.y, fr, w4);     bt[3] = b3n;
-                        q5 = W.ring[slot][5][sn][lane]; q6 = W.ring[slot][6][sn][lane]; q7 = W.ring[slot][7][sn][lane];
-                        q8 = W.ring[slot][8][sn][lane];
                         t[6] = t6n;                   bt[5] = h5;
                         bt[9] = b9n;
                         nt[0] = nt0n;
                         nt[1] = un1; nb[0] = vn0; nt[2] = un2; nb[1] = vn1; nt[3] = un3; nb[2] = vn2;
                         nt[4] = un4; nb[3] = vn3; nt[5] = un5; nb[4] = vn4; nb[5] = nb5n;
-                        const double radm = fma(-KC(K_MB21), m_rY, rc), radn = fma(-KC(K_NB21), n_rY, rd);
+                        const double radm = c_ma20 * rc, radn = c_na20 * rd;
                         m_ry = refl; m_rx = mx1; m_rY = radm;
                         n_ry = refn; n_rx = nx1; n_rY = radn;
-                        yo[si] = fma(th, KC(K_GAIN), radm + radn);
+                        yo[si] = fma(th, c_gain, radm + radn);
                     }
                     *reinterpret_cast<double2 *>(&orow[s0]) = make_double2(yo[0], yo[1]);
                 }
-#undef KC
                 __syncwarp(FULL);
                 if (lane == 0) mbar_arrive(&W.empty[slot]);
                 {
@@ -676,11 +661,12 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
     const bool modulation = D->usesModulation != 0;
     const int div1 = D->div1, div2 = D->div2;
 
-    enum { C_BASICINC, C_TNDELTA, C_DAMP, C_SR, C_NR1SQ, C_APSCALE2, C_MOUTH0, C_BF, C_CMIX, C_TA0, C_RSR };
+    enum { C_BASICINC, C_TNDELTA, C_DAMP, C_SR, C_NR1SQ, C_APSCALE2, C_MOUTH0, C_BF, C_CMIX, C_TA0, C_RSR, C_INVDIV1 };
     if (hl == 0) {
         S.CST[C_BASICINC] = D->basicIncrement; S.CST[C_TNDELTA] = D->tnDelta; S.CST[C_DAMP] = D->dampingFactor;
         S.CST[C_SR] = D->sampleRate; S.CST[C_RSR] = 1.0 / D->sampleRate; S.CST[C_NR1SQ] = D->nr1sq; S.CST[C_APSCALE2] = D->apScale2; S.CST[C_MOUTH0] = D->mouth[0];
         S.CST[C_BF] = D->breathinessFactor; S.CST[C_CMIX] = D->crossmixFactor; S.CST[C_TA0] = D->ta0;
+        S.CST[C_INVDIV1] = 1.0 / (double)D->div1;
     }
     const bool feeds = n_tube > 0;
     const int n_chunks = (n_frames + FRAME_CHUNK - 1) / FRAME_CHUNK;
@@ -760,11 +746,15 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
     }
     // conformance-mode staging: where this parameter lane puts its value / its function inside the ring slot.  Unit
     // u (16 bytes) of sample t sits at ring[slot][u][(t + u) & 15][ucol]; the reader (lane = sample) takes units 0..9:
-    //   {p1,p2} {p3,p4} {r1,r2} {r3,r4} {r5,r6} {r7,r8} {velum,inc} {c1,c2} {c3,cos5} {cos6,sin6}
-    const int uA = F64C ? (hl >= 7 ? (hl - 3) >> 1 : (hl - 1) >> 1) : pf, cA = F64C ? (hl >= 7 ? (hl - 3) & 1 : (hl - 1) & 1) : pc;
-    const bool wantA = !F64C || !(hl == 0 || hl == 5 || hl == 6);
-    const int uB = hl == 0 ? 6 : (hl <= 2 ? 7 : (hl == 3 || hl == 5 ? 8 : 9)), cB = (hl == 0 || hl == 2 || hl == 5) ? 1 : 0;
-    const bool wantB = F64C && (fn_exp || fn_rot), wantC = F64C && hl == 6;
+    //   {p1,p2} {p3,p4} {r1,r2} {r3,r4} {r5,r6} {r7,r8} {velum,sin6} {inc,c1} {c2,c3} {cos5,cos6}
+    // Two stores per lane and step: store A carries the parameter (lane 6, whose parameter nobody reads, sends the sine
+    // of its angle through it), store B the function value -- every store instruction of the parameter phase costs
+    // shared-memory wavefronts, the resource that bounds this kernel.
+    const int uA = F64C ? (hl == 6 ? 6 : (hl >= 7 ? (hl - 3) >> 1 : (hl - 1) >> 1)) : pf, cA = F64C ? (hl == 6 ? 1 : (hl >= 7 ? (hl - 3) & 1 : (hl - 1) & 1)) : pc;
+    const bool wantA = !F64C || !(hl == 0 || hl == 5);
+    const bool sendsSine = F64C && hl == 6;
+    const int uB = hl <= 1 ? 7 : (hl <= 3 ? 8 : 9), cB = (hl == 1 || hl == 3 || hl == 6) ? 1 : 0;
+    const bool wantB = F64C && (fn_exp || fn_rot);
     __syncwarp(FULL);
 
 #if TRM_PROFILE_PHASES
@@ -826,14 +816,12 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
             }
             double *const a0 = reinterpret_cast<double *>(&W.ring[slot][uA][uA][ucol]) + cA;   // row of step 0; steps TB-u .. wrap
             double *const b0 = reinterpret_cast<double *>(&W.ring[slot][uB][uB][ucol]) + cB;
-            double *const c0 = reinterpret_cast<double *>(&W.ring[slot][9][9][ucol]) + 1;
             if (!starts) {
 #pragma unroll
                 for (int i = 0; i < TB; ++i) {
-                    sts_f64_if(wantA, (i + uA < TB ? a0 : a0 - TB * RS) + i * RS, p_cur);
+                    sts_f64_if(wantA, (i + uA < TB ? a0 : a0 - TB * RS) + i * RS, sendsSine ? rs : p_cur);
                     if constexpr (F64C) {
                         sts_f64_if(wantB, (i + uB < TB ? b0 : b0 - TB * RS) + i * RS, rc);
-                        sts_f64_if(wantC, (i + 9 < TB ? c0 : c0 - TB * RS) + i * RS, rs);
                         step_functions();
                     }
                     p_cur += p_delta;
@@ -845,10 +833,9 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
                         p_cur = np; p_delta = nd;
                         if constexpr (F64C) { rc = nrc; rs = nrs; dc = ndc; ds = nds; }
                     }
-                    sts_f64_if(wantA, (i + uA < TB ? a0 : a0 - TB * RS) + i * RS, p_cur);
+                    sts_f64_if(wantA, (i + uA < TB ? a0 : a0 - TB * RS) + i * RS, sendsSine ? rs : p_cur);
                     if constexpr (F64C) {
                         sts_f64_if(wantB, (i + uB < TB ? b0 : b0 - TB * RS) + i * RS, rc);
-                        sts_f64_if(wantC, (i + 9 < TB ? c0 : c0 - TB * RS) + i * RS, rs);
                         step_functions();
                     }
                     p_cur += p_delta;
@@ -874,10 +861,9 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
                 }
                 const int run = min(TB - s, cp - jc);
                 for (int i = 0; i < run; ++i) {
-                    sts_f64_if(wantA, reinterpret_cast<double *>(&W.ring[slot][uA][(s + i + uA) & (TB - 1)][ucol]) + cA, p_cur);
+                    sts_f64_if(wantA, reinterpret_cast<double *>(&W.ring[slot][uA][(s + i + uA) & (TB - 1)][ucol]) + cA, sendsSine ? rs : p_cur);
                     if constexpr (F64C) {
                         sts_f64_if(wantB, reinterpret_cast<double *>(&W.ring[slot][uB][(s + i + uB) & (TB - 1)][ucol]) + cB, rc);
-                        sts_f64_if(wantC, reinterpret_cast<double *>(&W.ring[slot][9][(s + i + 9) & (TB - 1)][ucol]) + 1, rs);
                         step_functions();
                     }
                     p_cur += p_delta;
@@ -908,7 +894,7 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
         TPH(2);
         double inc_d;
         if constexpr (F64C) {
-            inc_d = prm[13];
+            inc_d = prm[14];
         } else {
             const double f0 = 220.0 * exp2(div_known(prm[0] + 3.0, 12.0, 1.0 / 12.0));
             inc_d = (f0 / 2.0) * S.CST[C_BASICINC];
@@ -920,7 +906,7 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
         if constexpr (F64C) {
             // amplitude() (TRMUtility.m:26-41): clamps decided on the exact parameter, value from the geometric sequence
             const double p1 = prm[0], p2 = prm[1], p3 = prm[2], fpos = prm[3];
-            ax_d = (p1 <= 0.0) ? 0.0 : ((p1 >= 60.0) ? 1.0 : prm[14]);
+            ax_d = (p1 <= 0.0) ? 0.0 : ((p1 >= 60.0) ? 1.0 : prm[15]);
             {
                 // glottal closure point rint(ax * tnDelta) (TRMWavetable.m:122): when the product is within 1e-6 of a
                 // rounding boundary, decide with the amplitude computed directly from the parameter
@@ -929,8 +915,8 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
                     ax_d = exp2_inline((p1 - 60.0) * 0.16609640474436813);
             }
             ax = ax_d;
-            ah1 = (p2 <= 0.0) ? 0.0 : ((p2 >= 60.0) ? 1.0 : prm[15]);
-            const double fa = (p3 <= 0.0) ? 0.0 : ((p3 >= 60.0) ? 1.0 : prm[16]);
+            ah1 = (p2 <= 0.0) ? 0.0 : ((p2 >= 60.0) ? 1.0 : prm[16]);
+            const double fa = (p3 <= 0.0) ? 0.0 : ((p3 >= 60.0) ? 1.0 : prm[17]);
             const double dd = S.CST[C_DAMP];
             double r2[8];
 #pragma unroll
@@ -955,7 +941,7 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
                 for (int q = 0; q < 8; ++q) tap[q] = (q == ipos) ? t0 : ((ipos >= 0 && q == ipos + 1) ? t1 : 0.0);
             }
             // band-pass (TRMFilters.m:9-17): beta = (1 - tan u) / (2 (1 + tan u)) = (cos u - sin u) / (2 (cos u + sin u))
-            const double cu = prm[18], su = prm[19], cosv = prm[17];
+            const double cu = prm[19], su = prm[13], cosv = prm[18];
             const double beta2 = (cu - su) * rcp_fast(cu + su);
             const double gamma2 = (1.0 + beta2) * cosv;
             bp_alpha2 = 0.5 - 0.5 * beta2;
@@ -1089,11 +1075,18 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
         // noise (TRMUtility.m:71-85 as the MCG mod 2^44) + one-zero low-pass (TRMFilters.m:81-86)
         R lp_noise;
         {
+            // (a 44-bit integer becomes a double by placing it in the mantissa of 2^52 and subtracting 2^52 -- exact, like the
+            //  conversion instruction, but two ALU operations and an add instead of a trip through the conversion unit)
+            auto draw = [&](unsigned long long k) {
+                const double kd_ = __hiloint2double((int)(0x43300000u | (unsigned)(k >> 32)), (int)(unsigned)k) - 4503599627370496.0;
+                return kd_ * TWO_M44 - 0.5;
+            };
             const unsigned long long kt = (kb * pw1) & MASK44;
-            const double nz = (double)(long long)kt * TWO_M44 - 0.5;
+            const double nz = draw(kt);
             // x[n-1]: the draw of the lane below; lane 0 takes the last draw of the previous block (the state kb itself)
             double nzp = __shfl_up_sync(FULL, nz, 1, 16);
-            if (hl == 0) nzp = (fresh && n0 == 0) ? 0.0 : ((double)(long long)kb * TWO_M44 - 0.5);
+            const double nz_prev = (fresh && n0 == 0) ? 0.0 : draw(kb);
+            nzp = (hl == 0) ? nz_prev : nzp;
             lp_noise = (R)(nz + nzp);
             kb = (kb * pwB) & MASK44;
         }
@@ -1190,12 +1183,30 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
                 S.HO[FIR_HIST + hl] = w10 + ((float)(p1 - (double)lo1) * (w11 - w10));
             } else {
                 const R scale = F64C ? (R)rcp_fast(Ld * Ld) : (R)(1.0 / (Ld * Ld));
-                R w0 = table_value<R>(wt_base, lo0, div1, div2, newDiv2, scale, pulse_wave);
-                R w1 = table_value<R>(wt_base, hi0, div1, div2, newDiv2, scale, pulse_wave);
-                S.HE[FIR_HIST + hl] = w0 + ((R)(p0 - (double)lo0) * (w1 - w0));
-                w0 = table_value<R>(wt_base, lo1, div1, div2, newDiv2, scale, pulse_wave);
-                w1 = table_value<R>(wt_base, hi1, div1, div2, newDiv2, scale, pulse_wave);
-                S.HO[FIR_HIST + hl] = w0 + ((R)(p1 - (double)lo1) * (w1 - w0));
+                if (F64C && pulse_wave) {
+                    // conformance mode, pulse waveform: the whole table is a function of the index -- rise 3x^2 - 2x^3 with
+                    // x = i / div1 (TRMWavetable.m:78-87), fall 1 - j^2 / L^2 up to the closure point, 0 after it -- so it is
+                    // evaluated without a memory access or a branch (the strict mode reads the rise from the init-time table)
+                    const double inv_div1 = S.CST[C_INVDIV1];
+                    auto value = [&](int i) {
+                        const double di = (double)i, x = di * inv_div1, x2 = x * x;
+                        const double rise = fma(-2.0 * x2, x, 3.0 * x2);
+                        const double j = di - (double)div1;
+                        const double fall = fma(-(j * j), scale, 1.0);
+                        const double v = (i < div1) ? rise : fall;
+                        return (di >= newDiv2) ? 0.0 : v;
+                    };
+                    const double w00 = value(lo0), w01 = value(hi0), w10 = value(lo1), w11 = value(hi1);
+                    S.HE[FIR_HIST + hl] = fma(p0 - (double)lo0, w01 - w00, w00);
+                    S.HO[FIR_HIST + hl] = fma(p1 - (double)lo1, w11 - w10, w10);
+                } else {
+                    R w0 = table_value<R>(wt_base, lo0, div1, div2, newDiv2, scale, pulse_wave);
+                    R w1 = table_value<R>(wt_base, hi0, div1, div2, newDiv2, scale, pulse_wave);
+                    S.HE[FIR_HIST + hl] = w0 + ((R)(p0 - (double)lo0) * (w1 - w0));
+                    w0 = table_value<R>(wt_base, lo1, div1, div2, newDiv2, scale, pulse_wave);
+                    w1 = table_value<R>(wt_base, hi1, div1, div2, newDiv2, scale, pulse_wave);
+                    S.HO[FIR_HIST + hl] = w0 + ((R)(p1 - (double)lo1) * (w1 - w0));
+                }
             }
         }
         __syncwarp(FULL);
@@ -1204,6 +1215,8 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
         {
             const R *ho = &S.HO[FIR_HIST + hl], *he = &S.HE[FIR_HIST + hl];
             R pulse0;
+            // (Measured and not kept: two outputs per lane from 13 + 13 aligned 128-bit loads -- 52 shared-memory wavefronts
+            //  per block instead of 98, but half the lanes idle and twice the FP64 instructions: 10.85 -> 11.19 ms.)
             if constexpr (FAST || F64C) {
                 R s0 = (R)0, s1 = (R)0, s2 = (R)0, s3 = (R)0;
 #pragma unroll
