@@ -712,8 +712,11 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
     //   1..3 dB    -> 10^((p-60)/20), unclamped (the clamps of amplitude() are applied per sample on the exact parameter)
     //   5 centre f -> cos(2 pi p / sr)        6 bandwidth -> cos, sin(pi p / sr)        (TRMFilters.m:9-17)
     double rc = 0.0, rs = 0.0, dc = 0.0, ds = 0.0;
-    const bool fn_exp = hl < 4, fn_rot = (hl == 5) | (hl == 6);
-    const double fn_w = F64C ? (hl == 0 ? (1.0 / 12.0) : (hl < 4 ? 0.16609640474436813 : (hl == 5 ? 6.28318530717958647692 : 3.14159265358979323846) / D->sampleRate)) : 0.0;
+    // (FP32 fast mode: only function 0 -- the oscillator increment, which that mode keeps in double -- is carried this way;
+    //  its lane stages the increment in place of the pitch, which nothing else reads)
+    constexpr bool GEO = F64C || FAST;                      // modes whose parameter lanes carry functions
+    const bool fn_exp = F64C ? hl < 4 : hl == 0, fn_rot = F64C && ((hl == 5) | (hl == 6));
+    const double fn_w = GEO ? (hl == 0 ? (1.0 / 12.0) : (hl < 4 ? 0.16609640474436813 : (hl == 5 ? 6.28318530717958647692 : 3.14159265358979323846) / D->sampleRate)) : 0.0;
     const double fn_off = hl == 0 ? 3.0 : -60.0, fn_scale = hl == 0 ? 110.0 * D->basicIncrement : 1.0;
     auto seed_functions = [&](double pc0, double pd0, double &c, double &sn, double &cd, double &sd) {
         // for a control interval that starts at pc0 and moves by pd0 per sample: two exp2 or two sincos per interval
@@ -737,10 +740,10 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
         p_cur = p_next;
         p_delta = (nxt - p_cur) / (double)cp;
         p_next = nxt;
-        if constexpr (F64C) seed_functions(p_cur, p_delta, rc, rs, dc, ds);
+        if constexpr (GEO) seed_functions(p_cur, p_delta, rc, rs, dc, ds);
         for (int i = 0; i < D->jc0; ++i) {
             p_cur += p_delta;
-            if constexpr (F64C) step_functions();
+            if constexpr (F64C) step_functions(); else if constexpr (FAST) rc *= dc;
         }
         jc = D->jc0;
     }
@@ -752,7 +755,8 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
     // shared-memory wavefronts, the resource that bounds this kernel.
     const int uA = F64C ? (hl == 6 ? 6 : (hl >= 7 ? (hl - 3) >> 1 : (hl - 1) >> 1)) : pf, cA = F64C ? (hl == 6 ? 1 : (hl >= 7 ? (hl - 3) & 1 : (hl - 1) & 1)) : pc;
     const bool wantA = !F64C || !(hl == 0 || hl == 5);
-    const bool sendsSine = F64C && hl == 6;
+    const bool sendsFn = (F64C && hl == 6) || (FAST && hl == 0);      // lanes whose store A carries a function value
+    auto fn_value = [&]() { return FAST ? rc : rs; };
     const int uB = hl <= 1 ? 7 : (hl <= 3 ? 8 : 9), cB = (hl == 1 || hl == 3 || hl == 6) ? 1 : 0;
     const bool wantB = F64C && (fn_exp || fn_rot);
     __syncwarp(FULL);
@@ -811,7 +815,7 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
                 nd = (nxt - np) / (double)cp;
                 p_next = nxt;
                 TPHX(10);
-                if constexpr (F64C) seed_functions(np, nd, nrc, nrs, ndc, nds);
+                if constexpr (GEO) seed_functions(np, nd, nrc, nrs, ndc, nds);
                 TPHX(11);
             }
             double *const a0 = reinterpret_cast<double *>(&W.ring[slot][uA][uA][ucol]) + cA;   // row of step 0; steps TB-u .. wrap
@@ -819,10 +823,12 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
             if (!starts) {
 #pragma unroll
                 for (int i = 0; i < TB; ++i) {
-                    sts_f64_if(wantA, (i + uA < TB ? a0 : a0 - TB * RS) + i * RS, sendsSine ? rs : p_cur);
+                    sts_f64_if(wantA, (i + uA < TB ? a0 : a0 - TB * RS) + i * RS, sendsFn ? fn_value() : p_cur);
                     if constexpr (F64C) {
                         sts_f64_if(wantB, (i + uB < TB ? b0 : b0 - TB * RS) + i * RS, rc);
                         step_functions();
+                    } else if constexpr (FAST) {
+                        rc *= dc;
                     }
                     p_cur += p_delta;
                 }
@@ -832,11 +838,14 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
                     if (i == ib) {
                         p_cur = np; p_delta = nd;
                         if constexpr (F64C) { rc = nrc; rs = nrs; dc = ndc; ds = nds; }
+                        else if constexpr (FAST) { rc = nrc; dc = ndc; }
                     }
-                    sts_f64_if(wantA, (i + uA < TB ? a0 : a0 - TB * RS) + i * RS, sendsSine ? rs : p_cur);
+                    sts_f64_if(wantA, (i + uA < TB ? a0 : a0 - TB * RS) + i * RS, sendsFn ? fn_value() : p_cur);
                     if constexpr (F64C) {
                         sts_f64_if(wantB, (i + uB < TB ? b0 : b0 - TB * RS) + i * RS, rc);
                         step_functions();
+                    } else if constexpr (FAST) {
+                        rc *= dc;
                     }
                     p_cur += p_delta;
                 }
@@ -857,14 +866,16 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
                     p_cur = p_next;
                     p_delta = (nxt - p_cur) / (double)cp;
                     p_next = nxt;
-                    if constexpr (F64C) seed_functions(p_cur, p_delta, rc, rs, dc, ds);
+                    if constexpr (GEO) seed_functions(p_cur, p_delta, rc, rs, dc, ds);
                 }
                 const int run = min(TB - s, cp - jc);
                 for (int i = 0; i < run; ++i) {
-                    sts_f64_if(wantA, reinterpret_cast<double *>(&W.ring[slot][uA][(s + i + uA) & (TB - 1)][ucol]) + cA, sendsSine ? rs : p_cur);
+                    sts_f64_if(wantA, reinterpret_cast<double *>(&W.ring[slot][uA][(s + i + uA) & (TB - 1)][ucol]) + cA, sendsFn ? fn_value() : p_cur);
                     if constexpr (F64C) {
                         sts_f64_if(wantB, reinterpret_cast<double *>(&W.ring[slot][uB][(s + i + uB) & (TB - 1)][ucol]) + cB, rc);
                         step_functions();
+                    } else if constexpr (FAST) {
+                        rc *= dc;
                     }
                     p_cur += p_delta;
                 }
@@ -895,6 +906,8 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
         double inc_d;
         if constexpr (F64C) {
             inc_d = prm[14];
+        } else if constexpr (FAST) {
+            inc_d = prm[0];                                 // staged by parameter lane 0 in place of the pitch
         } else {
             const double f0 = 220.0 * exp2(div_known(prm[0] + 3.0, 12.0, 1.0 / 12.0));
             inc_d = (f0 / 2.0) * S.CST[C_BASICINC];
