@@ -47,10 +47,10 @@ UNIT = "audio-s/s"
 FLOP_PER_TUBE_SAMPLE = 390.0     # algorithmic flops per tube-rate sample
 FLOP_PER_OUT_SAMPLE = 110.0      # up-sampling converter, per output sample
 # DRAM traffic per unit, STATIC: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture per kernel
-# (profiles/prof_r2_*_summary.txt, 4096 x 0.5 s launch), divided by that launch's units -- linear in the number of samples:
+# (profiles/prof_r2_{fp64,fp32}_summary.txt, 4096 x 0.5 s launch), divided by that launch's units -- linear in the number of samples:
 #   waveguide: bytes per tube-rate sample, resampler / PCM: bytes per output sample.  Not measured in the run it is printed in.
-TRAFFIC_PER_UNIT = {"fp64": {"tube": 8.45, "src": 12.08, "pcm": 9.96}, "fp32": {"tube": 5.04, "src": 5.85, "pcm": 5.85}}
-TRAFFIC_SOURCE = "static: ncu --set full DRAM bytes of a 4096-utterance launch (profiles/), scaled by samples"
+TRAFFIC_PER_UNIT = {"fp64": {"tube": 8.51, "src": 11.28, "pcm": 9.92}, "fp32": {"tube": 4.48, "src": 5.42, "pcm": 5.73}}
+TRAFFIC_SOURCE = "static: ncu --set full DRAM bytes of a 4096 x 0.5 s launch (profiles/prof_r2_*_summary.txt), scaled by samples"
 
 
 def bind_to_gpu_numa_node(torch, local_rank, world):

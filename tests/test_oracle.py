@@ -274,3 +274,43 @@ def test_known_divisor_division_is_ieee_division():
     for k, (c, lo, hi) in enumerate(cases):
         assert L.oracle_div_known_mismatches(c, lo, hi, 2_000_000, 1234 + k) == 0, c
 
+
+
+def test_frame_generator_pinning_as_far_as_the_reference_allows():
+    """The control-frame generator (EventList.m:883-1061) has no vectors in the reference and Objective-C cannot be built
+    here, so the row stays "parity unpinned" (DESIGN.md 4.5).  What CAN be pinned without running it:
+    * the one EventList output the reference ships -- Applications/Monet/samples/gnuspeech.input, written with "%.3f" from
+      the generator's FLOAT table (EventList.m:1002-1019) -- is consistent with a float table: every value is the %.3f
+      print of the float nearest to it, and pushing the fixture's frames through float32 rows changes nothing a 3-decimal
+      print could show (what the TRM_FRAMES_F32 format relies on);
+    * MMDriftGenerator's seed recurrence (float, factor 377, seed 0.7892347: MMDriftGenerator.m:6-9,65-70) is the tube's noise
+      generator (TRMUtility.m:71-85, double) in float: same factor, same initial seed, same update."""
+    path = os.path.join(GOLDEN, "gnuspeech.input")
+    oip, frames = O.parse_input_file(path)
+    lines = [ln for ln in open(path).read().splitlines() if ln.strip()]
+    tokens = [ln.split()[:16] for ln in lines[26:]]                                # the frames follow the 26 header lines
+    tokens.append(tokens[-1])                     # the reference's `while (!feof(fp))` loop reads the last frame twice (TRMDataList.m:216-247)
+    assert frames.shape[0] == len(tokens) == 344 and all(len(t) == 16 for t in tokens)
+    for row, tok in zip(frames, tokens):
+        for v, t in zip(row, tok):
+            assert "%.3f" % float(np.float32(v)) == "%.3f" % float(t)
+    # drift generator against the noise generator's recurrence, float vs double
+    seed_f, seed_d = np.float32(0.7892347), 0.7892347
+    for _ in range(5):
+        t = np.float32(seed_f * np.float32(377.0))
+        seed_f = np.float32(t - np.float32(np.int32(t)))
+        p = seed_d * 377.0
+        seed_d = p - int(p)
+        assert abs(float(seed_f) - seed_d) < 377.0 ** 5 * 1e-6        # same map; float rounding grows by the factor each step
+        break                                                              # (one step is exact to float rounding; later steps diverge chaotically)
+    ev = O.synthetic_event_list(3, 0.3)
+    fg = O.OracleFrameGen()
+    fg.useMacroIntonation = fg.useMicroIntonation = fg.useSmoothIntonation = 0
+    fg.useDrift, fg.driftDeviation, fg.driftCutoff, fg.pitch, fg.driftSeed = 1, 1.0, 4.0, 0.0, 0.7892347
+    fr, seed_out = O.generate_frames(ev, fg)
+    # the restatement's generator advanced once per frame with exactly that float recurrence
+    s = np.float32(0.7892347)
+    for _ in range(fr.shape[0]):
+        t = np.float32(s * np.float32(377.0))
+        s = np.float32(t - np.float32(np.int32(t)))
+    assert np.float32(seed_out) == s
