@@ -49,7 +49,7 @@ def build(verbose=False, force=False, defines=(), tag=None):
         OBJ = os.path.join(ROOT, "build", "obj_" + tag)
     os.makedirs(LIB, exist_ok=True)
     os.makedirs(OBJ, exist_ok=True)
-    headers = [os.path.join(CSRC, h) for h in ("tube_kernel.cuh", "tube_wide.cuh", "src_kernel.cuh", "framegen_kernel.cuh",
+    headers = [os.path.join(CSRC, h) for h in ("tube_common.cuh", "tube_wide.cuh", "src_kernel.cuh", "framegen_kernel.cuh",
                                                "launch.cuh", "kernel_args.h")]
     headers += [os.path.join(INC, h) for h in ("trm.h", "trm_cuda.h", "trm_workload.h")]
     cu = [("kernels_f64s", ["-fmad=false"]), ("kernels_f64", []), ("kernels_f32", []), ("kernels_aux", ["-fmad=false"]), ("trm_cuda", [])]

@@ -21,8 +21,6 @@ constexpr int TB = 16;           // samples per block == lanes per utterance
 constexpr int FIR_TAPS = 49;     // TRMFIRFilter.h:7-9 fixed design -> 49 taps (checked on the host)
 constexpr int FIR_HIST = 24;     // (FIR_TAPS-1)/2 previous even / odd oscillator values
 constexpr int FRAME_CHUNK = 2;   // control frames per bulk copy (256 B)
-constexpr int WARPS_PER_CTA = 2;
-constexpr int UTT_PER_CTA = WARPS_PER_CTA * 2;
 
 
 constexpr int SRC_ROWS = TRM_SRC_ROWS; // staged input rows per work item (include/trm_cuda.h: the host checks rate ratios against it)
@@ -99,9 +97,6 @@ struct FrameGenArgs {
 };
 
 struct KernelInfo {
-    int tube_smem_bytes;
-    int tube_threads;
-    int tube_utt_per_cta;
     // resampler shapes (src_kernel.cuh SrcCfg): [0] handles every converter signature, [1] (if n_src_shapes == 2) is
     // the faster shape for up-sampling signatures whose work-item window fits its smaller staging buffer
     struct SrcShape {
@@ -111,8 +106,7 @@ struct KernelInfo {
         int nt_max;                // outputs per work item, at most
     } src[2];
     int n_src_shapes;
-    int tube_ctas_per_sm;
-    int tube_regs, pcm_regs;
+    int pcm_regs;
     int wide_smem_bytes, wide_threads, wide_max_utt, wide_regs;   // batch-throughput waveguide mapping (tube_wide.cuh)
 };
 

@@ -6,7 +6,6 @@
 #include <stdlib.h>
 
 #include "src_kernel.cuh"
-#include "tube_kernel.cuh"
 #include "tube_wide.cuh"
 
 namespace TRM_KERNEL_NS {
@@ -40,12 +39,7 @@ template <typename R, int SHAPE> static int configure_src(KernelInfo *info)
 
 template <typename R> static int configure_kernels(KernelInfo *info)
 {
-    const int tube_smem = UTT_PER_CTA * (int)sizeof(UttSmem<R>);
     cudaError_t e;
-    e = cudaFuncSetAttribute(tube_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, tube_smem);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(tube_kernel<R>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return (int)e;
     {
         int rc = configure_src<R, 0>(info);
         if (rc != 0) return rc;
@@ -63,13 +57,7 @@ template <typename R> static int configure_kernels(KernelInfo *info)
         info->wide_smem_bytes = wide_smem;
         info->wide_threads = Wide<R>::THREADS;
         info->wide_max_utt = 2 * Wide<R>::MAX_PAIRS;
-        info->tube_smem_bytes = tube_smem;
-        info->tube_threads = WARPS_PER_CTA * 32;
-        info->tube_utt_per_cta = UTT_PER_CTA;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&info->tube_ctas_per_sm, tube_kernel<R>, WARPS_PER_CTA * 32, tube_smem);
-        if (e != cudaSuccess) return (int)e;
         cudaFuncAttributes fa;
-        if (cudaFuncGetAttributes(&fa, tube_kernel<R>) == cudaSuccess) info->tube_regs = fa.numRegs;
         if (cudaFuncGetAttributes(&fa, tube_wide_kernel<R>) == cudaSuccess) info->wide_regs = fa.numRegs;
         if (cudaFuncGetAttributes(&fa, pcm_kernel<R>) == cudaSuccess) info->pcm_regs = fa.numRegs;
     }
@@ -89,15 +77,7 @@ static int upload_constants(const double *fir, int taps, const unsigned long lon
     return (int)e;
 }
 
-template <typename R> static int launch_tube(const TubeArgs &a, cudaStream_t s)
-{
-    if (a.n_utt <= 0) return 0;
-    const int grid = (a.n_utt + UTT_PER_CTA - 1) / UTT_PER_CTA;
-    tube_kernel<R><<<grid, WARPS_PER_CTA * 32, UTT_PER_CTA * sizeof(UttSmem<R>), s>>>(a);
-    return (int)cudaGetLastError();
-}
-
-// batch-throughput mapping: one CTA per group of <= 2*MAX_PAIRS utterances (tube_wide.cuh)
+// waveguide: one CTA per group of <= 2*MAX_PAIRS utterances (tube_wide.cuh)
 template <typename R> static int launch_tube_wide(const TubeArgs &a, int n_groups, cudaStream_t s)
 {
     if (a.n_utt <= 0 || n_groups <= 0) return 0;
@@ -148,7 +128,6 @@ template <typename R> static int launch_pcm(const PcmArgs &a, long long max_n_ou
     {                                                                                                             \
         return TRM_KERNEL_NS::upload_constants(fir, taps, np);                                                              \
     }                                                                                                             \
-    extern "C" int trm_k_tube_##SUF(const trm::TubeArgs *a, cudaStream_t s) { return TRM_KERNEL_NS::launch_tube<R>(*a, s); } \
     extern "C" int trm_k_tube_wide_##SUF(const trm::TubeArgs *a, int n_groups, cudaStream_t s)                    \
     {                                                                                                             \
         return TRM_KERNEL_NS::launch_tube_wide<R>(*a, n_groups, s);                                                         \

@@ -26,7 +26,7 @@
 
 #include "kernel_args.h"
 #include "trm_cuda.h"
-#include "tube_kernel.cuh"   // mbarrier / TMA bulk-copy helpers
+#include "tube_common.cuh"   // mbarrier / TMA bulk-copy helpers
 
 namespace TRM_KERNEL_NS {
 using namespace trm;

@@ -20,7 +20,6 @@
 #define TRM_DECLARE_LAUNCHERS(SUF)                                              \
     int trm_k_configure_##SUF(trm::KernelInfo *);                               \
     int trm_k_upload_##SUF(const double *, int, const unsigned long long *);    \
-    int trm_k_tube_##SUF(const trm::TubeArgs *, cudaStream_t);                  \
     int trm_k_tube_wide_##SUF(const trm::TubeArgs *, int, cudaStream_t);        \
     int trm_k_src_##SUF(const trm::SrcArgs *, int, int, cudaStream_t);          \
     int trm_k_src_ctab_##SUF(const void *, void *, cudaStream_t);               \
@@ -38,15 +37,14 @@ int trm_k_pcm_checksum(const trm_cuda_utterance *, int, const int16_t *, unsigne
 static inline bool prec_is_f64(int precision) { return precision != 1; }
 static inline size_t prec_esz(int precision) { return precision != 1 ? sizeof(double) : sizeof(float); }
 struct KernelSet {
-    int (*tube)(const trm::TubeArgs *, cudaStream_t);
     int (*tube_wide)(const trm::TubeArgs *, int, cudaStream_t);
     int (*src)(const trm::SrcArgs *, int, int, cudaStream_t);
     int (*pcm)(const trm::PcmArgs *, long long, cudaStream_t);
 };
 static const KernelSet g_kernels[3] = {
-    {trm_k_tube_f64, trm_k_tube_wide_f64, trm_k_src_f64, trm_k_pcm_f64},
-    {trm_k_tube_f32, trm_k_tube_wide_f32, trm_k_src_f32, trm_k_pcm_f32},
-    {trm_k_tube_f64s, trm_k_tube_wide_f64s, trm_k_src_f64s, trm_k_pcm_f64s},
+    {trm_k_tube_wide_f64, trm_k_src_f64, trm_k_pcm_f64},
+    {trm_k_tube_wide_f32, trm_k_src_f32, trm_k_pcm_f32},
+    {trm_k_tube_wide_f64s, trm_k_src_f64s, trm_k_pcm_f64s},
 };
 
 // FMA-chain kernels used to MEASURE the FP32 / FP64 CUDA-core peak of the device the bench runs on
@@ -252,7 +250,6 @@ struct trm_cuda_ctx {
     cudaEvent_t ev_in[MAX_SLOTS]{}, ev_run[MAX_SLOTS]{}, ev_out[MAX_SLOTS]{};
     cudaEvent_t ev_in2[MAX_SLOTS]{};                    // time split: the later frames are on the device
     cudaEvent_t ev_grp[MAX_SLOTS][MAX_OUT_GROUPS]{};   // a group's PCM is complete (copy-out of the group may start)
-    int wide_min_utt = 0;         // batches at least this large use the batch-throughput waveguide mapping
 };
 
 struct trm_cuda_resident {
@@ -524,17 +521,11 @@ int upload_frames(const ChunkPlan &p, const DeviceChunk &dc, const trm_cuda_utte
     return 0;
 }
 
-// Which waveguide mapping runs a chunk of n utterances: 0 = lane-per-section (tube_kernel.cuh), otherwise the
-// number of CTAs of the lane-per-utterance mapping (tube_wide.cuh), one per SM and wave.  The latter is the default at
-// every batch size: even a lone utterance finishes sooner when its feed-forward and recurrence parts run as two
-// concurrent warps than when they alternate inside one (measured, profiles/README.md).  TRM_TUBE_MAPPING=sections
-// selects the lane-per-section kernel (the two agree bit for bit in FP64).
+// CTAs of the waveguide kernel for a chunk of n utterances: one per SM and wave, at most wide_max_utt utterances each; small
+// chunks are spread two utterances per CTA (one feed-forward warp each) over as many SMs as there are pairs.
 int wide_groups(const trm_cuda_ctx *ctx, const trm::KernelInfo &ki, int n)
 {
-    const char *env = getenv("TRM_TUBE_MAPPING");
-    const bool force_sections = env && env[0] == 's', force_wide = env && env[0] == 'u';
-    if (n <= 0 || force_sections) return 0;
-    if (!force_wide && n < ctx->wide_min_utt) return 0;
+    if (n <= 0) return 0;
     const int sm = ctx->sm_count, gmax = ki.wide_max_utt;
     if ((long long)n <= (long long)sm * gmax) return std::max(1, std::min(sm, (n + 1) / 2));
     const int waves = (int)(((long long)n + (long long)sm * gmax - 1) / ((long long)sm * gmax));
@@ -554,9 +545,7 @@ int launch_stage(trm_cuda_ctx *ctx, int precision, int stage, const DeviceChunk 
         if (time_part >= 0) { a.desc = dc.desc_t[time_part]; a.state = dc.state; }     // (lane-per-utterance mapping only)
         const trm::KernelInfo &ki = ctx->ki(precision);
         const int groups = wide_groups(ctx, ki, dc.n);
-        if (time_part >= 0 && groups <= 0) return fail_msg("time split needs the lane-per-utterance waveguide mapping");
         if (groups > 0) rc = K.tube_wide(&a, groups, s);
-        else rc = K.tube(&a, s);
     } else if (stage == TRM_STAGE_SRC) {
         // (the running maxima are cleared once per chunk: by the ungrouped launch, or by the first group's)
         if (!grp || grp->u_begin == 0) CK(cudaMemsetAsync(dc.maxbits, 0, (size_t)dc.n * sizeof(unsigned long long), s));
@@ -694,7 +683,6 @@ int trm_cuda_ctx_create(int device, const trm_cuda_tables *t, trm_cuda_ctx **out
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     c->noise_k0 = t->noise_k0;
-    c->wide_min_utt = 1;     // measured: the batch-throughput mapping is the faster one at every batch size (profiles/README.md)
     int rc;
     if ((rc = trm_k_upload_f64(t->fir_coef, t->fir_taps, (const unsigned long long *)t->noise_pow)) != 0 ||
         (rc = trm_k_upload_f32(t->fir_coef, t->fir_taps, (const unsigned long long *)t->noise_pow)) != 0 ||

@@ -1,34 +1,39 @@
-// tube_wide.cuh -- the TRM waveguide kernel for sm_100a, batch-throughput mapping.
+// tube_wide.cuh -- the TRM waveguide kernel for sm_100a.
 //
-// Same path as tube_kernel.cuh (TRMTubeModel.m:292-354 and everything it calls) with the work split by
-// KIND instead of by utterance:
+// Replaces the sample-rate loop of -[TRMTubeModel synthesize] (/root/reference/Frameworks/Tube/TRMTubeModel.m:292-354) and
+// everything it calls: parameter interpolation (m:611-688), frequency()/amplitude() (TRMUtility.m:26-47), tube and
+// frication coefficients (m:712-773), band-pass coefficients/filter (TRMFilters.m:9-29), noise + one-zero low-pass
+// (TRMUtility.m:71-85, TRMFilters.m:81-86), glottal wavetable + 2x oversampling oscillator + 49-tap FIR
+// (TRMWavetable.m:117-195, TRMFIRFilter.m:116-146), source mixing (m:305-337), Kelly-Lochbaum ladder with the velum
+// 3-way junction and nasal branch (m:778-853), mouth/nose reflection + radiation filters (TRMFilters.m:34-60) and the
+// throat low-pass (TRMFilters.m:64-77).  The work is split by KIND, not by utterance:
 //
-//   feed-forward warps (one per utterance pair, lane = sample t of a 16-sample block, exactly the
-//       time-parallel phases S0/A1/S1/A2 of tube_kernel.cuh): parameter interpolation, conversions, junction /
-//       tap / band-pass coefficients, jump-ahead noise, oscillator position, glottal table look-ups, 49-tap FIR,
-//       source mixing.  Nothing here depends on the tube state.  Results go to a shared-memory ring of
-//       per-sample coefficient records.
+//   feed-forward warps (one per utterance pair; lane = parameter in the interpolation phase S0, lane = sample t of a
+//       16-sample block in the phases A1 / S1 / A2): parameter interpolation, conversions, junction / tap / band-pass
+//       coefficients, jump-ahead noise, oscillator position, glottal table, 49-tap FIR, source mixing.  Nothing here
+//       depends on the tube state.  Results go to a shared-memory ring of per-sample coefficient records.
 //   ONE recurrence warp per CTA (lane = utterance): the strictly sequential part only -- Kelly-Lochbaum ladder,
 //       velum 3-way junction, nasal branch, mouth / nose reflection + radiation filters, frication band-pass
 //       and throat low-pass recursions (TRMTubeModel.m:778-853, TRMFilters.m:19-29,47-77).  All 32 waves and
 //       9 filter memories of an utterance live in that lane's registers; the 16 junctions of one sample are
 //       independent of each other (they read the previous time slice only), so the lane has 16-wide ILP and
-//       there is NO cross-lane traffic: no shuffles, no role blends.  ~6 warp instructions per utterance-sample
-//       in FP64 and ~3.5 in FP32, against ~35 / ~18 for the lane-per-section ladder.
+//       there is NO cross-lane traffic: no shuffles, no role blends.
 //
-// One CTA per SM, up to 28 (FP64) / 30 (FP32) utterances per CTA; the ring is double-buffered so the
-// feed-forward warps work on block b+1 while the recurrence warp consumes block b (mbarrier full / empty
-// pairs).  Control frames are staged by TMA bulk copies as in tube_kernel.cuh.  Tube-rate output is transposed
-// through shared memory and stored with 128-bit coalesced stores.
+// One CTA per SM, up to 28 utterances per CTA; the ring is double-buffered so the feed-forward warps work on block b+1
+// while the recurrence warp consumes block b (mbarrier full / empty pairs).  Control frames are staged by TMA bulk copies
+// (cp.async.bulk + mbarrier, FRAME_CHUNK frames ahead of the sample loop).  Tube-rate output is transposed through shared
+// memory and stored with 128-bit coalesced stores.
 //
-// The lane-per-section kernel (tube_kernel.cuh) stays the mapping for small batches: a lone utterance
-// finishes soonest when its 16 sections are spread over lanes.  launch_stage() picks by batch size
-// (TRM_TUBE_MAPPING=sections|utterances overrides).  Both are checked against the same oracle.
+// Real = double : FP64 conformance mode (this file's cheaper forms, FMA contraction) or, with TRM_STRICT, the reference's
+//                 operations in the reference's order (that TU is compiled with -fmad=false).
+// Real = float  : FP32 fast mode: state/signal/coefficients FP32; parameter interpolation, pitch -> increment -> table
+//                 position, the glottal-closure decision rint(ax*tnDelta) and the noise MCG stay FP64 / integer
+//                 (SURVEY.md Appendix E).
 #pragma once
 
 #include <stdio.h>
 
-#include "tube_kernel.cuh"
+#include "tube_common.cuh"
 
 namespace TRM_KERNEL_NS {
 using namespace trm;
@@ -629,7 +634,7 @@ __device__ __forceinline__ void wide_recurrence_warp(WideSmem<R> &W, const WideA
 
 // =========================================================================================================
 // feed-forward warp: utterances 2*pair and 2*pair+1 of the group, lane = sample of a 16-sample block
-// (phases S0 / A1 / S1 / A2 of tube_kernel.cuh; the results go to the ring instead of the ladder's tables)
+// (phases S0 / A1 / S1 / A2; the results go to the ring)
 // =========================================================================================================
 template <typename R>
 __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const WideArgs &wargs, int g_start, int g_count, int n_blocks, int pair, int lane)

@@ -234,49 +234,6 @@ def test_synthesizer_adapter_and_file_outputs(tmp_path):
         assert np.array_equal(body.astype(np.int16), pcm)
 
 
-@pytest.mark.parametrize("precision", [2, 0, 1])
-def test_mappings_agree(precision, monkeypatch):
-    """The two waveguide mappings (lane-per-section / lane-per-utterance + feed-forward warps) compute the same path.
-    FP64 strict (reference order, no FMA contraction): identical bits everywhere -- tube-rate signal, output samples,
-    maxima, PCM.  FP64 conformance (the section kernel keeps the reference order with fused multiply-adds, the utterance
-    kernel uses the cheaper forms): within 1e-10 of peak.  FP32 fast mode: >= 100 dB between the mappings and PCM within
-    1 LSB.  Ragged lengths (utterances that end inside a 16-sample block, odd utterance count), mixed voices and rates."""
-    g = _g()
-    from gnuspeech_b200 import workloads as W
-    rng = np.random.default_rng(11)
-    n_frames = [int(x) for x in rng.integers(2, 260, 75)] + [1, 2, 301]
-    frames = W.random_walk_ragged(n_frames, seed=77)
-    voices = [dict(), dict(length=15.0), dict(length=10.0, temperature=32.0), dict(waveform=1), dict(usesModulation=0, lossFactor=1.5)]
-    ips = [g.TRMInputParameters(44100.0 if u % 3 else 22050.0, **voices[u % len(voices)]) for u in range(len(n_frames))]
-    out = {}
-    for mapping in ("sections", "utterances"):
-        monkeypatch.setenv("TRM_TUBE_MAPPING", mapping)
-        b, pcm, smp, tube = _run(ips, frames, n_frames, precision, want_tube=True)
-        out[mapping] = (b.numberSamples.copy(), b.maximumSampleValues.copy(), pcm, smp, tube, b.outOffsets.copy(),
-                        b.tubeOffsets.copy(), b.pcmOffsets.copy())
-    a, c = out["sections"], out["utterances"]
-    ns, oo, to, po = a[0], a[5], a[6], a[7]
-    assert np.array_equal(a[0], c[0])
-    if precision == g.TRM_PRECISION_FP64_STRICT:
-        assert np.array_equal(a[1], c[1]), "per-utterance maxima differ between the mappings"
-        assert np.array_equal(a[2], c[2]), "PCM differs between the mappings"
-    for u in range(len(n_frames)):
-        nt = (n_frames[u] - 1) * g.derive(ips[u], n_frames[u]).controlPeriod
-        ya, yc = a[3][oo[u]:oo[u] + ns[u]], c[3][oo[u]:oo[u] + ns[u]]
-        ta, tc = a[4][to[u]:to[u] + nt], c[4][to[u]:to[u] + nt]
-        if precision == g.TRM_PRECISION_FP64_STRICT:
-            assert np.array_equal(ya, yc), "output samples of utterance %d" % u
-            assert np.array_equal(ta, tc), "tube-rate signal of utterance %d" % u
-        elif precision == g.TRM_PRECISION_FP64:
-            if ns[u] and np.abs(ya).max() > 0:
-                assert np.abs(ya - yc).max() <= 1e-10 * np.abs(ya).max(), "utterance %d" % u
-        elif ns[u] and np.abs(ya).max() > 0:
-            assert O.snr_db(ya.astype(np.float64), yc.astype(np.float64)) >= 100.0, "utterance %d" % u
-            ch = 2 if ips[u].channels == 2 else 1
-            d = np.abs(a[2][po[u]:po[u] + ns[u] * ch].astype(np.int32) - c[2][po[u]:po[u] + ns[u] * ch].astype(np.int32))
-            assert d.max() <= 1, "utterance %d: PCM differs by %d LSB between the mappings" % (u, int(d.max()))
-
-
 def test_async_calls_overlap_and_match_blocking():
     """TRMBatchSynthesizeAsync / TRMBatchWait: two calls in flight on one device (two context lanes) return the same
     bytes as the blocking call, in any completion order; a ticket reports errors like the blocking call does."""

@@ -265,7 +265,7 @@ def test_frame_generator_restatement_properties():
 
 def test_known_divisor_division_is_ieee_division():
     """The kernels divide by 20, 12 and the tube sample rate with a multiply and two fused operations
-    (div_known(), tube_kernel.cuh); the result must be the IEEE quotient for the numerators the path produces."""
+    (div_known(), tube_common.cuh); the result must be the IEEE quotient for the numerators the path produces."""
     L = O.lib()
     cases = [(20.0, -60.0, 0.0),                  # amplitude(): (dB - 60) / 20
              (12.0, -30.0, 30.0),                 # frequency(): (pitch + 3) / 12

@@ -41,7 +41,7 @@ def main():
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], stdout=subprocess.PIPE, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     # a report may hold several kernels: keep the section whose "Kernel Name" row matches the demangled hint
-    hint = os.environ.get("NCU_KERNEL", "tube_kernel")
+    hint = os.environ.get("NCU_KERNEL", "tube_wide")
     starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
     for a, b in zip(starts[:-1], starts[1:]):
         if hint in rows[a][1]:
@@ -66,7 +66,7 @@ def main():
                 if os.path.exists(p):
                     src[fn] = open(p).read().splitlines()
     print("total instr/block %.0f" % (ti / B))
-    for (fn, ln), a in sorted(agg.items(), key=lambda kv: (kv[0][0] != "tube_kernel.cuh", kv[0][0], kv[0][1])):
+    for (fn, ln), a in sorted(agg.items(), key=lambda kv: (kv[0][0] != "tube_wide.cuh", kv[0][0], kv[0][1])):
         if a[0] / ti < 0.002:
             continue
         text = src[fn][ln - 1].strip()[:90] if fn in src and 0 < ln <= len(src[fn]) else ""

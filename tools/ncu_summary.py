@@ -33,7 +33,7 @@ def main():
             print("%-70s %-10s %s" % (n, u, v))
     rows = page(rep, "source")
     import os
-    hint = os.environ.get("NCU_KERNEL", "tube_kernel")
+    hint = os.environ.get("NCU_KERNEL", "tube_wide")
     starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
     for a, b in zip(starts[:-1], starts[1:]):
         if hint in rows[a][1]:
