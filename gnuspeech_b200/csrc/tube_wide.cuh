@@ -87,15 +87,6 @@ template <> struct Wide<double> {
     static constexpr int REGS_HI = DONORS ? (REGS_BASE + (DONORS * 32 * (REGS_BASE - REGS_DONOR) / 128) / 8 * 8) : 0;
 };
 constexpr int WIDE_SLOTS = 2;
-constexpr int WIDE_PARTS = 4;
-// FP64 conformance mode: the glottal FIR and the source mixing run in a warp of their own (warp 1, lane = utterance,
-// both oscillator windows in registers) instead of in the feed-forward warps, where every lane re-read 49 history
-// values from shared memory per sample -- 98 of a pair-block's ~340 shared-memory wavefronts, on the pipe that bounds
-// the kernel.  -DTRM_FIR_WARP=0 keeps the FIR in the feed-forward warps (as the strict and FP32 modes do).
-#ifndef TRM_FIR_WARP
-#define TRM_FIR_WARP 0
-#endif
-template <typename R> constexpr bool WIDE_FIRW = sizeof(R) == 8 && !STRICT && TRM_FIR_WARP != 0;
 // Warp w is scheduled by SM sub-partition w % 4, and the recurrence warp (warp 0) alone keeps its partition's FP64
 // pipe busy for ~2.6 feed-forward warps' worth of a block.  Warp WIDE_IDLE_WARP (same partition) therefore exits at
 // once and its pair moves to warp 15: partitions carry {recurrence + 2, 4, 4, 4} feed-forward warps instead of
@@ -109,9 +100,8 @@ struct alignas(16) FFHalf {
     unsigned long long mbar[2];
     double CST[12];                          // per-utterance constants of the feed-forward phases (global loads of the
                                              // descriptor inside the block loop sat on the warp's critical path)
-    double INC[WIDE_FIRW<R> ? 2 : TB]; // oscillator increments of the block (strict mode: every lane walks them)
-    R HE[WIDE_FIRW<R> ? 2 : FIR_HIST + TB], HO[WIDE_FIRW<R> ? 2 : FIR_HIST + TB];  // oscillator history, even / odd
-                                             // 2x-rate samples (with a FIR warp the history lives in that warp's registers)
+    double INC[TB];                          // oscillator increments of the block (conformance mode: every lane walks them)
+    R HE[FIR_HIST + TB], HO[FIR_HIST + TB];  // oscillator history, even / odd 2x-rate samples
     R pad[16 / sizeof(R)];                   // FP32: size = 64 mod 128 bytes, so the two utterances of a warp (adjacent
                                              // FFHalf's, 16 consecutive floats each) read disjoint bank halves
 };
@@ -122,13 +112,8 @@ struct WideSmem {
     typename Wide<R>::Unit ring[WIDE_SLOTS][Wide<R>::NF][TB][Wide<R>::UP];
     FFHalf<R> ff[2 * Wide<R>::MAX_PAIRS];
     alignas(16) R outb[32][Wide<R>::OUT_LD];
-    // full[slot][part]: samples 4 part .. 4 part + 3 of the slot's block are complete.  Only the FIR warp, which finishes
-    // a block sample by sample, signals the parts separately -- the recurrence warp starts a block after its first four
-    // samples instead of after all sixteen; without a FIR warp part 0 stands for the whole block.
-    unsigned long long full[WIDE_SLOTS][WIDE_PARTS], empty[WIDE_SLOTS], mid[WIDE_SLOTS];
-    double kc[(sizeof(R) == 8 && STRICT) ? 18 : 1][32];   // strict mode: per-utterance constants of the recurrence warp
-    // FIR warp: {even, odd} oscillator sample of every utterance-sample of a block, feed-forward warps -> FIR warp
-    typename Wide<R>::Unit heo[WIDE_FIRW<R> ? WIDE_SLOTS : 1][WIDE_FIRW<R> ? TB : 1][WIDE_FIRW<R> ? Wide<R>::UP : 1];
+    unsigned long long full[WIDE_SLOTS], empty[WIDE_SLOTS];
+    double kc[sizeof(R) == 8 ? 18 : 1][32];   // conformance mode: per-utterance constants of the recurrence warp
     long long n_tube[32];
     R *out_ptr[32];
     long long n_cta;
@@ -261,7 +246,7 @@ __device__ __forceinline__ void wide_recurrence_warp(WideSmem<R> &W, const WideA
 
             for (int blk = 0; blk < n_blocks; ++blk) {
                 const int slot = blk & 1;
-                mbar_wait_sleep<TRM_WAIT_FULL_NS>(&W.full[slot][0], (uint32_t)((blk >> 1) & 1));
+                mbar_wait_sleep<TRM_WAIT_FULL_NS>(&W.full[slot], (uint32_t)((blk >> 1) & 1));
 #pragma unroll 1
                 for (int s0 = 0; s0 < ((TRM_PROFILE_SKIP & 2) ? 0 : TB); s0 += 4) {
                   float yo[4];
@@ -403,7 +388,7 @@ __device__ __forceinline__ void wide_recurrence_warp(WideSmem<R> &W, const WideA
 
             for (int blk = 0; blk < n_blocks; ++blk) {
                 const int slot = blk & 1;
-                mbar_wait_sleep<TRM_WAIT_FULL_NS>(&W.full[slot][0], (uint32_t)((blk >> 1) & 1));
+                mbar_wait_sleep<TRM_WAIT_FULL_NS>(&W.full[slot], (uint32_t)((blk >> 1) & 1));
 #pragma unroll 1
                 for (int s0 = 0; s0 < ((TRM_PROFILE_SKIP & 2) ? 0 : TB); s0 += 2) {
                     double yo[2];
@@ -538,16 +523,9 @@ __device__ __forceinline__ void wide_recurrence_warp(WideSmem<R> &W, const WideA
 
             for (int blk = 0; blk < n_blocks; ++blk) {
                 const int slot = blk & 1;
-                if constexpr (!WIDE_FIRW<R>) mbar_wait_sleep<TRM_WAIT_FULL_NS>(&W.full[slot][0], (uint32_t)((blk >> 1) & 1));
-                if (TRM_PROFILE_SKIP & 2) {
-                    for (int part = 0; WIDE_FIRW<R> && part < WIDE_PARTS; ++part)
-                        mbar_wait_sleep<TRM_WAIT_FULL_NS>(&W.full[slot][part], (uint32_t)((blk >> 1) & 1));
-                }
+                mbar_wait_sleep<TRM_WAIT_FULL_NS>(&W.full[slot], (uint32_t)((blk >> 1) & 1));
 #pragma unroll 1
                 for (int s0 = 0; s0 < ((TRM_PROFILE_SKIP & 2) ? 0 : TB); s0 += 2) {
-                    if constexpr (WIDE_FIRW<R>) {
-                        if ((s0 & 3) == 0) mbar_wait_sleep<TRM_WAIT_FULL_NS>(&W.full[slot][s0 >> 2], (uint32_t)((blk >> 1) & 1));
-                    }
                     double yo[2];
 #pragma unroll
                     for (int si = 0; si < 2; ++si) {
@@ -663,7 +641,6 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
 {
     constexpr bool FAST = sizeof(R) == 4;                  // FP32 fast mode
     constexpr bool F64C = !FAST && !STRICT;                // FP64 conformance mode (cheaper forms, see the top of the file)
-    constexpr bool FIRW = WIDE_FIRW<R>;              // FIR and source mixing are the FIR warp's
     (void)F64C;
     const TubeArgs &args = wargs.t;
     const int half = lane >> 4, hl = lane & 15;
@@ -731,10 +708,8 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
         pos_fx = st_h[1];
         kb = st_h[2];
         fresh = st_h[3] != 0ull;
-        if constexpr (!FIRW) {
-            xm1 = st_v[STATE_XM]; xm2 = st_v[STATE_XM + 1];
-            for (int i = hl; i < FIR_HIST; i += TB) { S.HE[i] = st_v[STATE_HE + i]; S.HO[i] = st_v[STATE_HO + i]; }
-        }
+        xm1 = st_v[STATE_XM]; xm2 = st_v[STATE_XM + 1];
+        for (int i = hl; i < FIR_HIST; i += TB) { S.HE[i] = st_v[STATE_HE + i]; S.HO[i] = st_v[STATE_HO + i]; }
     }
     // FP64 conformance mode: parameter lane p also carries function p of its parameter as a complex number (rc, rs) that
     // is multiplied by (dc, ds) every sample -- geometric for the exponentials (rs = ds = 0), a rotation for the angles:
@@ -812,7 +787,7 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
         if (blk >= WIDE_SLOTS) mbar_wait_sleep<TRM_WAIT_NS>(&W.empty[slot], (uint32_t)(((blk >> 1) - 1) & 1));
         if (TRM_PROFILE_SKIP & 1) {
             __syncwarp(FULL);
-            if (lane == 0) mbar_arrive(FIRW ? &W.mid[slot] : &W.full[slot][0]);
+            if (lane == 0) mbar_arrive(&W.full[slot]);
             continue;
         }
 
@@ -1206,7 +1181,6 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
 
         TPH(5);
         // ---- A2: table look-ups, FIR, source mixing (TRMWavetable.m:174-195, m:305-337) --------------------------
-        R he_v, ho_v;                                       // this sample's even / odd oscillator value (2x rate)
         {
             if (!active) { p0 = 0.0; p1 = 0.0; }
             const double newDiv2 = (double)div2 - rint(ax_d * S.CST[C_TNDELTA]);
@@ -1223,8 +1197,8 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
                 const float w01 = table_value_fast(wt_base, hi0, div1, inv_div1, newDiv2, scale, pulse_wave);
                 const float w10 = table_value_fast(wt_base, lo1, div1, inv_div1, newDiv2, scale, pulse_wave);
                 const float w11 = table_value_fast(wt_base, hi1, div1, inv_div1, newDiv2, scale, pulse_wave);
-                he_v = w00 + ((float)(p0 - (double)lo0) * (w01 - w00));
-                ho_v = w10 + ((float)(p1 - (double)lo1) * (w11 - w10));
+                S.HE[FIR_HIST + hl] = w00 + ((float)(p0 - (double)lo0) * (w01 - w00));
+                S.HO[FIR_HIST + hl] = w10 + ((float)(p1 - (double)lo1) * (w11 - w10));
             } else {
                 const R scale = F64C ? (R)rcp_fast(Ld * Ld) : (R)(1.0 / (Ld * Ld));
                 if (F64C && pulse_wave) {
@@ -1241,32 +1215,18 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
                         return (di >= newDiv2) ? 0.0 : v;
                     };
                     const double w00 = value(lo0), w01 = value(hi0), w10 = value(lo1), w11 = value(hi1);
-                    he_v = fma(p0 - (double)lo0, w01 - w00, w00);
-                    ho_v = fma(p1 - (double)lo1, w11 - w10, w10);
+                    S.HE[FIR_HIST + hl] = fma(p0 - (double)lo0, w01 - w00, w00);
+                    S.HO[FIR_HIST + hl] = fma(p1 - (double)lo1, w11 - w10, w10);
                 } else {
                     R w0 = table_value<R>(wt_base, lo0, div1, div2, newDiv2, scale, pulse_wave);
                     R w1 = table_value<R>(wt_base, hi0, div1, div2, newDiv2, scale, pulse_wave);
-                    he_v = w0 + ((R)(p0 - (double)lo0) * (w1 - w0));
+                    S.HE[FIR_HIST + hl] = w0 + ((R)(p0 - (double)lo0) * (w1 - w0));
                     w0 = table_value<R>(wt_base, lo1, div1, div2, newDiv2, scale, pulse_wave);
                     w1 = table_value<R>(wt_base, hi1, div1, div2, newDiv2, scale, pulse_wave);
-                    ho_v = w0 + ((R)(p1 - (double)lo1) * (w1 - w0));
+                    S.HO[FIR_HIST + hl] = w0 + ((R)(p1 - (double)lo1) * (w1 - w0));
                 }
             }
         }
-        if constexpr (FIRW) {
-            // hand the sample to the FIR warp: oscillator pair, and in the record's last three words what the mixing
-            // needs (the FIR warp replaces them with the ladder's inputs; it derives alpha from the record's 2 beta)
-            W.heo[slot][hl][ucol] = make_double2(he_v, ho_v);
-            reinterpret_cast<double *>(&W.ring[slot][10][hl][ucol])[1] = lp_noise;
-            W.ring[slot][11][hl][ucol] = make_double2(ax, ah1);
-            (void)bp_alpha2;
-            __syncwarp(FULL);
-            TPH(6);
-            if (lane == 0) mbar_arrive(&W.mid[slot]);
-            TPH(8);
-        } else {
-        S.HE[FIR_HIST + hl] = he_v;
-        S.HO[FIR_HIST + hl] = ho_v;
         __syncwarp(FULL);
         TPH(6);
         R sig;
@@ -1326,7 +1286,7 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
         }
         __syncwarp(FULL);
         TPH(7);
-        if (lane == 0) mbar_arrive(&W.full[slot][0]);
+        if (lane == 0) mbar_arrive(&W.full[slot]);
         {
             // slide the oscillator history down by one block (rows TB.. -> 0..)
             const R e0 = S.HE[TB + hl], o0 = S.HO[TB + hl];
@@ -1338,7 +1298,6 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
         }
         __syncwarp(FULL);
         TPH(8);
-        }
     }
 #if TRM_PROFILE_PHASES
     if (tph_on)
@@ -1354,96 +1313,9 @@ __device__ __forceinline__ void wide_feed_forward_warp(WideSmem<R> &W, const Wid
             st_h[1] = pos_fx;
             st_h[2] = kb;
             st_h[3] = 0ull;
-            if constexpr (!FIRW) { st_v[STATE_XM] = xm1; st_v[STATE_XM + 1] = xm2; }
+            st_v[STATE_XM] = xm1; st_v[STATE_XM + 1] = xm2;
         }
-        if constexpr (!FIRW)
-            for (int i = hl; i < FIR_HIST; i += TB) { st_v[STATE_HE + i] = S.HE[i]; st_v[STATE_HO + i] = S.HO[i]; }
-    }
-}
-
-
-// =========================================================================================================
-// FIR warp (FP64 conformance mode, warp 1 of the CTA): lane = utterance
-// =========================================================================================================
-// Glottal FIR at twice the tube rate decimated by two (TRMWavetable.m:174-195 with TRMFIRFilter.m's 49 taps), then the
-// source mixing of TRMTubeModel.m:305-337.  The feed-forward warps deliver, per utterance-sample, the two oscillator
-// values and {lp_noise, ax, ah1} (in the record's last three words); this warp keeps both 25-value oscillator windows in
-// registers -- the sample loop is unrolled over the window positions, so every tap reads a fixed register -- and
-// overwrites those three words with the ladder's inputs {in, bp_ff, thr}.
-template <typename R>
-__device__ __forceinline__ void wide_fir_mix_warp(WideSmem<R> &W, const WideArgs &wargs, int g_start, int g_count, int n_blocks, int lane)
-{
-    static_assert(sizeof(R) == 8, "FP64 conformance mode only");
-    const TubeArgs &args = wargs.t;
-    const bool has = lane < g_count;
-    const int u = args.order ? args.order[g_start + (has ? lane : 0)] : g_start + (has ? lane : 0);
-    const trm_cuda_utterance *__restrict__ D = args.desc + u;
-    // lanes without an utterance work on the pad column, which nobody reads
-    const int col = lane < 2 * Wide<R>::MAX_PAIRS ? lane : 2 * Wide<R>::MAX_PAIRS;
-    const double bf = D->breathinessFactor, one_minus_bf = 1.0 - D->breathinessFactor;
-    const double cmix = D->crossmixFactor, ta0 = D->ta0;
-    const bool modulation = D->usesModulation != 0;
-    // Transposed form: instead of a window of the last 25 oscillator pairs (100 registers, and a sample loop unrolled
-    // over the window positions -- measured: ~50 KB of straight-line code, instruction-fetch bound) the warp keeps the
-    // partial sums of the next 24 outputs.  A[j] is the output j samples ahead; a new pair adds its two taps to each and
-    // the sums move down one place, which costs nothing because each is written to its new place by its own fma:
-    // 25 independent two-instruction chains per sample.
-    double A[FIR_HIST];
-#pragma unroll
-    for (int j = 0; j < FIR_HIST; ++j) A[j] = 0.0;
-    double xm1 = 0.0, xm2 = 0.0;
-    double *const st_v = (args.state && has) ? state_vals<double>(args.state, u) : nullptr;
-    if (st_v) {
-        // streaming: the 24 pending partial sums live where the other modes keep the even-sample history
-        xm1 = st_v[STATE_XM]; xm2 = st_v[STATE_XM + 1];
-#pragma unroll
-        for (int j = 0; j < FIR_HIST; ++j) A[j] = st_v[STATE_HE + j];
-    }
-    // pulse0[n] = sum_q c[2q] ho[n-q] + c[2q+1] he[n-q]  (TRMWavetable.m:174-195)
-    auto fir = [&](int slot, int t) -> double {
-        const double2 eo = W.heo[slot][t][col];
-        const double he = eo.x, ho = eo.y;
-        const double out = fma(he, FirCoef<double>::at(1), fma(ho, FirCoef<double>::at(0), A[0]));
-#pragma unroll
-        for (int j = 0; j < FIR_HIST - 1; ++j)
-            A[j] = fma(he, FirCoef<double>::at(2 * j + 3), fma(ho, FirCoef<double>::at(2 * j + 2), A[j + 1]));
-        A[FIR_HIST - 1] = ho * FirCoef<double>::at(2 * FIR_HIST);
-        return out;
-    };
-    // stage B: source mixing (TRMTubeModel.m:305-337); the ladder's inputs replace {lp_noise, ax, ah1} in the record
-    auto mix = [&](int slot, int t, double pulse0) {
-        const double2 q10 = W.ring[slot][10][t][col], q11 = W.ring[slot][11][t][col];
-        const double lp_noise = q10.y, ax = q11.x, ah1 = q11.y;
-        const double bp_alpha2 = 0.5 - 0.5 * q10.x;
-        const double pulsed_noise = lp_noise * pulse0;
-        const double pulse = ax * ((pulse0 * one_minus_bf) + (pulsed_noise * bf));
-        double crossmix = ax * cmix;
-        crossmix = (crossmix < 1.0) ? crossmix : 1.0;
-        const double mixed = (pulsed_noise * crossmix) + (lp_noise * (1.0 - crossmix));
-        const double sig = modulation ? mixed : lp_noise;
-        const double tube_in = (pulse + (ah1 * sig)) * 0.125;
-        const double thr_in = ta0 * (pulse * 0.125);
-        const double bp_ff = bp_alpha2 * (sig - xm2);       // band-pass feed-forward part alpha (x[n] - x[n-2])
-        xm2 = xm1; xm1 = sig;
-        reinterpret_cast<double *>(&W.ring[slot][10][t][col])[1] = tube_in;
-        W.ring[slot][11][t][col] = make_double2(bp_ff, thr_in);
-    };
-    for (int blk = 0; blk < n_blocks; ++blk) {
-        const int slot = blk & 1;
-        mbar_wait_sleep<TRM_WAIT_FULL_NS>(&W.mid[slot], (uint32_t)((blk >> 1) & 1));
-#pragma unroll 1
-        for (int part = 0; part < WIDE_PARTS; ++part) {
-#pragma unroll
-            for (int t = 0; t < TB / WIDE_PARTS; ++t) mix(slot, part * (TB / WIDE_PARTS) + t, fir(slot, part * (TB / WIDE_PARTS) + t));
-            __syncwarp(FULL);
-            if (lane == 0) mbar_arrive(&W.full[slot][part]);
-        }
-    }
-    if (st_v) {
-        // streaming calls cover whole 16-sample blocks
-#pragma unroll
-        for (int j = 0; j < FIR_HIST; ++j) st_v[STATE_HE + j] = A[j];
-        st_v[STATE_XM] = xm1; st_v[STATE_XM + 1] = xm2;
+        for (int i = hl; i < FIR_HIST; i += TB) { st_v[STATE_HE + i] = S.HE[i]; st_v[STATE_HO + i] = S.HO[i]; }
     }
 }
 
@@ -1464,18 +1336,12 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
         constexpr int NW = (int)(sizeof(W.ring) / 4);
         for (int i = threadIdx.x; i < NW; i += blockDim.x) w[i] = 0u;
         for (int h = warp; h < 2 * Wide<R>::MAX_PAIRS; h += blockDim.x >> 5) {
-            if constexpr (!WIDE_FIRW<R>) {
-                for (int i = lane; i < FIR_HIST + TB; i += 32) { W.ff[h].HE[i] = (R)0; W.ff[h].HO[i] = (R)0; }
-                if (lane < TB) W.ff[h].INC[lane] = 0.0;
-            }
+            for (int i = lane; i < FIR_HIST + TB; i += 32) { W.ff[h].HE[i] = (R)0; W.ff[h].HO[i] = (R)0; }
+            if (lane < TB) W.ff[h].INC[lane] = 0.0;
         }
         if (threadIdx.x == 0) {
             W.n_cta = 0;
-            for (int s = 0; s < WIDE_SLOTS; ++s) {
-                for (int part = 0; part < WIDE_PARTS; ++part) mbar_init(&W.full[s][part], WIDE_FIRW<R> ? 1u : (uint32_t)n_pairs);
-                mbar_init(&W.mid[s], (uint32_t)n_pairs);
-                mbar_init(&W.empty[s], 1);
-            }
+            for (int s = 0; s < WIDE_SLOTS; ++s) { mbar_init(&W.full[s], (uint32_t)n_pairs); mbar_init(&W.empty[s], 1); }
             mbar_fence_init();
         }
     }
@@ -1490,13 +1356,7 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
     }
     __syncthreads();
     const int64_t n_cta = W.n_cta;
-    // feed-forward warps: with a FIR warp, warps 2..15; else warps 1..15 without the idle one
-#if defined(TRM_P0_FREE)
-    // experiment: no feed-forward warp on the recurrence warp's SM sub-partition (11 pairs)
-    const int pair = warp < 2 ? -1 : ((warp & 3) == 0 ? 99 : warp - 2 - (warp >> 2));
-#else
-    const int pair = WIDE_FIRW<R> ? warp - 2 : warp - 1 - (warp > WIDE_IDLE_WARP ? 1 : 0);
-#endif
+    const int pair = warp - 1 - (warp > WIDE_IDLE_WARP ? 1 : 0);
     const int n_blocks = (int)((n_cta + TB - 1) / TB);
     // Register redistribution (setmaxnreg, warpgroup granularity; see Wide<double>).  Every warp of a warpgroup executes
     // the instruction, before any of them exits; the donors release before the recurrence warpgroup's request can be met.
@@ -1509,11 +1369,9 @@ __global__ void __launch_bounds__(Wide<R>::THREADS, 1) tube_wide_kernel(WideArgs
             asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Wide<R>::REGS_HI));
             if (n_cta <= 0 || pair >= n_pairs) return;
             if (warp == 0) wide_recurrence_warp<R>(W, wargs, g_start, g_count, n_blocks, lane);
-            else if (WIDE_FIRW<R> && warp == 1) {
-                if constexpr (WIDE_FIRW<R>) wide_fir_mix_warp<R>(W, wargs, g_start, g_count, n_blocks, lane);
-            } else wide_feed_forward_warp<R>(W, wargs, g_start, g_count, n_blocks, pair, lane);
+            else wide_feed_forward_warp<R>(W, wargs, g_start, g_count, n_blocks, pair, lane);
         } else {
-            if (n_cta <= 0 || (!WIDE_FIRW<R> && warp == WIDE_IDLE_WARP) || pair >= n_pairs) return;
+            if (n_cta <= 0 || warp == WIDE_IDLE_WARP || pair >= n_pairs) return;
             wide_feed_forward_warp<R>(W, wargs, g_start, g_count, n_blocks, pair, lane);
         }
     } else {
